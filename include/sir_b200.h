@@ -1,0 +1,131 @@
+/* sir_b200.h - C ABI of the B200-native speech-intent hot path (libsir_b200.so).
+ *
+ * The reference (avi2924/Speech-Intent-Recognizer) is pure Python: its "FFI" for this path is the set of
+ * Python call sites that hand tensors to torchaudio / torch.nn.  Each entry point below names the reference
+ * interface it stands in for (file:line under /root/reference).  The Python mirror of the reference classes
+ * (speech-intent-recognizer_b200/scripts/*.py, models/models.py) binds these symbols with ctypes - see
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer prefixed d_ is a DEVICE pointer owned by the caller (PyTorch allocates all tensors);
+ *     the library owns only its handles (device constants, repacked weights, workspace);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it, nothing
+ *     synchronises with the host except handle creation, weight upload and workspace growth;
+ *   - return value 0 = success, negative = error; sir_last_error() returns a thread-local message;
+ *   - a handle is bound to the device that was current when it was created and is not thread-safe;
+ *   - there is NO CPU fallback: every compute entry fails with SIR_ERR_CUDA if no CUDA device is usable.
+ */
+#ifndef SIR_B200_H
+#define SIR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIR_OK 0
+#define SIR_ERR_INVALID (-1)   /* bad argument (message says which) */
+#define SIR_ERR_CUDA (-2)      /* CUDA runtime error (message carries cudaGetErrorString) */
+#define SIR_ERR_UNSUPPORTED (-3)
+
+/* output selector of sir_frontend_forward */
+#define SIR_OUT_MEL_POWER 0    /* MelSpectrogram only                    (mel_transform attribute)          */
+#define SIR_OUT_MEL_DB 1       /* + AmplitudeToDB                        (amplitude_to_db(mel_transform(w))) */
+#define SIR_OUT_LOGMEL_NORM 2  /* + per-utterance (x-mean)/(std+1e-5)    (extract_features)                  */
+
+typedef struct sir_frontend sir_frontend;
+typedef struct sir_model sir_model;
+
+const char* sir_last_error(void);
+int sir_version(void);
+/* Number of kernels this library has launched in the calling process (bench.py "gpu_launches"). */
+int64_t sir_launch_count(void);
+
+/* ---- feature frontend ---------------------------------------------------------------------------------
+ * sir_frontend_create  <->  AudioFeatureExtractor.__init__        scripts/precompute_features.py:21-36
+ *                           (and the transform construction in    scripts/dataset.py:59-66)
+ * Builds the periodic Hann window, FFT twiddles and the sparse HTK mel filterbank on the device.
+ * Only n_fft = 1024, hop_length = 512 (every reference call site) and n_mels <= 128 are implemented;
+ * anything else returns SIR_ERR_UNSUPPORTED.
+ */
+int sir_frontend_create(sir_frontend** out, int sample_rate, int n_mels, int n_fft, int hop_length);
+void sir_frontend_destroy(sir_frontend* fe);
+
+/* sir_frontend_forward  <->  the body of AudioFeatureExtractor.extract_features
+ *                            scripts/precompute_features.py:59-73 (truncate, mel, dB, normalise),
+ *                            its twins scripts/dataset.py:138-152 and scripts/test_model.py:78-94,
+ *                            fused with SpecAugment masking (scripts/dataset.py:160-176 ==
+ *                            scripts/augment.py:137-165) and pad/trim to a fixed frame count
+ *                            (scripts/dataset.py:109-113, scripts/train.py:58-62), for a whole batch.
+ *
+ *   d_wave       [batch] rows of fp32 mono samples, row b starts at d_wave + b * wave_stride
+ *   d_lengths    [batch] valid samples per row, or NULL (all rows have n_samples)
+ *   n_samples    row capacity (>= every length)
+ *   max_samples  truncate every utterance to this many samples first (int(max_duration*sr)); <= 0: none
+ *   mode         SIR_OUT_*
+ *   out_frames   time extent of the output rows.  Utterance b has T_b = 1 + L_b / 512 frames; frames
+ *                beyond out_frames are dropped AFTER they took part in the normalisation statistics,
+ *                missing frames are written as 0.0
+ *   d_out        [batch, n_mels, out_frames] fp32
+ *   d_masks      NULL or [batch, 4] int32 (t_start, t_end, f_start, f_end): bands of the UNPADDED feature
+ *                map set to 0.0 after normalisation (only with SIR_OUT_LOGMEL_NORM)
+ *   d_status     NULL or [batch] int32: 0 ok, 1 = utterance has <= n_fft/2 samples (reflect padding is
+ *                undefined; the reference raises and returns None / zeros) -> row written as zeros
+ */
+int sir_frontend_forward(sir_frontend* fe, const float* d_wave, int64_t wave_stride, const int32_t* d_lengths,
+                         int n_samples, int batch, int max_samples, int mode, int out_frames, float* d_out,
+                         const int32_t* d_masks, int32_t* d_status, void* stream);
+
+/* sir_amplitude_to_db  <->  AudioFeatureExtractor.amplitude_to_db  scripts/precompute_features.py:36,67
+ * 10*log10(max(x, 1e-10)) elementwise over n values (in place allowed). */
+int sir_amplitude_to_db(const float* d_in, float* d_out, int64_t n, void* stream);
+
+/* sir_specaugment_sample  <->  the random draws of FSCIntentDataset.__getitem__/augment_features
+ *                              scripts/dataset.py:105,166-171 and torchaudio mask_along_axis.
+ * Counter-based Philox4x32-10 keyed on (seed, first_index + b): reproducible and independent of batch
+ * split.  Writes [batch,4] int32 band parameters (empty bands where the gates say "no mask").
+ *   d_frames   NULL or [batch] valid frame count per utterance (else n_frames for all)
+ */
+int sir_specaugment_sample(uint64_t seed, uint64_t first_index, int batch, int n_mels, int n_frames,
+                           const int32_t* d_frames, float augment_prob, int time_mask_param,
+                           int freq_mask_param, int32_t* d_masks, void* stream);
+
+/* sir_features_finalize  <->  FSCIntentDataset.__getitem__ tail + collate_fn on CACHED features
+ *                             scripts/dataset.py:105-113, scripts/train.py:49-70
+ * Masks (optional) applied on the valid frames, then pad/trim from in_frames to out_frames. */
+int sir_features_finalize(const float* d_in, int batch, int n_mels, int in_frames, const int32_t* d_frames,
+                          const int32_t* d_masks, int out_frames, float* d_out, void* stream);
+
+/* ---- classifier ---------------------------------------------------------------------------------------
+ * sir_model_create  <->  CNNAudioGRU.__init__                      models/models.py:6-39
+ * n_mels must be a multiple of 8 (GRU input = 128 * n_mels / 8; the reference hard-codes 1024 = 64 mels).
+ */
+int sir_model_create(sir_model** out, int num_classes, int n_mels);
+void sir_model_destroy(sir_model* m);
+
+/* sir_model_load_weights  <->  nn.Module.load_state_dict          scripts/evaluate.py:48, test_model.py:42
+ * `weights` is ONE contiguous fp32 buffer (host or device pointer) holding the state_dict tensors in the
+ * order of speech-intent-recognizer_b200/utils/synth.py:state_dict_spec (conv/bn 1..3, gru l0, l0_reverse,
+ * l1, l1_reverse as weight_ih, weight_hh, bias_ih, bias_hh, attention, fc).  BatchNorm is folded for
+ * inference (eval mode, eps = bn_eps).  Synchronises the stream. */
+int sir_model_load_weights(sir_model* m, const float* weights, int64_t count, float bn_eps, void* stream);
+int64_t sir_model_weight_count(const sir_model* m);
+
+/* sir_model_forward  <->  CNNAudioGRU.forward (eval)              models/models.py:41-68
+ *   d_features [batch, n_mels, n_frames] fp32 (the [B,1,n_mels,T] form has the same memory layout)
+ *   d_logits   [batch, num_classes] fp32
+ * n_frames >= 8. */
+int sir_model_forward(sir_model* m, const float* d_features, int batch, int n_frames, float* d_logits,
+                      void* stream);
+
+/* sir_pipeline_forward: frontend (SIR_OUT_LOGMEL_NORM, pad/trim to out_frames) + classifier in one call.
+ * d_features may be NULL (features then live only in the model's workspace). */
+int sir_pipeline_forward(sir_frontend* fe, sir_model* m, const float* d_wave, int64_t wave_stride,
+                         const int32_t* d_lengths, int n_samples, int batch, int max_samples, int out_frames,
+                         float* d_features, float* d_logits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIR_B200_H */

@@ -1,0 +1,210 @@
+"""ctypes binding of libsir_b200.so (include/sir_b200.h) - the only door from Python to the CUDA kernels.
+
+There is deliberately no fallback: if the shared library is missing or no CUDA device is usable, every
+compute call raises.  PyTorch is used for device memory and streams only; raw device pointers and the
+current stream handle cross the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsir_b200.so")
+
+OUT_MEL_POWER, OUT_MEL_DB, OUT_LOGMEL_NORM = 0, 1, 2
+
+# symbol -> (restype, argtypes); mirrors include/sir_b200.h one to one (tests/test_abi_cpu.py checks it)
+SIGNATURES = {
+    "sir_last_error": (c_char_p, []),
+    "sir_version": (c_int, []),
+    "sir_launch_count": (c_int64, []),
+    "sir_frontend_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int]),
+    "sir_frontend_destroy": (None, [c_void_p]),
+    "sir_frontend_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sir_amplitude_to_db": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "sir_specaugment_sample": (c_int, [c_uint64, c_uint64, c_int, c_int, c_int, c_void_p, c_float, c_int, c_int,
+                                       c_void_p, c_void_p]),
+    "sir_features_finalize": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "sir_model_create": (c_int, [POINTER(c_void_p), c_int, c_int]),
+    "sir_model_destroy": (None, [c_void_p]),
+    "sir_model_load_weights": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+    "sir_model_weight_count": (c_int64, [c_void_p]),
+    "sir_model_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "sir_pipeline_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen the extension once.  Raises NativeError (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(f"{LIB_PATH} is missing - build it with `python speech-intent-recognizer_b200/build.py` "
+                              "(there is no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise NativeError(f"{what} failed ({rc}): {load_library().sir_last_error().decode()}")
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype=torch.float32):
+    if not t.is_cuda:
+        raise NativeError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise NativeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(load_library().sir_launch_count())
+
+
+class Frontend:
+    """Owns a ``sir_frontend`` handle on the current CUDA device."""
+
+    def __init__(self, sample_rate=16000, n_mels=64, n_fft=1024, hop_length=512):
+        lib = load_library()
+        if not torch.cuda.is_available():
+            raise NativeError("no CUDA device: the feature frontend has no CPU path")
+        h = c_void_p()
+        check(lib.sir_frontend_create(ctypes.byref(h), sample_rate, n_mels, n_fft, hop_length), "sir_frontend_create")
+        self._h = h
+        self.n_mels, self.hop = n_mels, hop_length
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and _lib is not None:
+            _lib.sir_frontend_destroy(h)
+
+    def forward(self, wave, lengths=None, max_samples=0, mode=OUT_LOGMEL_NORM, out_frames=None, masks=None,
+                status=None, out=None):
+        """wave [B, L] fp32 CUDA (rows may be strided) -> [B, n_mels, out_frames] fp32 CUDA."""
+        require_cuda(wave, "wave")
+        if wave.dim() != 2 or wave.stride(1) != 1:
+            raise NativeError("wave must be [batch, samples] with contiguous rows")
+        B, L = wave.shape
+        if lengths is not None:
+            require_cuda(lengths, "lengths", torch.int32)
+        if out_frames is None:
+            eff = min(L, max_samples) if max_samples and max_samples > 0 else L
+            out_frames = 1 + eff // self.hop
+        if out is None:
+            out = torch.empty((B, self.n_mels, out_frames), device=wave.device, dtype=torch.float32)
+        else:
+            require_cuda(out, "out")
+            assert out.is_contiguous() and tuple(out.shape) == (B, self.n_mels, out_frames)
+        if masks is not None:
+            require_cuda(masks, "masks", torch.int32)
+            assert masks.is_contiguous() and tuple(masks.shape) == (B, 4)
+        if status is not None:
+            require_cuda(status, "status", torch.int32)
+        stride = wave.stride(0) if B > 1 else max(L, 1)
+        check(load_library().sir_frontend_forward(self._h, ptr(wave), stride, ptr(lengths), L, B, int(max_samples or 0),
+                                                  mode, out_frames, ptr(out), ptr(masks), ptr(status), stream_ptr()),
+              "sir_frontend_forward")
+        return out
+
+
+def amplitude_to_db(x: torch.Tensor) -> torch.Tensor:
+    require_cuda(x, "x")
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    check(load_library().sir_amplitude_to_db(ptr(x), ptr(out), x.numel(), stream_ptr()), "sir_amplitude_to_db")
+    return out
+
+
+def specaugment_sample(seed, first_index, batch, n_mels, n_frames, frames=None, augment_prob=1.0, time_mask_param=20,
+                       freq_mask_param=10, device="cuda"):
+    masks = torch.empty((batch, 4), device=device, dtype=torch.int32)
+    if frames is not None:
+        require_cuda(frames, "frames", torch.int32)
+    check(load_library().sir_specaugment_sample(int(seed), int(first_index), batch, n_mels, n_frames, ptr(frames),
+                                                float(augment_prob), time_mask_param, freq_mask_param, ptr(masks),
+                                                stream_ptr()), "sir_specaugment_sample")
+    return masks
+
+
+def features_finalize(feat, out_frames, frames=None, masks=None):
+    require_cuda(feat, "feat")
+    feat = feat.contiguous()
+    B, M, T = feat.shape
+    out = torch.empty((B, M, out_frames), device=feat.device, dtype=torch.float32)
+    check(load_library().sir_features_finalize(ptr(feat), B, M, T, ptr(frames), ptr(masks), out_frames, ptr(out),
+                                               stream_ptr()), "sir_features_finalize")
+    return out
+
+
+class Model:
+    """Owns a ``sir_model`` handle (repacked weights + activation workspace)."""
+
+    def __init__(self, num_classes, n_mels=64):
+        lib = load_library()
+        if not torch.cuda.is_available():
+            raise NativeError("no CUDA device: the classifier has no CPU path")
+        h = c_void_p()
+        check(lib.sir_model_create(ctypes.byref(h), num_classes, n_mels), "sir_model_create")
+        self._h = h
+        self.num_classes, self.n_mels = num_classes, n_mels
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and _lib is not None:
+            _lib.sir_model_destroy(h)
+
+    def weight_count(self) -> int:
+        return int(load_library().sir_model_weight_count(self._h))
+
+    def load_weights(self, flat: torch.Tensor, bn_eps: float = 1e-5):
+        """flat: contiguous fp32 tensor (CPU or CUDA) in utils/synth.py:state_dict_spec order."""
+        flat = flat.detach().contiguous()
+        assert flat.dtype == torch.float32
+        check(load_library().sir_model_load_weights(self._h, ptr(flat), flat.numel(), bn_eps, stream_ptr()),
+              "sir_model_load_weights")
+
+    def forward(self, feat: torch.Tensor) -> torch.Tensor:
+        require_cuda(feat, "features")
+        feat = feat.contiguous()
+        B, M, T = feat.shape
+        logits = torch.empty((B, self.num_classes), device=feat.device, dtype=torch.float32)
+        check(load_library().sir_model_forward(self._h, ptr(feat), B, T, ptr(logits), stream_ptr()), "sir_model_forward")
+        return logits
+
+    def pipeline(self, fe: Frontend, wave, lengths=None, max_samples=0, out_frames=200, features=None):
+        require_cuda(wave, "wave")
+        B, L = wave.shape
+        if features is None:
+            features = torch.empty((B, self.n_mels, out_frames), device=wave.device, dtype=torch.float32)
+        logits = torch.empty((B, self.num_classes), device=wave.device, dtype=torch.float32)
+        stride = wave.stride(0) if B > 1 else max(L, 1)
+        check(load_library().sir_pipeline_forward(fe._h, self._h, ptr(wave), stride, ptr(lengths), L, B,
+                                                  int(max_samples or 0), out_frames, ptr(features), ptr(logits),
+                                                  stream_ptr()), "sir_pipeline_forward")
+        return logits, features

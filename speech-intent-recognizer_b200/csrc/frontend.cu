@@ -1,0 +1,554 @@
+// Fused log-mel frontend for sm_100a: waveform -> reflect-padded framing -> Hann -> 1024-point real FFT ->
+// |X|^2 -> sparse HTK mel -> 10 log10 -> per-utterance (x-mean)/(std+1e-5) -> SpecAugment bands -> pad/trim.
+//
+// Replaces (per utterance) scripts/precompute_features.py:59-73, scripts/dataset.py:105-113,160-176 of the
+// reference and the torchaudio calls behind them with ONE kernel launch for a batch.
+//
+// Mapping
+//   * one thread-block CLUSTER per utterance (1, 2, 4 or 8 CTAs, picked so the grid covers the 148 SMs a
+//     few times over even for small batches); the cluster's CTAs take 8-frame groups round-robin;
+//   * a CTA (4 warps) stages the 9 hop-blocks (4608 samples) its 8 frames need into shared memory with
+//     128-bit streaming loads - every sample is fetched from HBM once per group, reflect padding is resolved
+//     while staging;
+//   * each HALF-WARP owns one frame: 512-point complex FFT as 32-point x 16-point register FFTs with one
+//     shared-memory transposition (logmel_frame.cuh), real-FFT post-pass, power, sparse mel taps, log10;
+//   * un-normalised values go to the output through an 8-frame shared tile (32-byte row segments), the
+//     per-utterance mean / unbiased std are combined across the cluster through distributed shared memory
+//     (shifted sums + Chan's merge), then each CTA re-reads its own L2-resident values, normalises, applies
+//     the mask bands and writes the zero padding.  HBM sees each sample once and each feature once.
+//
+// Roofline: HBM-bound by intent (4 L + 4 n_mels T bytes per utterance), but at ~19 k fp32 instructions per
+// frame the kernel sits at the fp32-issue ridge; see DESIGN.md for the arithmetic.
+#include <cooperative_groups.h>
+
+#include <vector>
+
+#include "frontend_tables.h"
+#include "logmel_frame.cuh"
+#include "sir_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace sir {
+
+thread_local char g_error[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+constexpr int kFeWarps = 4;
+constexpr int kFeThreads = kFeWarps * 32;
+constexpr int kGroupFrames = 2 * kFeWarps;                 // one frame per half-warp
+constexpr int kStageFloats = (kGroupFrames + 1) * kHop;    // 9 hop blocks
+constexpr int kTileStride = kGroupFrames + 1;              // padded to dodge bank conflicts
+constexpr int kMelWeightCap = 1280;
+
+// shared-memory carve-up (float offsets)
+constexpr int kOffWindow = 0;
+constexpr int kOffTw512 = kOffWindow + 1024;
+constexpr int kOffTw1024 = kOffTw512 + 1024;
+constexpr int kOffMelStart = kOffTw1024 + 516;
+constexpr int kOffMelCount = kOffMelStart + kMaxMels;
+constexpr int kOffMelOffset = kOffMelCount + kMaxMels;
+constexpr int kOffMelWeight = kOffMelOffset + kMaxMels;
+constexpr int kOffStage = kOffMelWeight + kMelWeightCap;
+constexpr int kOffScratch = kOffStage + kStageFloats;
+constexpr int kOffTile = kOffScratch + kGroupFrames * kFrameScratch;
+constexpr int kOffReduce = kOffTile + kMaxMels * kTileStride;
+constexpr int kFeSmemFloats = kOffReduce + 64;
+constexpr size_t kFeSmemBytes = (size_t)kFeSmemFloats * sizeof(float);
+static_assert(kOffStage % 4 == 0 && kOffScratch % 4 == 0, "16-byte alignment of vector regions");
+static_assert(3 * (kFeSmemBytes + 1024) <= 232448, "three CTAs per SM");
+
+struct FrontendParams {
+    const float* wave;
+    int64_t wave_stride;
+    const int32_t* lengths;
+    int n_samples;
+    int max_samples;
+    int n_mels;
+    int mode;
+    int out_frames;
+    float* out;
+    const int32_t* masks;
+    int32_t* status;
+    FrontendTables tables;
+    int mel_weight_count;
+};
+
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kFeThreads, 3) logmel_frontend_kernel(const FrontendParams p) {
+    extern __shared__ __align__(16) float smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = (int)cluster.num_blocks();
+    const int crank = (int)cluster.block_rank();
+    const int b = blockIdx.x / csize;
+    const int tid = threadIdx.x;
+
+    // ---- constants into shared memory ------------------------------------------------------------------
+    for (int i = tid; i < 1024; i += kFeThreads) {
+        smem[kOffWindow + i] = p.tables.window[i];
+        smem[kOffTw512 + i] = p.tables.tw512[i];
+    }
+    for (int i = tid; i < 514; i += kFeThreads) smem[kOffTw1024 + i] = p.tables.tw1024[i];
+    int* s_mel_start = reinterpret_cast<int*>(smem + kOffMelStart);
+    int* s_mel_count = reinterpret_cast<int*>(smem + kOffMelCount);
+    int* s_mel_offset = reinterpret_cast<int*>(smem + kOffMelOffset);
+    for (int i = tid; i < p.n_mels; i += kFeThreads) {
+        s_mel_start[i] = p.tables.mel_start[i];
+        s_mel_count[i] = p.tables.mel_count[i];
+        s_mel_offset[i] = p.tables.mel_offset[i];
+    }
+    for (int i = tid; i < p.mel_weight_count; i += kFeThreads) smem[kOffMelWeight + i] = p.tables.mel_weight[i];
+    const FrontendTables st{smem + kOffWindow, smem + kOffTw512, smem + kOffTw1024, s_mel_start,
+                            s_mel_count,       s_mel_offset,     smem + kOffMelWeight};
+
+    // ---- this utterance --------------------------------------------------------------------------------
+    int L = p.lengths ? min(p.lengths[b], p.n_samples) : p.n_samples;
+    if (p.max_samples > 0) L = min(L, p.max_samples);
+    const bool valid = L > kNfft / 2;                       // reflect padding needs L > 512
+    const int T = valid ? 1 + L / kHop : 0;
+    const int n_groups = (T + kGroupFrames - 1) / kGroupFrames;
+    const float* __restrict__ row = p.wave + (int64_t)b * p.wave_stride;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
+    float* __restrict__ out = p.out + (int64_t)b * p.n_mels * p.out_frames;
+    const bool out_vec = (p.out_frames % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+    if (p.status && crank == 0 && tid == 0) p.status[b] = valid ? 0 : 1;
+
+    float* stage = smem + kOffStage;
+    float* tile = smem + kOffTile;
+    float* red = smem + kOffReduce;
+    const int lane = tid & 31, warp = tid >> 5, half = lane >> 4, q = lane & 15;
+    const int slot = 2 * warp + half;
+    float* scr = smem + kOffScratch + slot * kFrameScratch;
+
+    float shift = 0.f, s1 = 0.f, s2 = 0.f;
+    bool have_shift = false;
+
+    for (int g = crank; g < n_groups; g += csize) {
+        const int t0 = g * kGroupFrames;
+        __syncthreads();                                    // previous group's stage/tile fully consumed
+        // stage padded samples [512 t0, 512 t0 + 4608): padded index pp <-> original index pp - 512
+        for (int q4 = tid; q4 < kStageFloats / 4; q4 += kFeThreads) {
+            const int i = t0 * kHop + 4 * q4 - kNfft / 2;
+            float4 v;
+            if (vec_ok && i >= 0 && i + 3 < L) {
+                v = ld_stream_f4(row + i);
+            } else {
+                float e[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int ii = i + u;
+                    const int r = ii < 0 ? -ii : (ii >= L ? 2 * (L - 1) - ii : ii);
+                    e[u] = (r >= 0 && r < L) ? __ldg(row + r) : 0.f;
+                }
+                v = make_float4(e[0], e[1], e[2], e[3]);
+            }
+            reinterpret_cast<float4*>(stage)[q4] = v;
+        }
+        __syncthreads();
+
+        const bool active = (t0 + slot) < T;
+        if (active) frame_phase_a(q, stage + slot * kHop, st.window, st.tw512, scr, scr + 16 * kRowPad);
+        __syncwarp();
+        {
+            PhaseBRegs rb;
+            if (active) frame_phase_b_load(q, scr, scr + 16 * kRowPad, rb);
+            __syncwarp();
+            if (active) frame_phase_b_store(q, rb, scr);
+        }
+        __syncwarp();
+        {
+            PhaseCRegs rc;
+            if (active) frame_phase_c_compute(q, scr, st.tw1024, rc);
+            __syncwarp();
+            if (active) frame_phase_c_store(q, rc, scr);
+        }
+        __syncwarp();
+        if (active) {
+            for (int j = 0; 16 * j < p.n_mels; ++j) {
+                const int m = mel_of_lane(q, j);
+                if (m < p.n_mels) {
+                    float v = mel_band_power(m, scr, st);
+                    if (p.mode != SIR_OUT_MEL_POWER) v = 10.0f * log10f(fmaxf(v, 1e-10f));
+                    tile[m * kTileStride + slot] = v;
+                }
+            }
+        }
+        __syncthreads();
+
+        // tile -> global (8 consecutive frames of one mel row = one 32-byte segment) + statistics
+        if (!have_shift) {
+            shift = tile[0];
+            have_shift = true;
+        }
+        const int nslots = min(kGroupFrames, T - t0);
+        if (out_vec && nslots == kGroupFrames && t0 + kGroupFrames <= p.out_frames) {
+            for (int idx = tid; idx < p.n_mels * 2; idx += kFeThreads) {
+                const int m = idx >> 1, h4 = (idx & 1) * 4;
+                const float* tp = tile + m * kTileStride + h4;
+                const float4 v = make_float4(tp[0], tp[1], tp[2], tp[3]);
+                *reinterpret_cast<float4*>(out + (int64_t)m * p.out_frames + t0 + h4) = v;
+                const float d0 = v.x - shift, d1 = v.y - shift, d2 = v.z - shift, d3 = v.w - shift;
+                s1 += (d0 + d1) + (d2 + d3);
+                s2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+            }
+        } else {
+            for (int idx = tid; idx < p.n_mels * kGroupFrames; idx += kFeThreads) {
+                const int m = idx >> 3, s = idx & 7;
+                if (s < nslots) {
+                    const float v = tile[m * kTileStride + s];
+                    if (t0 + s < p.out_frames) out[(int64_t)m * p.out_frames + t0 + s] = v;
+                    const float d = v - shift;
+                    s1 += d;
+                    s2 += d * d;
+                }
+            }
+        }
+    }
+
+    if (p.mode != SIR_OUT_LOGMEL_NORM || !valid) {
+        // zero padding (and whole rows of invalid utterances); rows are split over the cluster
+        const int first = valid ? min(T, p.out_frames) : 0;
+        for (int m = crank; m < p.n_mels; m += csize)
+            for (int t = first + tid; t < p.out_frames; t += kFeThreads) out[(int64_t)m * p.out_frames + t] = 0.f;
+        return;                                             // uniform over the whole cluster
+    }
+
+    // ---- per-utterance statistics: CTA partial (n, mean, M2) -> cluster merge over DSMEM ----------------
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    __syncthreads();
+    if (lane == 0) {
+        red[warp] = s1;
+        red[8 + warp] = s2;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int my_frames = 0;
+        for (int g = crank; g < n_groups; g += csize) my_frames += min(kGroupFrames, T - g * kGroupFrames);
+        const double n = (double)my_frames * (double)p.n_mels;
+        double S1 = 0, S2 = 0;
+        for (int w = 0; w < kFeWarps; ++w) {
+            S1 += (double)red[w];
+            S2 += (double)red[8 + w];
+        }
+        double mean = 0, m2 = 0;
+        if (n > 0) {
+            mean = (double)shift + S1 / n;
+            m2 = fmax(S2 - S1 * S1 / n, 0.0);
+        }
+        double* part = reinterpret_cast<double*>(red + 16);
+        part[0] = n;
+        part[1] = mean;
+        part[2] = m2;
+    }
+    cluster.sync();
+    {
+        double n = 0, mean = 0, m2 = 0;                     // every thread merges in rank order: deterministic
+        for (int r = 0; r < csize; ++r) {
+            const double* part = reinterpret_cast<const double*>(cluster.map_shared_rank(red + 16, r));
+            const double nb = part[0], mb = part[1], m2b = part[2];
+            if (nb > 0) {
+                const double nt = n + nb, delta = mb - mean;
+                mean += delta * nb / nt;
+                m2 += m2b + delta * delta * n * nb / nt;
+                n = nt;
+            }
+        }
+        const float fmean = (float)mean;
+        const float inv = (float)(1.0 / (sqrt(m2 / (n - 1.0)) + 1e-5));
+        int mt0 = 0, mt1 = 0, mf0 = 0, mf1 = 0;
+        if (p.masks) {
+            mt0 = p.masks[4 * b + 0];
+            mt1 = p.masks[4 * b + 1];
+            mf0 = p.masks[4 * b + 2];
+            mf1 = p.masks[4 * b + 3];
+        }
+        // normalise this CTA's own frames (still L2-resident; ld.cg so no stale L1 line is read)
+        for (int g = crank; g < n_groups; g += csize) {
+            const int t0 = g * kGroupFrames;
+            const int nslots = min(min(kGroupFrames, T - t0), p.out_frames - t0);
+            for (int idx = tid; idx < p.n_mels * kGroupFrames; idx += kFeThreads) {
+                const int m = idx >> 3, s = idx & 7;
+                if (s < nslots) {
+                    float* addr = out + (int64_t)m * p.out_frames + t0 + s;
+                    float v = (__ldcg(addr) - fmean) * inv;
+                    const int t = t0 + s;
+                    if ((t >= mt0 && t < mt1) || (m >= mf0 && m < mf1)) v = 0.f;
+                    *addr = v;
+                }
+            }
+        }
+        for (int m = crank; m < p.n_mels; m += csize)
+            for (int t = T + tid; t < p.out_frames; t += kFeThreads) out[(int64_t)m * p.out_frames + t] = 0.f;
+    }
+    cluster.sync();                                         // keep every CTA's shared memory alive for its peers
+}
+
+// ---- small companions ----------------------------------------------------------------------------------
+__global__ void amplitude_to_db_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = 10.0f * log10f(fmaxf(in[i], 1e-10f));
+}
+
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0;
+    c[1] = n1;
+    c[2] = n2;
+    c[3] = n3;
+}
+
+__device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t index, uint32_t block, uint32_t (&c)[4]) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    c[0] = (uint32_t)index;
+    c[1] = (uint32_t)(index >> 32);
+    c[2] = block;
+    c[3] = 0u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// One thread per utterance: the draws of scripts/dataset.py:105,166-171 + torchaudio mask_along_axis.
+__global__ void specaugment_sample_kernel(uint64_t seed, uint64_t first_index, int batch, int n_mels, int n_frames,
+                                          const int32_t* __restrict__ frames, float augment_prob, int tparam,
+                                          int fparam, int32_t* __restrict__ masks) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    uint32_t a[4], c[4];
+    philox4x32_10(seed, first_index + (uint64_t)b, 0u, a);
+    philox4x32_10(seed, first_index + (uint64_t)b, 1u, c);
+    const float gate_aug = u01(a[0]);
+    const float u[6] = {u01(a[1]), u01(a[2]), u01(a[3]), u01(c[0]), u01(c[1]), u01(c[2])};
+    const int T = frames ? frames[b] : n_frames;
+    int m[4] = {0, 0, 0, 0};
+    if (gate_aug < augment_prob) {
+        const int param[2] = {tparam, fparam};
+        const int size[2] = {T, n_mels};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (u[3 * k] < 0.5f && param[k] >= 1) {
+                const float value = __fmul_rn(u[3 * k + 1], (float)param[k]);
+                const float min_value = __fmul_rn(u[3 * k + 2], __fsub_rn((float)size[k], value));
+                const int start = (int)min_value;
+                m[2 * k] = start;
+                m[2 * k + 1] = start + (int)value;
+            }
+        }
+    }
+    reinterpret_cast<int4*>(masks)[b] = make_int4(m[0], m[1], m[2], m[3]);
+}
+
+__global__ void features_finalize_kernel(const float* __restrict__ in, int n_mels, int in_frames,
+                                         const int32_t* __restrict__ frames, const int32_t* __restrict__ masks,
+                                         int out_frames, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int T = frames ? min(frames[b], in_frames) : in_frames;
+    int mt0 = 0, mt1 = 0, mf0 = 0, mf1 = 0;
+    if (masks) {
+        mt0 = masks[4 * b];
+        mt1 = masks[4 * b + 1];
+        mf0 = masks[4 * b + 2];
+        mf1 = masks[4 * b + 3];
+    }
+    const int total = n_mels * out_frames;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int m = i / out_frames, t = i - m * out_frames;
+        float v = 0.f;
+        if (t < T) {
+            v = in[((int64_t)b * n_mels + m) * in_frames + t];
+            if ((t >= mt0 && t < mt1) || (m >= mf0 && m < mf1)) v = 0.f;
+        }
+        out[((int64_t)b * n_mels + m) * out_frames + t] = v;
+    }
+}
+
+}  // namespace sir
+
+// ---- C ABI ------------------------------------------------------------------------------------------------
+using namespace sir;
+
+struct sir_frontend {
+    int device = 0;
+    int sample_rate = 16000, n_mels = 64;
+    int num_sms = 148;
+    int mel_weight_count = 0;
+    DeviceBuffer tables;
+    FrontendTables dev{};
+};
+
+extern "C" const char* sir_last_error(void) { return g_error; }
+extern "C" int sir_version(void) { return 100; }
+extern "C" int64_t sir_launch_count(void) { return g_launches.load(); }
+
+extern "C" int sir_frontend_create(sir_frontend** out, int sample_rate, int n_mels, int n_fft, int hop_length) {
+    if (!out) return fail(SIR_ERR_INVALID, "sir_frontend_create: out is NULL");
+    *out = nullptr;
+    if (n_fft != kNfft || hop_length != kHop)
+        return fail(SIR_ERR_UNSUPPORTED, "only n_fft=1024 / hop_length=512 are implemented (got %d / %d)", n_fft,
+                    hop_length);
+    if (n_mels < 1 || n_mels > kMaxMels) return fail(SIR_ERR_UNSUPPORTED, "n_mels must be in [1,%d]", kMaxMels);
+    if (sample_rate < 2) return fail(SIR_ERR_INVALID, "bad sample_rate %d", sample_rate);
+    HostFrontendTables h = build_frontend_tables(sample_rate, n_mels);
+    if ((int)h.mel_weight.size() > kMelWeightCap)
+        return fail(SIR_ERR_UNSUPPORTED, "filterbank has %zu taps (cap %d)", h.mel_weight.size(), kMelWeightCap);
+    sir_frontend* fe = new sir_frontend();
+    fe->sample_rate = sample_rate;
+    fe->n_mels = n_mels;
+    fe->mel_weight_count = (int)h.mel_weight.size();
+    cudaError_t e = cudaGetDevice(&fe->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&fe->num_sms, cudaDevAttrMultiProcessorCount, fe->device);
+    if (e != cudaSuccess) {
+        delete fe;
+        return fail(SIR_ERR_CUDA, "no usable CUDA device: %s", cudaGetErrorString(e));
+    }
+    // one allocation, 16-byte aligned sections
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t o_win = 0, o_512 = al(o_win + 1024 * 4), o_1024 = al(o_512 + 1024 * 4),
+                 o_ms = al(o_1024 + 514 * 4), o_mc = al(o_ms + n_mels * 4), o_mo = al(o_mc + n_mels * 4),
+                 o_mw = al(o_mo + n_mels * 4), total = al(o_mw + h.mel_weight.size() * 4);
+    int rc = fe->tables.reserve(total);
+    if (rc != SIR_OK) {
+        delete fe;
+        return rc;
+    }
+    char* base = (char*)fe->tables.ptr;
+    struct Up {
+        size_t off;
+        const void* src;
+        size_t bytes;
+    } ups[] = {{o_win, h.window.data(), 1024 * 4},          {o_512, h.tw512.data(), 1024 * 4},
+               {o_1024, h.tw1024.data(), 514 * 4},          {o_ms, h.mel_start.data(), (size_t)n_mels * 4},
+               {o_mc, h.mel_count.data(), (size_t)n_mels * 4}, {o_mo, h.mel_offset.data(), (size_t)n_mels * 4},
+               {o_mw, h.mel_weight.data(), h.mel_weight.size() * 4}};
+    for (auto& u : ups) {
+        e = cudaMemcpy(base + u.off, u.src, u.bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            fe->tables.release();
+            delete fe;
+            return fail(SIR_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(e));
+        }
+    }
+    fe->dev = FrontendTables{(const float*)(base + o_win), (const float*)(base + o_512), (const float*)(base + o_1024),
+                             (const int*)(base + o_ms),    (const int*)(base + o_mc),    (const int*)(base + o_mo),
+                             (const float*)(base + o_mw)};
+    e = cudaFuncSetAttribute(logmel_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFeSmemBytes);
+    if (e != cudaSuccess) {
+        fe->tables.release();
+        delete fe;
+        return fail(SIR_ERR_CUDA, "cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+    }
+    *out = fe;
+    return SIR_OK;
+}
+
+extern "C" void sir_frontend_destroy(sir_frontend* fe) {
+    if (!fe) return;
+    fe->tables.release();
+    delete fe;
+}
+
+extern "C" int sir_frontend_forward(sir_frontend* fe, const float* d_wave, int64_t wave_stride,
+                                    const int32_t* d_lengths, int n_samples, int batch, int max_samples, int mode,
+                                    int out_frames, float* d_out, const int32_t* d_masks, int32_t* d_status,
+                                    void* stream) {
+    if (!fe || !d_wave || !d_out) return fail(SIR_ERR_INVALID, "sir_frontend_forward: NULL handle or buffer");
+    if (batch < 0 || n_samples < 0 || out_frames < 1 || wave_stride < n_samples)
+        return fail(SIR_ERR_INVALID, "sir_frontend_forward: bad sizes (batch %d, n_samples %d, out_frames %d)", batch,
+                    n_samples, out_frames);
+    if (mode < SIR_OUT_MEL_POWER || mode > SIR_OUT_LOGMEL_NORM) return fail(SIR_ERR_INVALID, "bad mode %d", mode);
+    if (d_masks && mode != SIR_OUT_LOGMEL_NORM)
+        return fail(SIR_ERR_INVALID, "mask bands are applied to normalised features only");
+    if (batch == 0) return SIR_OK;
+    FrontendParams p{};
+    p.wave = d_wave;
+    p.wave_stride = wave_stride;
+    p.lengths = d_lengths;
+    p.n_samples = n_samples;
+    p.max_samples = max_samples;
+    p.n_mels = fe->n_mels;
+    p.mode = mode;
+    p.out_frames = out_frames;
+    p.out = d_out;
+    p.masks = d_masks;
+    p.status = d_status;
+    p.tables = fe->dev;
+    p.mel_weight_count = fe->mel_weight_count;
+    // cluster size: enough CTAs for ~2 waves of 3 CTAs/SM, never more CTAs than 8-frame groups
+    int eff = max_samples > 0 && max_samples < n_samples ? max_samples : n_samples;
+    const int groups = (1 + eff / kHop + kGroupFrames - 1) / kGroupFrames;
+    int csize = 1;
+    while (csize < 8 && (int64_t)batch * csize < (int64_t)fe->num_sms * 6 && csize * 2 <= groups) csize *= 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(batch * csize));
+    cfg.blockDim = dim3(kFeThreads);
+    cfg.dynamicSmemBytes = kFeSmemBytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SIR_CUDA(cudaLaunchKernelEx(&cfg, logmel_frontend_kernel, p));
+    SIR_CHECK_LAUNCH("logmel_frontend_kernel");
+    return SIR_OK;
+}
+
+extern "C" int sir_amplitude_to_db(const float* d_in, float* d_out, int64_t n, void* stream) {
+    if (!d_in || !d_out || n < 0) return fail(SIR_ERR_INVALID, "sir_amplitude_to_db: bad arguments");
+    if (n == 0) return SIR_OK;
+    const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    amplitude_to_db_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, n);
+    SIR_CHECK_LAUNCH("amplitude_to_db_kernel");
+    return SIR_OK;
+}
+
+extern "C" int sir_specaugment_sample(uint64_t seed, uint64_t first_index, int batch, int n_mels, int n_frames,
+                                      const int32_t* d_frames, float augment_prob, int time_mask_param,
+                                      int freq_mask_param, int32_t* d_masks, void* stream) {
+    if (!d_masks || batch < 0) return fail(SIR_ERR_INVALID, "sir_specaugment_sample: bad arguments");
+    if ((reinterpret_cast<uintptr_t>(d_masks) & 15u) != 0)
+        return fail(SIR_ERR_INVALID, "sir_specaugment_sample: d_masks must be 16-byte aligned");
+    if (batch == 0) return SIR_OK;
+    specaugment_sample_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        seed, first_index, batch, n_mels, n_frames, d_frames, augment_prob, time_mask_param, freq_mask_param, d_masks);
+    SIR_CHECK_LAUNCH("specaugment_sample_kernel");
+    return SIR_OK;
+}
+
+extern "C" int sir_features_finalize(const float* d_in, int batch, int n_mels, int in_frames,
+                                     const int32_t* d_frames, const int32_t* d_masks, int out_frames, float* d_out,
+                                     void* stream) {
+    if (!d_in || !d_out || batch < 0 || n_mels < 1 || in_frames < 0 || out_frames < 1)
+        return fail(SIR_ERR_INVALID, "sir_features_finalize: bad arguments");
+    if (batch == 0) return SIR_OK;
+    if (batch > 65535) return fail(SIR_ERR_UNSUPPORTED, "sir_features_finalize: batch > 65535");
+    const int total = n_mels * out_frames;
+    dim3 grid((unsigned)((total + 255) / 256), (unsigned)batch);
+    features_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, n_mels, in_frames, d_frames, d_masks,
+                                                                     out_frames, d_out);
+    SIR_CHECK_LAUNCH("features_finalize_kernel");
+    return SIR_OK;
+}

@@ -1,0 +1,67 @@
+// Shared host-side plumbing of libsir_b200: error reporting, launch counting, small device helpers.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/sir_b200.h"
+
+namespace sir {
+
+extern thread_local char g_error[512];
+extern std::atomic<int64_t> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define SIR_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return ::sir::fail(SIR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                               __LINE__);                                                                \
+    } while (0)
+
+#define SIR_CHECK_LAUNCH(name)                                                                           \
+    do {                                                                                                 \
+        cudaError_t _e = cudaGetLastError();                                                             \
+        if (_e != cudaSuccess)                                                                           \
+            return ::sir::fail(SIR_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e));   \
+        ::sir::count_launch();                                                                           \
+    } while (0)
+
+// Grow-only device buffer owned by a handle.
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t want) {
+        if (want <= bytes) return SIR_OK;
+        if (ptr) {
+            SIR_CUDA(cudaDeviceSynchronize());
+            SIR_CUDA(cudaFree(ptr));
+            ptr = nullptr;
+            bytes = 0;
+        }
+        SIR_CUDA(cudaMalloc(&ptr, want));
+        bytes = want;
+        return SIR_OK;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+};
+
+}  // namespace sir

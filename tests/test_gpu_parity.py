@@ -1,0 +1,184 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden vectors.
+
+Run on the B200 box: ``python -m pytest tests -m gpu``.  Bars: features within 1e-4 of the tensor scale,
+logits within 1e-3 absolute, identical argmax, integer outputs (mask parameters) bit-exact.
+"""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import classifier_np, logmel_np
+from tests.util import FEATURE_REL_TOL, LOGIT_ABS_TOL, golden, golden_waves, rel_to_scale, synth
+
+pytestmark = pytest.mark.gpu
+native = importlib.import_module("speech-intent-recognizer_b200._native")
+
+
+@pytest.fixture(scope="module")
+def fe():
+    return native.Frontend()
+
+
+@pytest.fixture(scope="module")
+def model():
+    m = native.Model(31, 64)
+    m.load_weights(torch.from_numpy(synth.flatten_weights(synth.make_weights(1234))))
+    return m
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+def test_library_is_the_cuda_extension():
+    lib = native.load_library()
+    assert lib.sir_version() >= 100
+    before = native.launch_count()
+    native.amplitude_to_db(torch.ones(8, device="cuda"))
+    assert native.launch_count() == before + 1
+
+
+def test_frontend_matches_golden_ragged_batch(fe):
+    g, waves, lengths, noise = golden_waves()
+    out = fe.forward(dev(waves), lengths=dev(np.asarray(lengths, np.int32)), max_samples=80000, out_frames=200)
+    out = out.cpu().numpy()
+    for i, n in enumerate(lengths):
+        want = g[f"feat_{i}"]
+        T = want.shape[1]
+        assert rel_to_scale(out[i, :, :T], want) < FEATURE_REL_TOL, i
+        assert not out[i, :, T:].any()                      # zero padding, scripts/dataset.py:111-113
+    single = fe.forward(dev(noise)).cpu().numpy()           # one utterance, unpadded T = 94
+    assert single.shape == (1, 64, 94)
+    assert rel_to_scale(single[0], g["feat_noise"]) < FEATURE_REL_TOL
+
+
+def test_frontend_stages_and_untruncated_twin(fe):
+    g, waves, lengths, _ = golden_waves()
+    w0 = dev(waves[0:1, :lengths[0]].copy())
+    p = fe.forward(w0, mode=native.OUT_MEL_POWER).cpu().numpy()[0]
+    assert rel_to_scale(p, g["mel_power_0"]) < 1e-5
+    d = fe.forward(w0, mode=native.OUT_MEL_DB).cpu().numpy()[0]
+    assert np.max(np.abs(d - g["mel_db_0"])) < 1e-2         # dB; |dB| up to 100 -> 1e-4 of scale
+    d2 = native.amplitude_to_db(dev(g["mel_power_0"])).cpu().numpy()
+    assert np.max(np.abs(d2 - g["mel_db_0"])) < 1e-4
+    full = fe.forward(dev(waves[2:3, :90000].copy())).cpu().numpy()[0]      # scripts/test_model.py twin: no 5 s cut
+    assert full.shape == (64, 176) and rel_to_scale(full, g["feat_2_untruncated"]) < FEATURE_REL_TOL
+
+
+def test_frontend_trim_keeps_statistics_of_all_frames(fe):
+    """Long audio: normalise over all T frames, THEN trim (scripts/test_model.py:94,116)."""
+    g, waves, lengths, _ = golden_waves()
+    out = fe.forward(dev(waves[2:3, :90000].copy()), out_frames=100).cpu().numpy()[0]
+    assert rel_to_scale(out, g["feat_2_untruncated"][:, :100]) < FEATURE_REL_TOL
+
+
+def test_frontend_edge_cases(fe):
+    g, waves, lengths, _ = golden_waves()
+    sil = fe.forward(torch.zeros(1, 16000, device="cuda")).cpu().numpy()[0]
+    assert sil.shape == g["feat_silence"].shape and not sil.any()
+    # too-short utterances (<= 512 samples: reflect padding undefined, the reference returns None/zeros)
+    w = torch.randn(3, 2048, device="cuda") * 0.1
+    lens = torch.tensor([2048, 512, 0], dtype=torch.int32, device="cuda")
+    status = torch.full((3,), -1, dtype=torch.int32, device="cuda")
+    out = fe.forward(w, lengths=lens, out_frames=8, status=status).cpu().numpy()
+    assert status.cpu().tolist() == [0, 1, 1]
+    assert out[0].any() and not out[1].any() and not out[2].any()
+    want = logmel_np.pad_or_trim(logmel_np.extract_features(w[0].cpu().numpy()), 8)
+    assert rel_to_scale(out[0], want) < FEATURE_REL_TOL
+    # strided rows + unaligned row starts take the scalar staging path
+    big = torch.zeros(2, 48003, device="cuda")
+    big[:, 1:48001] = dev(waves[:2, :48000].copy())
+    view = big[:, 1:48001]
+    out = fe.forward(view).cpu().numpy()
+    for i in range(2):
+        assert rel_to_scale(out[i], logmel_np.extract_features(waves[i, :48000])) < FEATURE_REL_TOL
+    # 80-mel frontend (config 5)
+    fe80 = native.Frontend(n_mels=80)
+    f80 = fe80.forward(dev(waves[0:1, :32000].copy())).cpu().numpy()[0]
+    assert rel_to_scale(f80, g["feat80_0"]) < FEATURE_REL_TOL
+    with pytest.raises(native.NativeError):
+        native.Frontend(n_fft=512, hop_length=256)
+
+
+@pytest.mark.parametrize("batch,samples", [(1, 48000), (37, 24000), (1200, 4096)])
+def test_frontend_cluster_shapes_against_oracle(fe, batch, samples):
+    """Cluster size 8 / 4 / 1 launches (small, medium, large batch) agree with the restatement."""
+    w = synth.white_noise(100 + batch, batch, samples) * np.linspace(0.01, 1.0, batch, dtype=np.float32)[:, None]
+    out = fe.forward(dev(w), out_frames=64).cpu().numpy()
+    for i in sorted({0, batch // 2, batch - 1}):
+        want = logmel_np.pad_or_trim(logmel_np.extract_features(w[i]), 64)
+        assert rel_to_scale(out[i], want) < FEATURE_REL_TOL, (batch, i)
+
+
+def test_specaugment_sampler_bit_exact():
+    frames = np.asarray([94, 40, 157, 10, 200, 94, 94, 33], np.int32)
+    for prob in (1.0, 0.7):
+        got = native.specaugment_sample(1234567890123, 1000, 8, 64, 0, frames=dev(frames), augment_prob=prob)
+        want = logmel_np.sample_masks(1234567890123, 1000, 8, 64, frames, augment_prob=prob)
+        assert np.array_equal(got.cpu().numpy(), want)
+    got = native.specaugment_sample(7, 0, 4096, 64, 94).cpu().numpy()
+    assert np.array_equal(got, logmel_np.sample_masks(7, 0, 4096, 64, 94))
+    tw, fw = got[:, 1] - got[:, 0], got[:, 3] - got[:, 2]
+    assert tw.max() == 19 and fw.max() == 9 and 0.4 < (tw > 0).mean() < 0.55
+
+
+def test_fused_masks_match_reference_semantics(fe):
+    g, waves, lengths, _ = golden_waves()
+    ga = golden("augment")
+    w0 = dev(waves[0:1, :lengths[0]].copy()).repeat(len(ga["uniforms"]), 1)
+    params = np.stack([logmel_np.sample_mask_params(u, 64, 94) for u in ga["uniforms"]])
+    out = fe.forward(w0, masks=dev(params)).cpu().numpy()
+    for k in range(len(params)):
+        want = ga["outputs"][k]
+        assert np.array_equal(out[k] == 0, want == 0) or rel_to_scale(out[k], want) < FEATURE_REL_TOL
+        assert rel_to_scale(out[k], want) < FEATURE_REL_TOL
+    # the same masks applied to cached features + pad to 200 (dataset.__getitem__ tail on a cache hit)
+    base = dev(ga["base"][None].repeat(len(params), 0))
+    fin = native.features_finalize(base, 200, masks=dev(params)).cpu().numpy()
+    for k in range(len(params)):
+        assert np.array_equal(fin[k], logmel_np.pad_or_trim(ga["outputs"][k], 200))
+
+
+def test_classifier_matches_golden(model):
+    g = golden("classifier")
+    y = model.forward(dev(g["x"])).cpu().numpy()
+    assert np.max(np.abs(y - g["logits"])) < LOGIT_ABS_TOL
+    assert np.array_equal(y.argmax(1), g["logits"].argmax(1))
+    yv = model.forward(dev(g["x_var"][None])).cpu().numpy()            # variable T = 40, no padding (config 1)
+    assert np.max(np.abs(yv - g["logits_var"])) < LOGIT_ABS_TOL
+
+
+def test_pipeline_matches_oracle_and_argmax(fe, model):
+    """waveform -> logits: config-2 shape at a size the oracle finishes in seconds."""
+    B = 24
+    w = synth.speech_like(21, B)
+    logits, feats = model.pipeline(fe, dev(w), max_samples=80000, out_frames=200)
+    logits, feats = logits.cpu().numpy(), feats.cpu().numpy()
+    want_f = np.stack([logmel_np.dataset_item(x) for x in w])
+    assert rel_to_scale(feats, want_f) < FEATURE_REL_TOL
+    want = classifier_np.forward(want_f, synth.make_weights(1234))
+    assert np.max(np.abs(logits - want)) < LOGIT_ABS_TOL
+    top = np.sort(want, axis=1)
+    safe = (top[:, -1] - top[:, -2]) > 4 * LOGIT_ABS_TOL
+    assert safe.sum() >= B - 2
+    assert np.array_equal(logits.argmax(1)[safe], want.argmax(1)[safe])
+    assert len(set(want.argmax(1).tolist())) >= 6                       # not vacuous
+
+
+def test_full_size_properties(fe, model):
+    """Config-2 size (256 x 3 s): size-independent properties instead of a full oracle run."""
+    B = 256
+    w = dev(synth.white_noise(5, 64, 48000)).repeat(4, 1) * 1.0
+    logits, feats = model.pipeline(fe, w, out_frames=200)
+    f = feats[:, :, :94]
+    mean = f.reshape(B, -1).mean(1)
+    std = f.reshape(B, -1).std(1)
+    assert mean.abs().max().item() < 1e-4 and (std - 1).abs().max().item() < 1e-3     # normalised per utterance
+    assert not feats[:, :, 94:].any().item()
+    assert torch.equal(feats[:64], feats[192:]) and torch.equal(logits[:64], logits[192:])   # batch-position invariant
+    # gain invariance: log-mel of a*x is a dB shift, removed by the normalisation
+    f2 = fe.forward(w[:8] * 0.25, out_frames=200)
+    assert rel_to_scale(f2.cpu().numpy(), feats[:8].cpu().numpy()) < FEATURE_REL_TOL
