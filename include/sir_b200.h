@@ -42,6 +42,13 @@ int sir_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py "gpu_launches"). */
 int64_t sir_launch_count(void);
 
+/* Per-stage device timing for bench.py / profiling (off by default): when enabled every kernel stage is
+ * bracketed by CUDA events on the launching stream.  sir_profile_read synchronises the device, writes a
+ * ';'-separated list of stage names plus total milliseconds and call counts per stage, clears the records and
+ * returns the number of stages. */
+void sir_profile_enable(int on);
+int sir_profile_read(char* names, int names_cap, float* ms, int* calls, int max_stages);
+
 /* ---- feature frontend ---------------------------------------------------------------------------------
  * sir_frontend_create  <->  AudioFeatureExtractor.__init__        scripts/precompute_features.py:21-36
  *                           (and the transform construction in    scripts/dataset.py:59-66)

@@ -22,6 +22,8 @@ SIGNATURES = {
     "sir_last_error": (c_char_p, []),
     "sir_version": (c_int, []),
     "sir_launch_count": (c_int64, []),
+    "sir_profile_enable": (None, [c_int]),
+    "sir_profile_read": (c_int, [c_char_p, c_int, POINTER(c_float), POINTER(c_int), c_int]),
     "sir_frontend_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int]),
     "sir_frontend_destroy": (None, [c_void_p]),
     "sir_frontend_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
@@ -85,6 +87,20 @@ def stream_ptr():
 
 def launch_count() -> int:
     return int(load_library().sir_launch_count())
+
+
+def profile_enable(on: bool):
+    load_library().sir_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """-> {stage: (total_ms, calls)} since the last read (synchronises the device)."""
+    names = ctypes.create_string_buffer(4096)
+    ms = (c_float * 64)()
+    calls = (c_int * 64)()
+    n = load_library().sir_profile_read(names, 4096, ms, calls, 64)
+    keys = names.value.decode().split(";") if n else []
+    return {k: (float(ms[i]), int(calls[i])) for i, k in enumerate(keys)}
 
 
 class Frontend:

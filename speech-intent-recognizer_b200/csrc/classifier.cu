@@ -554,18 +554,21 @@ int model_forward_chunk(sir_model* m, const Workspace& ws, const float* feat, in
     const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2, Tg = W4 / 2;
     {
         dim3 grid((unsigned)((H2 * W2 + 127) / 128), (unsigned)B);
+        ProfScope ps("conv1_bn_relu_pool", st);
         conv1_bn_relu_pool_kernel<<<grid, 128, 0, st>>>(feat, m->w1, m->sh1, ws.act1, H, W);
         SIR_CHECK_LAUNCH("conv1_bn_relu_pool_kernel");
     }
     {
         constexpr size_t smem = (size_t)(180 * (32 + 4) + 32 * 64) * sizeof(float);
         dim3 grid((unsigned)((W2 + 15) / 16), (unsigned)((H2 + 7) / 8), (unsigned)B);
+        ProfScope ps("conv2_bn_relu_pool", st);
         conv3x3_bn_relu_pool_kernel<32, 64, false><<<grid, 256, smem, st>>>(ws.act1, m->w2, m->sh2, ws.act2, H2, W2);
         SIR_CHECK_LAUNCH("conv3x3_bn_relu_pool_kernel<32,64>");
     }
     {
         constexpr size_t smem = (size_t)(180 * (64 + 4) + 64 * 128) * sizeof(float);
         dim3 grid((unsigned)((W4 + 15) / 16), (unsigned)((H4 + 7) / 8), (unsigned)B);
+        ProfScope ps("conv3_bn_relu_pool", st);
         conv3x3_bn_relu_pool_kernel<64, 128, true><<<grid, 256, smem, st>>>(ws.act2, m->w3, m->sh3, ws.gru_in, H4, W4);
         SIR_CHECK_LAUNCH("conv3x3_bn_relu_pool_kernel<64,128>");
     }
@@ -575,8 +578,12 @@ int model_forward_chunk(sir_model* m, const Workspace& ws, const float* feat, in
     for (int l = 0; l < 2; ++l) {
         const int M = B * Tg;
         dim3 ggrid(1536 / 128, (unsigned)((M + 127) / 128));
-        gemm_nt_bias_kernel<<<ggrid, 256, 0, st>>>(x, m->wih[l], m->bih[l], ws.gi, M, 1536, in_sz);
+        {
+            ProfScope ps(l == 0 ? "gru_l0_input_gemm" : "gru_l1_input_gemm", st);
+            gemm_nt_bias_kernel<<<ggrid, 256, 0, st>>>(x, m->wih[l], m->bih[l], ws.gi, M, 1536, in_sz);
+        }
         SIR_CHECK_LAUNCH("gemm_nt_bias_kernel");
+        ProfScope ps(l == 0 ? "gru_l0_recurrence" : "gru_l1_recurrence", st);
         float* h0 = ws.h;
         float* h1 = ws.h + (size_t)2 * B * 256;
         for (int s = 0; s < Tg; ++s) {
@@ -590,6 +597,7 @@ int model_forward_chunk(sir_model* m, const Workspace& ws, const float* feat, in
     }
     {
         const size_t smem = (size_t)(Tg + 512) * sizeof(float);
+        ProfScope ps("attention_fc", st);
         attention_fc_kernel<<<(unsigned)B, 128, smem, st>>>(ws.y1, m->att_w, m->att_b, m->fc_w, m->fc_b, logits, Tg,
                                                              m->num_classes);
         SIR_CHECK_LAUNCH("attention_fc_kernel");

@@ -33,6 +33,29 @@ namespace sir {
 
 thread_local char g_error[512] = "";
 std::atomic<int64_t> g_launches{0};
+bool g_profile = false;
+
+struct ProfRecord {
+    const char* name;
+    cudaEvent_t begin, end;
+};
+static std::vector<ProfRecord> g_prof_records;
+
+void prof_mark(const char* name, cudaStream_t st, bool begin) {
+    if (begin) {
+        ProfRecord r{name, nullptr, nullptr};
+        cudaEventCreate(&r.begin);
+        cudaEventCreate(&r.end);
+        cudaEventRecord(r.begin, st);
+        g_prof_records.push_back(r);
+    } else {
+        for (size_t i = g_prof_records.size(); i-- > 0;)
+            if (g_prof_records[i].name == name) {
+                cudaEventRecord(g_prof_records[i].end, st);
+                break;
+            }
+    }
+}
 
 constexpr int kFeWarps = 4;
 constexpr int kFeThreads = kFeWarps * 32;
@@ -401,6 +424,42 @@ extern "C" const char* sir_last_error(void) { return g_error; }
 extern "C" int sir_version(void) { return 100; }
 extern "C" int64_t sir_launch_count(void) { return g_launches.load(); }
 
+extern "C" void sir_profile_enable(int on) { g_profile = on != 0; }
+
+// Aggregates the recorded stages by name: names are written as a ';'-separated list, ms[i] / calls[i] hold the
+// total device time and number of occurrences.  Clears the records.  Synchronises the device.
+extern "C" int sir_profile_read(char* names, int names_cap, float* ms, int* calls, int max_stages) {
+    cudaDeviceSynchronize();
+    std::vector<const char*> order;
+    std::vector<float> total;
+    std::vector<int> count;
+    for (auto& r : g_prof_records) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.begin, r.end);
+        cudaEventDestroy(r.begin);
+        cudaEventDestroy(r.end);
+        size_t i = 0;
+        for (; i < order.size(); ++i)
+            if (order[i] == r.name) break;
+        if (i == order.size()) {
+            order.push_back(r.name);
+            total.push_back(0.f);
+            count.push_back(0);
+        }
+        total[i] += t;
+        count[i] += 1;
+    }
+    g_prof_records.clear();
+    int n = 0, pos = 0;
+    if (names && names_cap > 0) names[0] = 0;
+    for (size_t i = 0; i < order.size() && n < max_stages; ++i, ++n) {
+        ms[n] = total[i];
+        calls[n] = count[i];
+        if (names) pos += snprintf(names + pos, pos < names_cap ? names_cap - pos : 0, "%s%s", n ? ";" : "", order[i]);
+    }
+    return n;
+}
+
 extern "C" int sir_frontend_create(sir_frontend** out, int sample_rate, int n_mels, int n_fft, int hop_length) {
     if (!out) return fail(SIR_ERR_INVALID, "sir_frontend_create: out is NULL");
     *out = nullptr;
@@ -511,7 +570,10 @@ extern "C" int sir_frontend_forward(sir_frontend* fe, const float* d_wave, int64
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SIR_CUDA(cudaLaunchKernelEx(&cfg, logmel_frontend_kernel, p));
+    {
+        ProfScope ps("logmel_frontend_kernel", cfg.stream);
+        SIR_CUDA(cudaLaunchKernelEx(&cfg, logmel_frontend_kernel, p));
+    }
     SIR_CHECK_LAUNCH("logmel_frontend_kernel");
     return SIR_OK;
 }

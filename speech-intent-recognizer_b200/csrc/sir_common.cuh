@@ -25,6 +25,21 @@ inline int fail(int code, const char* fmt, ...) {
 
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Optional per-stage device timing (sir_profile_enable / sir_profile_read): a pair of CUDA events on the
+// launching stream around each named stage.  Off by default; bench.py turns it on for a separate pass.
+extern bool g_profile;
+void prof_mark(const char* name, cudaStream_t st, bool begin);
+struct ProfScope {
+    const char* name;
+    cudaStream_t st;
+    ProfScope(const char* n, cudaStream_t s) : name(n), st(s) {
+        if (g_profile) prof_mark(name, st, true);
+    }
+    ~ProfScope() {
+        if (g_profile) prof_mark(name, st, false);
+    }
+};
+
 #define SIR_CUDA(expr)                                                                                   \
     do {                                                                                                 \
         cudaError_t _e = (expr);                                                                         \
