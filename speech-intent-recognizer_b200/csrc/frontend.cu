@@ -7,10 +7,11 @@
 // Mapping
 //   * one thread-block CLUSTER per utterance (1, 2, 4 or 8 CTAs, picked so the grid covers the 148 SMs a
 //     few times over even for small batches); the cluster's CTAs take 8-frame groups round-robin;
-//   * a CTA (4 warps) stages the 9 hop-blocks (4608 samples) its 8 frames need into shared memory with
-//     128-bit streaming loads - every sample is fetched from HBM once per group, reflect padding is resolved
-//     while staging;
-//   * each HALF-WARP owns one frame: 512-point complex FFT as 32-point x 16-point register FFTs with one
+//   * each HALF-WARP owns one frame and reads its 1024 samples straight from global memory (128 contiguous
+//     bytes per half-warp request; the 50 % overlap with the neighbouring frame, held by the other half of
+//     the same warp, is served by L1/L2, so HBM sees every sample once); only the first and last frame of an
+//     utterance take the scalar path that resolves torch.stft's reflect padding;
+//   * per frame: 512-point complex FFT as 32-point x 16-point register FFTs with one
 //     shared-memory transposition (logmel_frame.cuh), real-FFT post-pass, power, sparse mel taps, log10;
 //   * un-normalised values go to the output through an 8-frame shared tile (32-byte row segments), the
 //     per-utterance mean / unbiased std are combined across the cluster through distributed shared memory
@@ -60,7 +61,6 @@ void prof_mark(const char* name, cudaStream_t st, bool begin) {
 constexpr int kFeWarps = 4;
 constexpr int kFeThreads = kFeWarps * 32;
 constexpr int kGroupFrames = 2 * kFeWarps;                 // one frame per half-warp
-constexpr int kStageFloats = (kGroupFrames + 1) * kHop;    // 9 hop blocks
 constexpr int kTileStride = kGroupFrames + 1;              // padded to dodge bank conflicts
 constexpr int kMelWeightCap = 1280;
 
@@ -72,13 +72,12 @@ constexpr int kOffMelStart = kOffTw1024 + 516;
 constexpr int kOffMelCount = kOffMelStart + kMaxMels;
 constexpr int kOffMelOffset = kOffMelCount + kMaxMels;
 constexpr int kOffMelWeight = kOffMelOffset + kMaxMels;
-constexpr int kOffStage = kOffMelWeight + kMelWeightCap;
-constexpr int kOffScratch = kOffStage + kStageFloats;
+constexpr int kOffScratch = kOffMelWeight + kMelWeightCap;
 constexpr int kOffTile = kOffScratch + kGroupFrames * kFrameScratch;
 constexpr int kOffReduce = kOffTile + kMaxMels * kTileStride;
 constexpr int kFeSmemFloats = kOffReduce + 64;
 constexpr size_t kFeSmemBytes = (size_t)kFeSmemFloats * sizeof(float);
-static_assert(kOffStage % 4 == 0 && kOffScratch % 4 == 0, "16-byte alignment of vector regions");
+static_assert(kOffScratch % 4 == 0 && kOffTile % 4 == 0, "16-byte alignment of vector regions");
 static_assert(3 * (kFeSmemBytes + 1024) <= 232448, "three CTAs per SM");
 
 struct FrontendParams {
@@ -97,13 +96,16 @@ struct FrontendParams {
     int mel_weight_count;
 };
 
-__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(p));
-    return v;
-}
+// Interior frames read their 1024 samples straight from global memory: lane l takes the 8-byte words
+// l + 16 j, so a half-warp covers 128 contiguous bytes per request, and the 50 % overlap with the neighbouring
+// frame (the other half of the same warp) is served by L1/L2 - HBM still sees every sample once.
+struct GlobalFrame {
+    const float2* base;
+    __device__ __forceinline__ F2 operator()(int n) const {
+        const float2 v = __ldg(base + n);
+        return F2{v.x, v.y};
+    }
+};
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -144,12 +146,11 @@ __global__ void __launch_bounds__(kFeThreads, 3) logmel_frontend_kernel(const Fr
     const int T = valid ? 1 + L / kHop : 0;
     const int n_groups = (T + kGroupFrames - 1) / kGroupFrames;
     const float* __restrict__ row = p.wave + (int64_t)b * p.wave_stride;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 7u) == 0);
     float* __restrict__ out = p.out + (int64_t)b * p.n_mels * p.out_frames;
     const bool out_vec = (p.out_frames % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
     if (p.status && crank == 0 && tid == 0) p.status[b] = valid ? 0 : 1;
 
-    float* stage = smem + kOffStage;
     float* tile = smem + kOffTile;
     float* red = smem + kOffReduce;
     const int lane = tid & 31, warp = tid >> 5, half = lane >> 4, q = lane & 15;
@@ -158,32 +159,23 @@ __global__ void __launch_bounds__(kFeThreads, 3) logmel_frontend_kernel(const Fr
 
     float shift = 0.f, s1 = 0.f, s2 = 0.f;
     bool have_shift = false;
+    __syncthreads();                                        // tables visible
 
     for (int g = crank; g < n_groups; g += csize) {
         const int t0 = g * kGroupFrames;
-        __syncthreads();                                    // previous group's stage/tile fully consumed
-        // stage padded samples [512 t0, 512 t0 + 4608): padded index pp <-> original index pp - 512
-        for (int q4 = tid; q4 < kStageFloats / 4; q4 += kFeThreads) {
-            const int i = t0 * kHop + 4 * q4 - kNfft / 2;
-            float4 v;
-            if (vec_ok && i >= 0 && i + 3 < L) {
-                v = ld_stream_f4(row + i);
+        const int t = t0 + slot;
+        const bool active = t < T;
+        if (active) {
+            // frame t covers original samples [512 t - 512, 512 t + 512)
+            const int first = t * kHop - kNfft / 2;
+            if (vec_ok && first >= 0 && first + kNfft <= L) {
+                const GlobalFrame ld{reinterpret_cast<const float2*>(row + first)};
+                frame_phase_a(q, ld, st.window, st.tw512, scr, scr + 16 * kRowPad);
             } else {
-                float e[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int ii = i + u;
-                    const int r = ii < 0 ? -ii : (ii >= L ? 2 * (L - 1) - ii : ii);
-                    e[u] = (r >= 0 && r < L) ? __ldg(row + r) : 0.f;
-                }
-                v = make_float4(e[0], e[1], e[2], e[3]);
+                const ReflectFrame ld{row, first, L};
+                frame_phase_a(q, ld, st.window, st.tw512, scr, scr + 16 * kRowPad);
             }
-            reinterpret_cast<float4*>(stage)[q4] = v;
         }
-        __syncthreads();
-
-        const bool active = (t0 + slot) < T;
-        if (active) frame_phase_a(q, stage + slot * kHop, st.window, st.tw512, scr, scr + 16 * kRowPad);
         __syncwarp();
         {
             PhaseBRegs rb;
@@ -209,7 +201,7 @@ __global__ void __launch_bounds__(kFeThreads, 3) logmel_frontend_kernel(const Fr
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();                                    // tile complete
 
         // tile -> global (8 consecutive frames of one mel row = one 32-byte segment) + statistics
         if (!have_shift) {
@@ -239,6 +231,7 @@ __global__ void __launch_bounds__(kFeThreads, 3) logmel_frontend_kernel(const Fr
                 }
             }
         }
+        __syncthreads();                                    // tile consumed before the next group overwrites it
     }
 
     if (p.mode != SIR_OUT_LOGMEL_NORM || !valid) {

@@ -17,7 +17,7 @@ namespace sir {
 
 struct HostFrontendTables {
     std::vector<float> window;      // [1024]
-    std::vector<float> tw512;       // [16*32*2]  (cos, -sin)(2 pi l k2 / 512)
+    std::vector<float> tw512;       // [32*16*2]  (cos, -sin)(2 pi l k2 / 512), index k2*16 + l
     std::vector<float> tw1024;      // [257*2]    (cos,  sin)(2 pi k / 1024)
     std::vector<int32_t> mel_start, mel_count, mel_offset;
     std::vector<float> mel_weight;
@@ -32,8 +32,8 @@ inline HostFrontendTables build_frontend_tables(int sample_rate, int n_mels) {
     for (int l = 0; l < 16; ++l)
         for (int k2 = 0; k2 < 32; ++k2) {
             const double a = 2.0 * pi * (double)(l * k2) / 512.0;
-            t.tw512[(l * 32 + k2) * 2] = (float)std::cos(a);
-            t.tw512[(l * 32 + k2) * 2 + 1] = (float)(-std::sin(a));
+            t.tw512[(k2 * 16 + l) * 2] = (float)std::cos(a);
+            t.tw512[(k2 * 16 + l) * 2 + 1] = (float)(-std::sin(a));
         }
     t.tw1024.resize(257 * 2);
     for (int k = 0; k <= 256; ++k) {

@@ -38,7 +38,7 @@ struct alignas(8) F2 {      // 64-bit shared-memory accesses on the device, plai
 // Device-resident constant tables, built on the host in double precision (frontend.cu: build_tables).
 struct FrontendTables {
     const float* window;      // [1024] periodic Hann
-    const float* tw512;       // [16][32][2]  (cos, -sin) of 2*pi*l*k2/512
+    const float* tw512;       // [32][16][2]  (cos, -sin) of 2*pi*l*k2/512, index k2*16 + l
     const float* tw1024;      // [257][2]     (cos, sin)  of 2*pi*k/1024
     const int* mel_start;     // [n_mels] first bin with non-zero weight
     const int* mel_count;     // [n_mels] number of taps
@@ -47,29 +47,48 @@ struct FrontendTables {
 };
 
 // ---- phase A ------------------------------------------------------------------------------------------------
-// frame: 1024 contiguous samples (smem staging); scr_re/scr_im: 16*33 floats each.
-SIR_HD void frame_phase_a(int l, const float* __restrict__ frame, const float* __restrict__ window,
+// `load(n)` returns the real samples (2n, 2n+1) of the frame as an F2; scr_re/scr_im: 16*33 floats each.
+// tw512 is stored [k2][l] so that the 16 lanes read consecutive 8-byte words (conflict-free).
+template <typename Loader>
+SIR_HD void frame_phase_a(int l, const Loader& load, const float* __restrict__ window,
                           const float* __restrict__ tw512, float* __restrict__ scr_re, float* __restrict__ scr_im) {
     float re[32], im[32];
-    const F2* __restrict__ f2 = reinterpret_cast<const F2*>(frame);
     const F2* __restrict__ w2 = reinterpret_cast<const F2*>(window);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         const int n = l + 16 * j;            // complex index; samples 2n, 2n+1
-        const F2 v = f2[n], w = w2[n];
+        const F2 v = load(n), w = w2[n];
         re[j] = v.x * w.x;
         im[j] = v.y * w.y;
     }
     fft_dif<32>(re, im);
-    const F2* __restrict__ tw = reinterpret_cast<const F2*>(tw512) + l * 32;
+    const F2* __restrict__ tw = reinterpret_cast<const F2*>(tw512) + l;
 #pragma unroll
     for (int k2 = 0; k2 < 32; ++k2) {
         const float yr = re[bitrev<32>(k2)], yi = im[bitrev<32>(k2)];
-        const F2 t = tw[k2];                 // (cos, -sin)
+        const F2 t = tw[k2 * 16];            // (cos, -sin)(2 pi l k2 / 512)
         scr_re[l * kRowPad + k2] = yr * t.x - yi * t.y;
         scr_im[l * kRowPad + k2] = yr * t.y + yi * t.x;
     }
 }
+
+// Loader over 1024 contiguous, 8-byte aligned samples (interior frames read global memory directly).
+struct ContiguousFrame {
+    const F2* base;
+    SIR_HD F2 operator()(int n) const { return base[n]; }
+};
+
+// Loader that resolves torch.stft's reflect padding: sample i of the utterance for i in [first, first+1024),
+// mirrored at 0 and at L-1 (TA:functional/functional.py:123-134, pad_mode="reflect").
+struct ReflectFrame {
+    const float* row;
+    int first, L;
+    SIR_HD float at(int i) const {
+        const int r = i < 0 ? -i : (i >= L ? 2 * (L - 1) - i : i);
+        return (r >= 0 && r < L) ? row[r] : 0.f;
+    }
+    SIR_HD F2 operator()(int n) const { return F2{at(first + 2 * n), at(first + 2 * n + 1)}; }
+};
 
 // ---- phase B ------------------------------------------------------------------------------------------------
 // Split in load / compute+store so the caller can put a lane barrier between them (Z overwrites the

@@ -26,7 +26,13 @@ int main(int argc, char** argv) {
         std::vector<float> scratch(kFrameScratch, 0.f);
         float* scr_re = scratch.data();
         float* scr_im = scratch.data() + 16 * kRowPad;
-        for (int l = 0; l < 16; ++l) frame_phase_a(l, frame.data(), t.window, t.tw512, scr_re, scr_im);
+        if (trial & 1) {   // exercise both loaders: contiguous, and reflect with the frame inside the signal
+            ContiguousFrame ld{reinterpret_cast<const F2*>(frame.data())};
+            for (int l = 0; l < 16; ++l) frame_phase_a(l, ld, t.window, t.tw512, scr_re, scr_im);
+        } else {
+            ReflectFrame ld{frame.data(), 0, 1024};
+            for (int l = 0; l < 16; ++l) frame_phase_a(l, ld, t.window, t.tw512, scr_re, scr_im);
+        }
         std::vector<PhaseBRegs> rb(16);
         for (int q = 0; q < 16; ++q) frame_phase_b_load(q, scr_re, scr_im, rb[q]);
         for (int q = 0; q < 16; ++q) frame_phase_b_store(q, rb[q], scratch.data());
