@@ -13,7 +13,8 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsir_b200.so")
+# SIR_B200_LIB lets kernel experiments A/B a differently built library; the default is the in-tree build.
+LIB_PATH = os.environ.get("SIR_B200_LIB") or os.path.join(_HERE, "libsir_b200.so")
 
 OUT_MEL_POWER, OUT_MEL_DB, OUT_LOGMEL_NORM = 0, 1, 2
 

@@ -248,70 +248,106 @@ __global__ void __launch_bounds__(256) gemm_nt_bias_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// One GRU time step for both directions.  CTA: 32 hidden units x 32 utterances of one direction.
+// GRU recurrence of one layer, both directions, all T steps in ONE launch.
+//
 //   r = s(gi_r + W_hr h + b_hr)  z = s(gi_z + W_hz h + b_hz)  n = tanh(gi_n + r * (W_hn h + b_hn))
 //   h' = (1 - z) n + z h                                             (torch.nn.GRU; gi already holds b_i*)
+//
+// A thread-block CLUSTER of 8 CTAs owns one (direction, slice of 32 utterances); CTA r of the cluster keeps
+// the recurrent weights of hidden units [32 r, 32 r + 32) - 3 gates x 32 units x 256 k fp32 = 96 KB -
+// resident in shared memory for all steps.  Per step every CTA loads the slice's previous hidden state
+// (32 x 256 fp32, written by its 7 peers to the layer output y, still in L2) into shared memory, does its
+// 96 x 256 by 256 x 32 product on the fp32 pipe, applies the gates and writes its 32 x 32 block of h' to y;
+// one cluster barrier (release/acquire) per step orders the exchange.  No grid-wide synchronisation, no
+// per-step launch.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gru_step_kernel(const float* __restrict__ gi,     // [B*T, 1536]
-                                                       const float* __restrict__ whh,    // [2][768][256]
-                                                       const float* __restrict__ bhh,    // [2][768]
-                                                       const float* __restrict__ h_prev, // [2][B][256]
-                                                       float* __restrict__ h_next,       // [2][B][256]
-                                                       float* __restrict__ y,            // [B, T, 512]
-                                                       int B, int T, int step) {
-    __shared__ float Ws[3][32][33];
-    __shared__ float Hs[32][33];
-    const int dir = blockIdx.z;
-    const int j0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
-    const int t = dir == 0 ? step : T - 1 - step;
-    const int tid = threadIdx.x;
-    const int j = tid & 31, bg = tid >> 5;             // hidden unit, group of 4 utterances
-    float acc[3][4];
-#pragma unroll
-    for (int g = 0; g < 3; ++g)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[g][u] = 0.f;
+constexpr int kGruCluster = 8;
+constexpr int kGruUnits = 32;        // hidden units per CTA
+constexpr int kGruBatch = 32;        // utterances per cluster
+constexpr int kGruHStride = 256 + 4; // padded row of the staged hidden state (floats)
+constexpr size_t kGruSmemBytes = (size_t)(3 * 64 * kGruUnits * 4 + kGruBatch * kGruHStride) * sizeof(float);
+
+__global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(256, 1)
+    gru_layer_kernel(const float* __restrict__ gi,   // [B*T, 1536]
+                     const float* __restrict__ whh,  // [2][768][256]
+                     const float* __restrict__ bhh,  // [2][768]
+                     float* __restrict__ y,          // [B, T, 512]
+                     int B, int T) {
+    extern __shared__ __align__(16) float gsm[];
+    float* Wsh = gsm;                                   // [3][64][32][4]
+    float* Hs = gsm + 3 * 64 * kGruUnits * 4;           // [32][260]
+    const int tid = threadIdx.x, unit = tid & 31, bg = tid >> 5;
+    const int rank = blockIdx.x % kGruCluster;          // == cluster rank for a 1-D cluster
+    const int slice = blockIdx.x / kGruCluster;
+    const int dir = blockIdx.y;
+    const int j0 = rank * kGruUnits, b0 = slice * kGruBatch;
     const float* __restrict__ W = whh + (int64_t)dir * 768 * 256;
-    const float* __restrict__ hp = h_prev + (int64_t)dir * B * 256;
-    if (step > 0) {
-        for (int k0 = 0; k0 < 256; k0 += 32) {
-            __syncthreads();
-            for (int idx = tid; idx < 3 * 32 * 32; idx += 256) {
-                const int g = idx >> 10, rr = (idx >> 5) & 31, kk = idx & 31;
-                Ws[g][rr][kk] = __ldg(W + (int64_t)(g * 256 + j0 + rr) * 256 + k0 + kk);
+
+    for (int idx = tid; idx < 3 * kGruUnits * 256; idx += 256) {
+        const int k = idx & 255, u = (idx >> 8) & 31, g = idx >> 13;
+        Wsh[((g * 64 + (k >> 2)) * kGruUnits + u) * 4 + (k & 3)] = __ldg(W + (int64_t)(g * 256 + j0 + u) * 256 + k);
+    }
+    const float br = __ldg(bhh + dir * 768 + j0 + unit), bz = __ldg(bhh + dir * 768 + 256 + j0 + unit),
+                bn = __ldg(bhh + dir * 768 + 512 + j0 + unit);
+    float hprev[4] = {0.f, 0.f, 0.f, 0.f};              // this thread's own (unit, 4 utterances) state
+    __syncthreads();
+
+    for (int s = 0; s < T; ++s) {
+        const int t = dir == 0 ? s : T - 1 - s;
+        // gate pre-activations from the input projection: issue the loads before the matrix product
+        float g_in[3][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int bb = b0 + bg * 4 + u;
+            const float* __restrict__ gp = gi + ((int64_t)(bb < B ? bb : B - 1) * T + t) * 1536 + dir * 768 + j0 + unit;
+            g_in[0][u] = __ldg(gp);
+            g_in[1][u] = __ldg(gp + 256);
+            g_in[2][u] = __ldg(gp + 512);
+        }
+        float acc[3][4];
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[g][u] = 0.f;
+        if (s > 0) {
+            const int tp = dir == 0 ? t - 1 : t + 1;
+            // stage h_{s-1} of the whole slice: 32 rows x 1 KB, written by the cluster's CTAs in the last step
+            for (int idx = tid; idx < kGruBatch * 64; idx += 256) {
+                const int row = idx >> 6, c4 = idx & 63;
+                const int bb = b0 + row;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bb < B) v = __ldcg(reinterpret_cast<const float4*>(y + ((int64_t)bb * T + tp) * 512 + dir * 256) + c4);
+                *reinterpret_cast<float4*>(Hs + row * kGruHStride + 4 * c4) = v;
             }
-            for (int idx = tid; idx < 32 * 32; idx += 256) {
-                const int bb = idx >> 5, kk = idx & 31;
-                Hs[bb][kk] = (b0 + bb < B) ? hp[(int64_t)(b0 + bb) * 256 + k0 + kk] : 0.f;
-            }
             __syncthreads();
-#pragma unroll 8
-            for (int kk = 0; kk < 32; ++kk) {
-                const float w0 = Ws[0][j][kk], w1 = Ws[1][j][kk], w2 = Ws[2][j][kk];
+            const float4* __restrict__ w4 = reinterpret_cast<const float4*>(Wsh) + unit;
+            const float* __restrict__ hrow = Hs + (bg * 4) * kGruHStride;
+#pragma unroll 4
+            for (int k4 = 0; k4 < 64; ++k4) {
+                const float4 w0 = w4[(0 * 64 + k4) * kGruUnits], w1 = w4[(1 * 64 + k4) * kGruUnits],
+                             w2 = w4[(2 * 64 + k4) * kGruUnits];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const float hv = Hs[bg * 4 + u][kk];
-                    acc[0][u] = fmaf(w0, hv, acc[0][u]);
-                    acc[1][u] = fmaf(w1, hv, acc[1][u]);
-                    acc[2][u] = fmaf(w2, hv, acc[2][u]);
+                    const float4 h = *reinterpret_cast<const float4*>(hrow + u * kGruHStride + 4 * k4);
+                    acc[0][u] = fmaf(w0.w, h.w, fmaf(w0.z, h.z, fmaf(w0.y, h.y, fmaf(w0.x, h.x, acc[0][u]))));
+                    acc[1][u] = fmaf(w1.w, h.w, fmaf(w1.z, h.z, fmaf(w1.y, h.y, fmaf(w1.x, h.x, acc[1][u]))));
+                    acc[2][u] = fmaf(w2.w, h.w, fmaf(w2.z, h.z, fmaf(w2.y, h.y, fmaf(w2.x, h.x, acc[2][u]))));
                 }
             }
         }
-    }
-    const float br = __ldg(bhh + dir * 768 + j0 + j), bz = __ldg(bhh + dir * 768 + 256 + j0 + j),
-                bn = __ldg(bhh + dir * 768 + 512 + j0 + j);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const int bb = b0 + bg * 4 + u;
-        if (bb >= B) continue;
-        const float* __restrict__ g = gi + ((int64_t)bb * T + t) * 1536 + dir * 768 + j0 + j;
-        const float r = 1.f / (1.f + expf(-(g[0] + acc[0][u] + br)));
-        const float z = 1.f / (1.f + expf(-(g[256] + acc[1][u] + bz)));
-        const float n = tanhf(g[512] + r * (acc[2][u] + bn));
-        const float hprev = step > 0 ? hp[(int64_t)bb * 256 + j0 + j] : 0.f;
-        const float hn = (1.f - z) * n + z * hprev;
-        h_next[((int64_t)dir * B + bb) * 256 + j0 + j] = hn;
-        y[((int64_t)bb * T + t) * 512 + dir * 256 + j0 + j] = hn;
+        for (int u = 0; u < 4; ++u) {
+            const int bb = b0 + bg * 4 + u;
+            const float r = 1.f / (1.f + expf(-(g_in[0][u] + acc[0][u] + br)));
+            const float z = 1.f / (1.f + expf(-(g_in[1][u] + acc[1][u] + bz)));
+            const float n = tanhf(g_in[2][u] + r * (acc[2][u] + bn));
+            const float hn = (1.f - z) * n + z * hprev[u];
+            hprev[u] = hn;
+            if (bb < B) y[((int64_t)bb * T + t) * 512 + dir * 256 + j0 + unit] = hn;
+        }
+        // publish this step's h' to the 7 peers (and make sure nobody still reads Hs) before the next step
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     }
 }
 
@@ -584,13 +620,10 @@ int model_forward_chunk(sir_model* m, const Workspace& ws, const float* feat, in
         }
         SIR_CHECK_LAUNCH("gemm_nt_bias_kernel");
         ProfScope ps(l == 0 ? "gru_l0_recurrence" : "gru_l1_recurrence", st);
-        float* h0 = ws.h;
-        float* h1 = ws.h + (size_t)2 * B * 256;
-        for (int s = 0; s < Tg; ++s) {
-            dim3 sgrid(256 / 32, (unsigned)((B + 31) / 32), 2);
-            gru_step_kernel<<<sgrid, 256, 0, st>>>(ws.gi, m->whh[l], m->bhh[l], (s & 1) ? h1 : h0, (s & 1) ? h0 : h1,
-                                                   ys[l], B, Tg, s);
-            SIR_CHECK_LAUNCH("gru_step_kernel");
+        {
+            dim3 rgrid((unsigned)(kGruCluster * ((B + kGruBatch - 1) / kGruBatch)), 2);
+            gru_layer_kernel<<<rgrid, 256, kGruSmemBytes, st>>>(ws.gi, m->whh[l], m->bhh[l], ys[l], B, Tg);
+            SIR_CHECK_LAUNCH("gru_layer_kernel");
         }
         x = ys[l];
         in_sz = 512;
@@ -618,6 +651,8 @@ static int model_prepare(sir_model* m, int batch, int n_frames, Workspace& ws, i
         SIR_CUDA(cudaFuncSetAttribute(conv3x3_bn_relu_pool_kernel<32, 64, false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)((180 * 36 + 32 * 64) * sizeof(float))));
+        SIR_CUDA(cudaFuncSetAttribute(gru_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kGruSmemBytes));
         attr_done = true;
     }
     chunk = batch < kModelChunk ? batch : kModelChunk;

@@ -78,7 +78,10 @@ constexpr int kOffReduce = kOffTile + kMaxMels * kTileStride;
 constexpr int kFeSmemFloats = kOffReduce + 64;
 constexpr size_t kFeSmemBytes = (size_t)kFeSmemFloats * sizeof(float);
 static_assert(kOffScratch % 4 == 0 && kOffTile % 4 == 0, "16-byte alignment of vector regions");
-static_assert(3 * (kFeSmemBytes + 1024) <= 232448, "three CTAs per SM");
+#ifndef SIR_FE_MIN_CTAS
+#define SIR_FE_MIN_CTAS 3
+#endif
+static_assert(SIR_FE_MIN_CTAS * (kFeSmemBytes + 1024) <= 232448, "resident CTAs per SM");
 
 struct FrontendParams {
     const float* wave;
@@ -113,7 +116,7 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-__global__ void __launch_bounds__(kFeThreads, 3) logmel_frontend_kernel(const FrontendParams p) {
+__global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_kernel(const FrontendParams p) {
     extern __shared__ __align__(16) float smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
