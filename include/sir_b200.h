@@ -126,6 +126,14 @@ int64_t sir_model_weight_count(const sir_model* m);
 int sir_model_forward(sir_model* m, const float* d_features, int batch, int n_frames, float* d_logits,
                       void* stream);
 
+/* sir_gemm_nt_split_f16: C[M,N] = A[M,K] W[N,K]^T + bias[N] on the 5th-gen tensor cores (tcgen05, TMEM
+ * accumulators, TMA-staged operands) with the 3-pass fp16 hi/lo operand split that keeps fp32-level accuracy.
+ * It is the contraction behind nn.GRU's input projection (models/models.py:60) and, in implicit-GEMM form,
+ * conv2/conv3 (:51-52); exported stand-alone so that tests can check it against an fp64 matmul.
+ * N % 128 == 0 and K % 64 == 0.  All pointers are device pointers to fp32. */
+int sir_gemm_nt_split_f16(const float* d_a, const float* d_w, const float* d_bias, float* d_c, int M, int N, int K,
+                          void* stream);
+
 /* sir_pipeline_forward: frontend (SIR_OUT_LOGMEL_NORM, pad/trim to out_frames) + classifier in one call.
  * d_features may be NULL (features then live only in the model's workspace). */
 int sir_pipeline_forward(sir_frontend* fe, sir_model* m, const float* d_wave, int64_t wave_stride,

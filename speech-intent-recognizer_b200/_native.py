@@ -38,6 +38,7 @@ SIGNATURES = {
     "sir_model_load_weights": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "sir_model_weight_count": (c_int64, [c_void_p]),
     "sir_model_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "sir_gemm_nt_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "sir_pipeline_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p]),
 }
@@ -177,6 +178,19 @@ def features_finalize(feat, out_frames, frames=None, masks=None):
     check(load_library().sir_features_finalize(ptr(feat), B, M, T, ptr(frames), ptr(masks), out_frames, ptr(out),
                                                stream_ptr()), "sir_features_finalize")
     return out
+
+
+def gemm_nt_split_f16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """``a [M,K] @ w[N,K].T + bias`` on tcgen05 with the fp16 hi/lo split (fp32 in/out, CUDA tensors)."""
+    for t, n in ((a, "a"), (w, "w"), (bias, "bias")):
+        require_cuda(t, n)
+    a, w, bias = a.contiguous(), w.contiguous(), bias.contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    c = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    check(load_library().sir_gemm_nt_split_f16(ptr(a), ptr(w), ptr(bias), ptr(c), M, N, K, stream_ptr()),
+          "sir_gemm_nt_split_f16")
+    return c
 
 
 class Model:

@@ -1,0 +1,371 @@
+// tcgen05 contractions of the classifier: GRU input projections (plain GEMM) and conv2/conv3 (implicit GEMM),
+// each as a 3-pass fp16 hi/lo split with fp32 accumulation in TMEM (tc_common.cuh explains the numerics).
+//
+// Replaces the dense contractions behind models/models.py:51-52 (conv2/conv3 + BN + ReLU + pool) and :60
+// (nn.GRU's W_ih x for all time steps) - 88 % of the classifier's 400.6 MFLOP per utterance.
+//
+// One CTA computes one 128-row output tile; 6 warps:
+//   warp 0   : TMA producer - per k-block, four bulk-tensor loads (A_hi, A_lo, B_hi, B_lo) into a
+//              STAGES-deep shared-memory ring, completion on a `full` mbarrier (expect_tx);
+//   warp 1   : allocates TMEM, one elected lane issues tcgen05.mma (128 x BLOCK_N x 16, kind::f16) - three
+//              per 16-wide k-slice: hi.hi, hi.lo, lo.hi - and tcgen05.commit's the stage's `empty` mbarrier;
+//   warps 2-5: epilogue - tcgen05.ld the accumulator (TMEM lane = tile row, column = output channel),
+//              GEMM : + bias -> fp32 [M, N];
+//              CONV : 2x2 max-pool by warp shuffles (the tile is 16 x 8 pixels, so a warp's 32 rows are a
+//                     2 x 16 pixel patch and pooling partners are lanes ^1 and ^16), + BN shift, ReLU,
+//                     split to fp16 hi/lo, channels-last store - directly the next contraction's A operand.
+//
+// Implicit GEMM: the activation is a 4-D TMA tensor (C, W, H, B); tap (kh, kw) of the 3x3 stencil is the box
+// (C, 16, 8, 1) at (0, x0+kw-1, y0+kh-1, b) - the halo and the image border come for free from TMA's
+// out-of-bounds zero fill, and the box lands in shared memory exactly as the K-major, swizzled UMMA operand
+// (128 rows of C fp16).  K-blocks = 9 taps; weights are stored [tap][C_out][C_in].
+#include <cstdio>
+#include <cstring>
+
+#include "sir_common.cuh"
+#include "tc_common.cuh"
+
+namespace sir {
+namespace tc {
+
+constexpr int kTcThreads = 192;
+enum { kModeGemm = 0, kModeConv = 1 };
+
+struct TcParams {
+    int num_kblocks;
+    // GEMM
+    int M, N;
+    const float* bias;
+    float* C;
+    // CONV (input dims H x W, output pooled H/2 x W/2)
+    int H, W, tiles_x;
+    const float* shift;
+    __half* out_hi;
+    __half* out_lo;
+    int out_whc;        // 0: [B][H2][W2][C]   1: [B][W2][H2][C]  (the GRU input order: time-major, then mel, then channel)
+};
+
+template <int MODE, int BLOCK_N, int BLOCK_K, int STAGES>
+struct TcLayout {
+    static constexpr int kSwizzle = BLOCK_K * 2;
+    static constexpr int kABytes = 128 * BLOCK_K * 2;
+    static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+    static constexpr int kBarrierOffset = STAGES * kStageBytes;
+    static constexpr int kSmemBytes = kBarrierOffset + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+    static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "tiles must keep 1024-byte alignment");
+};
+
+template <int MODE, int BLOCK_N, int BLOCK_K, int STAGES>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    tc_contract_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                       const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                       const TcParams p) {
+    using L = TcLayout<MODE, BLOCK_N, BLOCK_K, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarrierOffset);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates
+    int m0 = 0, n0 = 0, img = 0, x0 = 0, y0 = 0;
+    if constexpr (MODE == kModeGemm) {
+        n0 = blockIdx.x * BLOCK_N;
+        m0 = blockIdx.y * 128;
+    } else {
+        img = blockIdx.y;
+        y0 = (blockIdx.x / p.tiles_x) * 8;
+        x0 = (blockIdx.x % p.tiles_x) * 16;
+    }
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_a_hi);
+        prefetch_tmap(&tm_a_lo);
+        prefetch_tmap(&tm_b_hi);
+        prefetch_tmap(&tm_b_lo);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<BLOCK_N>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < p.num_kblocks; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                uint8_t* st = smem + s * L::kStageBytes;
+                mbar_arrive_expect_tx(&full[s], L::kStageBytes);
+                if constexpr (MODE == kModeGemm) {
+                    tma_load_2d(st, &tm_a_hi, &full[s], kb * BLOCK_K, m0);
+                    tma_load_2d(st + L::kABytes, &tm_a_lo, &full[s], kb * BLOCK_K, m0);
+                    tma_load_2d(st + 2 * L::kABytes, &tm_b_hi, &full[s], kb * BLOCK_K, n0);
+                    tma_load_2d(st + 2 * L::kABytes + L::kBBytes, &tm_b_lo, &full[s], kb * BLOCK_K, n0);
+                } else {
+                    const int kh = kb / 3, kw = kb - kh * 3;
+                    tma_load_4d(st, &tm_a_hi, &full[s], 0, x0 + kw - 1, y0 + kh - 1, img);
+                    tma_load_4d(st + L::kABytes, &tm_a_lo, &full[s], 0, x0 + kw - 1, y0 + kh - 1, img);
+                    tma_load_2d(st + 2 * L::kABytes, &tm_b_hi, &full[s], 0, kb * BLOCK_N);
+                    tma_load_2d(st + 2 * L::kABytes + L::kBBytes, &tm_b_lo, &full[s], 0, kb * BLOCK_N);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N);
+            for (int kb = 0; kb < p.num_kblocks; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t base = smem_u32(smem + s * L::kStageBytes);
+                const uint64_t a_hi = make_kmajor_desc<L::kSwizzle>(base);
+                const uint64_t a_lo = make_kmajor_desc<L::kSwizzle>(base + L::kABytes);
+                const uint64_t b_hi = make_kmajor_desc<L::kSwizzle>(base + 2 * L::kABytes);
+                const uint64_t b_lo = make_kmajor_desc<L::kSwizzle>(base + 2 * L::kABytes + L::kBBytes);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K; k += 16) {
+                    umma_f16(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(b_hi, k), idesc, (kb | k) ? 1u : 0u);
+                    umma_f16(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(b_lo, k), idesc, 1u);
+                    umma_f16(tmem_base, desc_advance_k(a_lo, k), desc_advance_k(b_hi, k), idesc, 1u);
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        // ---- epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) ------------------------------------------
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        if constexpr (MODE == kModeGemm) {
+            const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                float v[32];
+                tmem_ld_32x32(trow + c, v);
+                if (m < p.M) {
+                    float4* dst = reinterpret_cast<float4*>(p.C + (int64_t)m * p.N + n0 + c);
+                    const float4* bs = reinterpret_cast<const float4*>(p.bias + n0 + c);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b4 = __ldg(bs + i);
+                        dst[i] = make_float4(v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z,
+                                             v[4 * i + 3] + b4.w);
+                    }
+                }
+            }
+        } else {
+            // rows of this warp: dy = 2q + (lane >> 4), x = lane & 15  ->  one 2 x 16 pixel patch
+            const int H2 = p.H / 2, W2 = p.W / 2;
+            const int y2 = y0 / 2 + q, x2 = x0 / 2 + ((lane & 15) >> 1);
+            const bool writer = ((lane & 17) == 0) && y2 < H2 && x2 < W2;
+            const int64_t pix = p.out_whc ? ((int64_t)img * W2 + x2) * H2 + y2 : ((int64_t)img * H2 + y2) * W2 + x2;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                float v[32];
+                tmem_ld_32x32(trow + c, v);
+                uint32_t hi2[16], lo2[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float a = v[i], b = v[i + 1];
+                    a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
+                    b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, 1));
+                    a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 16));
+                    b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, 16));
+                    a = fmaxf(a + __ldg(p.shift + c + i), 0.f);
+                    b = fmaxf(b + __ldg(p.shift + c + i + 1), 0.f);
+                    __half ah, al, bh, bl;
+                    split_f16(a, ah, al);
+                    split_f16(b, bh, bl);
+                    hi2[i >> 1] = (uint32_t)__half_as_ushort(ah) | ((uint32_t)__half_as_ushort(bh) << 16);
+                    lo2[i >> 1] = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
+                }
+                if (writer) {
+                    uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * BLOCK_N + c);
+                    uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * BLOCK_N + c);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        dh[i] = make_uint4(hi2[4 * i], hi2[4 * i + 1], hi2[4 * i + 2], hi2[4 * i + 3]);
+                        dl[i] = make_uint4(lo2[4 * i], lo2[4 * i + 1], lo2[4 * i + 2], lo2[4 * i + 3]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<BLOCK_N>(tmem_base);
+    }
+}
+
+__global__ void split_f16_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo,
+                                 int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        __half h, l;
+        split_f16(in[i], h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// fp16 tensor of `rank` dims (innermost first), box of the same rank, swizzle = inner box bytes (64 or 128).
+static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(SIR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[4], gstride[3];
+    cuuint32_t bdim[4], estride[4];
+    uint64_t stride = 2;
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estride[i] = 1;
+        stride *= dims[i];
+        if (i < rank - 1) gstride[i] = stride;
+    }
+    const uint32_t inner_bytes = box[0] * 2;
+    const CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE;
+    if (sw == CU_TENSOR_MAP_SWIZZLE_NONE) return fail(SIR_ERR_INVALID, "make_tmap: inner box must be 64 or 128 bytes");
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, bdim,
+                    estride, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SIR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SIR_OK;
+}
+
+template <int MODE, int BLOCK_N, int BLOCK_K, int STAGES>
+static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                     const TcParams& p, dim3 grid, cudaStream_t st, const char* name) {
+    using L = TcLayout<MODE, BLOCK_N, BLOCK_K, STAGES>;
+    auto kern = tc_contract_kernel<MODE, BLOCK_N, BLOCK_K, STAGES>;
+    static bool attr = false;
+    if (!attr) {
+        SIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes));
+        attr = true;
+    }
+    {
+        ProfScope ps(name, st);
+        kern<<<grid, kTcThreads, L::kSmemBytes, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    }
+    SIR_CHECK_LAUNCH(name);
+    return SIR_OK;
+}
+
+// C[M,N] = A[M,K] W[N,K]^T + bias ; operands as fp16 hi/lo pairs.  N % 128 == 0, K % 64 == 0.
+int tc_gemm_nt(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo, const float* bias,
+               float* C, int M, int N, int K, cudaStream_t st, const char* name) {
+    if (N % 128 || K % 64) return fail(SIR_ERR_INVALID, "tc_gemm_nt: N %% 128 and K %% 64 required (N %d, K %d)", N, K);
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    const uint64_t adims[2] = {(uint64_t)K, (uint64_t)M}, bdims[2] = {(uint64_t)K, (uint64_t)N};
+    const uint32_t abox[2] = {64, 128}, bbox[2] = {64, 128};
+    int rc;
+    if ((rc = make_tmap(&ta_hi, a_hi, 2, adims, abox)) || (rc = make_tmap(&ta_lo, a_lo, 2, adims, abox)) ||
+        (rc = make_tmap(&tb_hi, w_hi, 2, bdims, bbox)) || (rc = make_tmap(&tb_lo, w_lo, 2, bdims, bbox)))
+        return rc;
+    TcParams p{};
+    p.num_kblocks = K / 64;
+    p.M = M;
+    p.N = N;
+    p.bias = bias;
+    p.C = C;
+    dim3 grid((unsigned)(N / 128), (unsigned)((M + 127) / 128));
+    return launch_tc<kModeGemm, 128, 64, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, st, name);
+}
+
+// 3x3 conv (s1, p1) + shift + ReLU + 2x2 max-pool on channels-last fp16 hi/lo activations [B,H,W,CIN];
+// weights [9][COUT][CIN] hi/lo (BN scale folded); output [B,H/2,W/2,COUT] (or [B,W/2,H/2,COUT]) hi/lo.
+template <int CIN, int COUT>
+int tc_conv3x3(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
+               __half* out_hi, __half* out_lo, int B, int H, int W, int out_whc, cudaStream_t st, const char* name) {
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    const uint64_t adims[4] = {(uint64_t)CIN, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint32_t abox[4] = {(uint32_t)CIN, 16, 8, 1};
+    const uint64_t bdims[2] = {(uint64_t)CIN, (uint64_t)(9 * COUT)};
+    const uint32_t bbox[2] = {(uint32_t)CIN, (uint32_t)COUT};
+    int rc;
+    if ((rc = make_tmap(&ta_hi, in_hi, 4, adims, abox)) || (rc = make_tmap(&ta_lo, in_lo, 4, adims, abox)) ||
+        (rc = make_tmap(&tb_hi, w_hi, 2, bdims, bbox)) || (rc = make_tmap(&tb_lo, w_lo, 2, bdims, bbox)))
+        return rc;
+    TcParams p{};
+    p.num_kblocks = 9;
+    p.H = H;
+    p.W = W;
+    p.tiles_x = (W + 15) / 16;
+    p.shift = shift;
+    p.out_hi = out_hi;
+    p.out_lo = out_lo;
+    p.out_whc = out_whc;
+    const int tiles_y = (H + 7) / 8;
+    dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)B);
+    return launch_tc<kModeConv, COUT, CIN, (CIN == 32 ? 4 : 3)>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, st, name);
+}
+
+template int tc_conv3x3<32, 64>(const __half*, const __half*, const __half*, const __half*, const float*, __half*,
+                                __half*, int, int, int, int, cudaStream_t, const char*);
+template int tc_conv3x3<64, 128>(const __half*, const __half*, const __half*, const __half*, const float*, __half*,
+                                 __half*, int, int, int, int, cudaStream_t, const char*);
+
+int split_f16_async(const float* in, __half* hi, __half* lo, int64_t n, cudaStream_t st) {
+    if (n <= 0) return SIR_OK;
+    const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    split_f16_kernel<<<blocks, 256, 0, st>>>(in, hi, lo, n);
+    SIR_CHECK_LAUNCH("split_f16_kernel");
+    return SIR_OK;
+}
+
+}  // namespace tc
+}  // namespace sir
+
+// ---- C ABI: the split-precision tensor-core GEMM as a stand-alone operator --------------------------------------
+using namespace sir;
+
+extern "C" int sir_gemm_nt_split_f16(const float* d_a, const float* d_w, const float* d_bias, float* d_c, int M, int N,
+                                     int K, void* stream) {
+    if (!d_a || !d_w || !d_bias || !d_c || M < 1) return fail(SIR_ERR_INVALID, "sir_gemm_nt_split_f16: bad arguments");
+    static DeviceBuffer scratch;
+    const size_t na = (size_t)M * K, nw = (size_t)N * K;
+    int rc = scratch.reserve((na + nw) * 2 * sizeof(__half) + 1024);
+    if (rc != SIR_OK) return rc;
+    __half* a_hi = (__half*)scratch.ptr;
+    __half* a_lo = a_hi + na;
+    __half* w_hi = a_lo + na;
+    __half* w_lo = w_hi + nw;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = tc::split_f16_async(d_a, a_hi, a_lo, (int64_t)na, st))) return rc;
+    if ((rc = tc::split_f16_async(d_w, w_hi, w_lo, (int64_t)nw, st))) return rc;
+    return tc::tc_gemm_nt(a_hi, a_lo, w_hi, w_lo, d_bias, d_c, M, N, K, st, "gemm_nt_split_f16");
+}

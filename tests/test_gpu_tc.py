@@ -1,0 +1,23 @@
+"""GPU tests of the tcgen05 split-precision contraction against an fp64 matmul."""
+import importlib
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+native = importlib.import_module("speech-intent-recognizer_b200._native")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 192), (6400, 1536, 1024), (275, 256, 512), (1, 128, 64)])
+def test_gemm_nt_split_f16_matches_fp64(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + K)
+    a = torch.randn(M, K, device="cuda", generator=g) * 3.0
+    a[:, ::7] *= 1e-3                                   # mixed magnitudes exercise the lo parts
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    bias = torch.randn(N, device="cuda", generator=g)
+    got = native.gemm_nt_split_f16(a, w, bias)
+    want = (a.double() @ w.double().t() + bias.double())
+    err = (got.double() - want).abs().max().item()
+    scale = want.abs().max().item()
+    # fp32 GEMM accuracy is ~1e-6 of the scale; a single fp16 pass would be ~1e-3
+    assert err < 2e-6 * scale * (K / 64) ** 0.5 + 1e-6, (err, scale)
