@@ -10,23 +10,36 @@
 // (the K dimension of the implicit GEMM); conv3's epilogue writes the GRU input [B, T/8, 128*H/8] directly,
 // so the reference's permute+contiguous copy (K9) never happens.
 //
-// These are the parity-reference kernels of the library (every op in fp32 FMA, fp32 accumulate); the
-// tensor-core (tcgen05) contractions in gemm_tc.cu replace conv2/conv3/GRU-input GEMMs when enabled.
+// conv2, conv3 and the two GRU input projections (88 % of the FLOPs) run on the tcgen05 tensor cores
+// (gemm_tc.cu) as 3-pass fp16 hi/lo contractions; every producer therefore writes its activations as an
+// fp16 (hi, lo) pair - the same 4 bytes per value as fp32.  conv1 (K = 9), the GRU recurrence and the
+// attention/fc head stay on the fp32 CUDA cores.
 #include <cmath>
 #include <cstring>
 #include <vector>
 
 #include "sir_common.cuh"
+#include "tc_common.cuh"
 
 namespace sir {
 
+namespace tc {
+int tc_gemm_nt(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo, const float* bias,
+               float* C, int M, int N, int K, cudaStream_t st, const char* name);
+template <int CIN, int COUT>
+int tc_conv3x3(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
+               __half* out_hi, __half* out_lo, int B, int H, int W, int out_whc, cudaStream_t st, const char* name);
+}  // namespace tc
+
 // ---------------------------------------------------------------------------------------------------------
-// conv1 (C_in = 1): one thread per pooled pixel, all 32 output channels; output NHWC [B, H/2, W/2, 32].
+// conv1 (C_in = 1): one thread per pooled pixel, all 32 output channels; output NHWC [B, H/2, W/2, 32] as
+// an fp16 (hi, lo) pair - the A operand of conv2's implicit GEMM.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) conv1_bn_relu_pool_kernel(const float* __restrict__ feat,
                                                                  const float* __restrict__ w1,      // [32][9] folded
                                                                  const float* __restrict__ shift1,  // [32]
-                                                                 float* __restrict__ out, int H, int W) {
+                                                                 __half* __restrict__ out_hi,
+                                                                 __half* __restrict__ out_lo, int H, int W) {
     __shared__ float s_w[32 * 9];
     __shared__ float s_shift[32];
     for (int i = threadIdx.x; i < 288; i += 128) s_w[i] = w1[i];
@@ -48,7 +61,9 @@ __global__ void __launch_bounds__(128) conv1_bn_relu_pool_kernel(const float* __
             patch[r][c] = (gh >= 0 && gh < H && gw >= 0 && gw < W) ? __ldg(img + (int64_t)gh * W + gw) : 0.f;
         }
     }
-    float4* __restrict__ dst = reinterpret_cast<float4*>(out + (((int64_t)b * H2 + h2) * W2 + w2) * 32);
+    const int64_t opix = (((int64_t)b * H2 + h2) * W2 + w2) * 32;
+    uint2* __restrict__ dst_hi = reinterpret_cast<uint2*>(out_hi + opix);
+    uint2* __restrict__ dst_lo = reinterpret_cast<uint2*>(out_lo + opix);
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4) {
         float res[4];
@@ -68,182 +83,13 @@ __global__ void __launch_bounds__(128) conv1_bn_relu_pool_kernel(const float* __
                 }
             res[cc] = fmaxf(fmaxf(fmaxf(o00, o01), fmaxf(o10, o11)) + s_shift[c4 * 4 + cc], 0.f);
         }
-        dst[c4] = make_float4(res[0], res[1], res[2], res[3]);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// conv2 / conv3: direct 3x3 convolution as an implicit GEMM on CUDA cores.
-// CTA tile: 8 x 16 conv outputs x all COUT; 256 threads = 16 pixel groups (2x4 pixels) x 16 channel groups.
-// ---------------------------------------------------------------------------------------------------------
-template <int CIN, int COUT, bool GRU_LAYOUT>
-__global__ void __launch_bounds__(256) conv3x3_bn_relu_pool_kernel(const float* __restrict__ in,     // [B,H,W,CIN]
-                                                                   const float* __restrict__ wt,     // [9][CIN][COUT]
-                                                                   const float* __restrict__ shift,  // [COUT]
-                                                                   float* __restrict__ out, int H, int W) {
-    constexpr int PSTRIDE = CIN + 4;                 // padded pixel stride: neighbouring pixel groups hit other banks
-    constexpr int CPT = COUT / 16;                   // channels per thread (4 or 8)
-    constexpr int NV = CPT / 4;
-    extern __shared__ __align__(16) float smem[];
-    float* patch = smem;                             // [10][18][PSTRIDE]
-    float* wtap = smem + 10 * 18 * PSTRIDE;          // [CIN][COUT]
-    const int tid = threadIdx.x;
-    const int b = blockIdx.z;
-    const int h0 = blockIdx.y * 8, w0 = blockIdx.x * 16;
-    const int H2 = H / 2, W2 = W / 2;
-
-    for (int idx = tid; idx < 180 * (CIN / 4); idx += 256) {
-        const int pi = idx / (CIN / 4), c4 = idx - pi * (CIN / 4);
-        const int r = pi / 18, c = pi - r * 18;
-        const int gh = h0 - 1 + r, gw = w0 - 1 + c;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gh >= 0 && gh < H && gw >= 0 && gw < W)
-            v = __ldg(reinterpret_cast<const float4*>(in + (((int64_t)b * H + gh) * W + gw) * CIN) + c4);
-        *reinterpret_cast<float4*>(patch + pi * PSTRIDE + 4 * c4) = v;
-    }
-
-    const int pg = tid >> 4, cgp = tid & 15;
-    const int pr = pg >> 2, pc = pg & 3;
-    float acc[8][CPT];
+        __half h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) acc[i][j] = 0.f;
-
-    for (int tap = 0; tap < 9; ++tap) {
-        __syncthreads();                             // previous tap's weights consumed (and patch visible)
-        {
-            const float4* __restrict__ src = reinterpret_cast<const float4*>(wt + (int64_t)tap * CIN * COUT);
-            for (int idx = tid; idx < CIN * COUT / 4; idx += 256) reinterpret_cast<float4*>(wtap)[idx] = __ldg(src + idx);
-        }
-        __syncthreads();
-        const int kh = tap / 3, kw = tap - kh * 3;
-#pragma unroll 2
-        for (int c4 = 0; c4 < CIN / 4; ++c4) {
-            float4 a[8];
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    a[r * 4 + c] = *reinterpret_cast<const float4*>(
-                        patch + ((pr * 2 + r + kh) * 18 + (pc * 4 + c + kw)) * PSTRIDE + 4 * c4);
-#pragma unroll
-            for (int ci = 0; ci < 4; ++ci) {
-                float w[CPT];
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    const float4 wv =
-                        *reinterpret_cast<const float4*>(wtap + (4 * c4 + ci) * COUT + 64 * v + 4 * cgp);
-                    w[4 * v] = wv.x;
-                    w[4 * v + 1] = wv.y;
-                    w[4 * v + 2] = wv.z;
-                    w[4 * v + 3] = wv.w;
-                }
-#pragma unroll
-                for (int px = 0; px < 8; ++px) {
-                    const float av = ci == 0 ? a[px].x : (ci == 1 ? a[px].y : (ci == 2 ? a[px].z : a[px].w));
-#pragma unroll
-                    for (int j = 0; j < CPT; ++j) acc[px][j] = fmaf(av, w[j], acc[px][j]);
-                }
-            }
-        }
-    }
-
-    // epilogue: + shift, ReLU, 2x2 max-pool (the thread's 2x4 pixels hold two complete windows)
-    const int h2 = h0 / 2 + pr;
-#pragma unroll
-    for (int win = 0; win < 2; ++win) {
-        const int w2 = w0 / 2 + pc * 2 + win;
-        if (h2 >= H2 || w2 >= W2) continue;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            float res[4];
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const int j = 4 * v + cc;
-                const float m = fmaxf(fmaxf(acc[2 * win][j], acc[2 * win + 1][j]),
-                                      fmaxf(acc[4 + 2 * win][j], acc[4 + 2 * win + 1][j]));
-                res[cc] = fmaxf(m + __ldg(shift + 64 * v + 4 * cgp + cc), 0.f);
-            }
-            const int ch = 64 * v + 4 * cgp;
-            if constexpr (GRU_LAYOUT) {              // out[b][w2][ch*H2 + h2]   (models/models.py:55-57)
-                float* dst = out + ((int64_t)b * W2 + w2) * (COUT * H2) + h2;
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) dst[(int64_t)(ch + cc) * H2] = res[cc];
-            } else {                                 // NHWC
-                *reinterpret_cast<float4*>(out + (((int64_t)b * H2 + h2) * W2 + w2) * COUT + ch) =
-                    make_float4(res[0], res[1], res[2], res[3]);
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// C[M,N] = A[M,K] * W[N,K]^T + bias[N]   (GRU input projections, both directions stacked along N)
-// 128x128 tile, BK = 8, 256 threads, 8x8 outputs per thread.
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gemm_nt_bias_kernel(const float* __restrict__ A, const float* __restrict__ Wt,
-                                                           const float* __restrict__ bias, float* __restrict__ C,
-                                                           int M, int N, int K) {
-    __shared__ __align__(16) float As[2][8][128 + 4];
-    __shared__ __align__(16) float Bs[2][8][128 + 4];
-    const int tid = threadIdx.x;
-    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
-    const int lrow = tid >> 1, lk = (tid & 1) * 4;       // each thread loads one float4 of A and one of W per k-tile
-    const int tx = tid & 15, ty = tid >> 4;
-    float acc[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    const int arow = m0 + lrow;
-    const float* __restrict__ ap = A + (int64_t)(arow < M ? arow : M - 1) * K + lk;
-    const float* __restrict__ bp = Wt + (int64_t)(n0 + lrow) * K + lk;
-    float4 av = __ldg(reinterpret_cast<const float4*>(ap));
-    float4 bv = __ldg(reinterpret_cast<const float4*>(bp));
-    const int nk = K / 8;
-    for (int kt = 0; kt < nk; ++kt) {
-        const int buf = kt & 1;
-        As[buf][lk + 0][lrow] = av.x;
-        As[buf][lk + 1][lrow] = av.y;
-        As[buf][lk + 2][lrow] = av.z;
-        As[buf][lk + 3][lrow] = av.w;
-        Bs[buf][lk + 0][lrow] = bv.x;
-        Bs[buf][lk + 1][lrow] = bv.y;
-        Bs[buf][lk + 2][lrow] = bv.z;
-        Bs[buf][lk + 3][lrow] = bv.w;
-        __syncthreads();
-        if (kt + 1 < nk) {
-            av = __ldg(reinterpret_cast<const float4*>(ap + (kt + 1) * 8));
-            bv = __ldg(reinterpret_cast<const float4*>(bp + (kt + 1) * 8));
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
-            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
-        }
-        // the next iteration writes the other buffer; one barrier per k-tile is enough with two buffers
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
-        if (m >= M) continue;
-#pragma unroll
-        for (int jv = 0; jv < 2; ++jv) {
-            const int n = n0 + jv * 64 + tx * 4;
-            const float4 bsv = __ldg(reinterpret_cast<const float4*>(bias + n));
-            *reinterpret_cast<float4*>(C + (int64_t)m * N + n) =
-                make_float4(acc[i][jv * 4 + 0] + bsv.x, acc[i][jv * 4 + 1] + bsv.y, acc[i][jv * 4 + 2] + bsv.z,
-                            acc[i][jv * 4 + 3] + bsv.w);
-        }
+        for (int cc = 0; cc < 4; ++cc) tc::split_f16(res[cc], h[cc], l[cc]);
+        dst_hi[c4] = make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+                                (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+        dst_lo[c4] = make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
+                                (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
     }
 }
 
@@ -272,7 +118,8 @@ __global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(256, 1)
                      const float* __restrict__ whh,  // [2][768][256]
                      const float* __restrict__ bhh,  // [2][768]
                      float* __restrict__ y,          // [B, T, 512]
-                     int B, int T) {
+                     __half* __restrict__ y_hi,      // optional fp16 (hi, lo) copy: the next layer's GEMM operand
+                     __half* __restrict__ y_lo, int B, int T) {
     extern __shared__ __align__(16) float gsm[];
     float* Wsh = gsm;                                   // [3][64][32][4]
     float* Hs = gsm + 3 * 64 * kGruUnits * 4;           // [32][260]
@@ -343,7 +190,16 @@ __global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(256, 1)
             const float n = tanhf(g_in[2][u] + r * (acc[2][u] + bn));
             const float hn = (1.f - z) * n + z * hprev[u];
             hprev[u] = hn;
-            if (bb < B) y[((int64_t)bb * T + t) * 512 + dir * 256 + j0 + unit] = hn;
+            if (bb < B) {
+                const int64_t o = ((int64_t)bb * T + t) * 512 + dir * 256 + j0 + unit;
+                y[o] = hn;
+                if (y_hi) {
+                    __half h, l;
+                    tc::split_f16(hn, h, l);
+                    y_hi[o] = h;
+                    y_lo[o] = l;
+                }
+            }
         }
         // publish this step's h' to the 7 peers (and make sure nobody still reads Hs) before the next step
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
@@ -413,13 +269,16 @@ struct sir_model {
     int num_classes = 31, n_mels = 64, gru_in = 1024;
     bool loaded = false;
     float att_b = 0.f;
-    DeviceBuffer weights;        // repacked parameters
+    DeviceBuffer weights;        // repacked fp32 parameters
+    DeviceBuffer weights_h;      // fp16 (hi, lo) operands of the tensor-core contractions
     DeviceBuffer work;           // activations
-    // device pointers into `weights`
-    float *w1 = nullptr, *sh1 = nullptr, *w2 = nullptr, *sh2 = nullptr, *w3 = nullptr, *sh3 = nullptr;
-    float *wih[2] = {nullptr, nullptr}, *bih[2] = {nullptr, nullptr}, *whh[2] = {nullptr, nullptr},
-          *bhh[2] = {nullptr, nullptr};
+    // fp32 pointers into `weights`
+    float *w1 = nullptr, *sh1 = nullptr, *sh2 = nullptr, *sh3 = nullptr;
+    float *bih[2] = {nullptr, nullptr}, *whh[2] = {nullptr, nullptr}, *bhh[2] = {nullptr, nullptr};
     float *att_w = nullptr, *fc_w = nullptr, *fc_b = nullptr;
+    // fp16 pointers into `weights_h`: conv weights [tap][C_out][C_in] (BN scale folded), W_ih [1536][K]
+    __half *w2_hi = nullptr, *w2_lo = nullptr, *w3_hi = nullptr, *w3_lo = nullptr;
+    __half *wih_hi[2] = {nullptr, nullptr}, *wih_lo[2] = {nullptr, nullptr};
 };
 
 static int64_t model_weight_count(int num_classes, int n_mels) {
@@ -451,6 +310,7 @@ extern "C" int sir_model_create(sir_model** out, int num_classes, int n_mels) {
 extern "C" void sir_model_destroy(sir_model* m) {
     if (!m) return;
     m->weights.release();
+    m->weights_h.release();
     m->work.release();
     delete m;
 }
@@ -458,6 +318,24 @@ extern "C" void sir_model_destroy(sir_model* m) {
 extern "C" int64_t sir_model_weight_count(const sir_model* m) {
     return m ? model_weight_count(m->num_classes, m->n_mels) : 0;
 }
+
+namespace {
+
+struct HalfPack {                       // host staging of the fp16 (hi, lo) arrays, 128-byte aligned sections
+    std::vector<__half> data;
+    size_t add(const std::vector<float>& v, bool lo) {
+        while (data.size() % 64) data.push_back(__float2half_rn(0.f));
+        const size_t off = data.size();
+        for (float x : v) {
+            x = std::fmin(std::fmax(x, -65504.f), 65504.f);
+            const __half h = __float2half_rn(x);
+            data.push_back(lo ? __float2half_rn(x - __half2float(h)) : h);
+        }
+        return off;
+    }
+};
+
+}  // namespace
 
 extern "C" int sir_model_load_weights(sir_model* m, const float* weights, int64_t count, float bn_eps, void* stream) {
     if (!m || !weights) return fail(SIR_ERR_INVALID, "sir_model_load_weights: NULL argument");
@@ -469,9 +347,8 @@ extern "C" int sir_model_load_weights(sir_model* m, const float* weights, int64_
     SIR_CUDA(cudaStreamSynchronize(st));
     std::vector<float> h((size_t)count);
     SIR_CUDA(cudaMemcpy(h.data(), weights, (size_t)count * sizeof(float), cudaMemcpyDefault));
-    const int gin = m->gru_in, C = m->num_classes;
-    // walk the flat buffer in state_dict_spec order
-    const float* p = h.data();
+    const int gin = m->gru_in, C = m->num_classes, H8 = m->n_mels / 8;
+    const float* p = h.data();               // walk the flat buffer in state_dict_spec order
     auto take = [&](int64_t n) {
         const float* r = p;
         p += n;
@@ -479,31 +356,36 @@ extern "C" int sir_model_load_weights(sir_model* m, const float* weights, int64_
     };
     const int cin[3] = {1, 32, 64}, cout[3] = {32, 64, 128};
     std::vector<float> packed;
+    HalfPack hp;
     auto al4 = [&]() {
         while (packed.size() % 4) packed.push_back(0.f);
     };
-    size_t off_w[3], off_s[3];
+    size_t off_w1 = 0, off_s[3], off_cw_hi[3] = {0, 0, 0}, off_cw_lo[3] = {0, 0, 0};
     for (int l = 0; l < 3; ++l) {
         const float* w = take((int64_t)cout[l] * cin[l] * 9);
         const float *g = take(cout[l]), *bt = take(cout[l]), *mu = take(cout[l]), *var = take(cout[l]);
         std::vector<double> scale(cout[l]);
         for (int o = 0; o < cout[l]; ++o) scale[o] = (double)g[o] / std::sqrt((double)var[o] + (double)bn_eps);
-        al4();
-        off_w[l] = packed.size();
-        if (l == 0) {                                 // [32][9]
+        if (l == 0) {                                 // [32][9] fp32
+            al4();
+            off_w1 = packed.size();
             for (int o = 0; o < 32; ++o)
                 for (int k = 0; k < 9; ++k) packed.push_back((float)((double)w[o * 9 + k] * scale[o]));
-        } else {                                      // [tap][cin][cout]
+        } else {                                      // [tap][cout][cin] -> fp16 hi/lo, K (= cin) contiguous
+            std::vector<float> wt((size_t)9 * cout[l] * cin[l]);
             for (int k = 0; k < 9; ++k)
-                for (int i = 0; i < cin[l]; ++i)
-                    for (int o = 0; o < cout[l]; ++o)
-                        packed.push_back((float)((double)w[((int64_t)o * cin[l] + i) * 9 + k] * scale[o]));
+                for (int o = 0; o < cout[l]; ++o)
+                    for (int i = 0; i < cin[l]; ++i)
+                        wt[((size_t)k * cout[l] + o) * cin[l] + i] =
+                            (float)((double)w[((int64_t)o * cin[l] + i) * 9 + k] * scale[o]);
+            off_cw_hi[l] = hp.add(wt, false);
+            off_cw_lo[l] = hp.add(wt, true);
         }
         al4();
         off_s[l] = packed.size();
         for (int o = 0; o < cout[l]; ++o) packed.push_back((float)((double)bt[o] - (double)mu[o] * scale[o]));
     }
-    size_t off_wih[2], off_bih[2], off_whh[2], off_bhh[2];
+    size_t off_bih[2], off_whh[2], off_bhh[2], off_wih_hi[2], off_wih_lo[2];
     for (int l = 0; l < 2; ++l) {
         const int in_sz = l == 0 ? gin : 512;
         const float *wih[2], *whh[2], *bih[2], *bhh[2];
@@ -513,9 +395,22 @@ extern "C" int sir_model_load_weights(sir_model* m, const float* weights, int64_
             bih[d] = take(768);
             bhh[d] = take(768);
         }
+        // both directions stacked along N; layer 0's columns are re-ordered from the reference's
+        // c * H8 + h (models/models.py:55-57) to h * 128 + c, the channels-last order conv3 writes
+        std::vector<float> wcat((size_t)1536 * in_sz);
+        for (int d = 0; d < 2; ++d)
+            for (int n = 0; n < 768; ++n)
+                for (int f = 0; f < in_sz; ++f) {
+                    int fp = f;
+                    if (l == 0) {
+                        const int c = f / H8, hh = f % H8;
+                        fp = hh * 128 + c;
+                    }
+                    wcat[((size_t)d * 768 + n) * in_sz + fp] = wih[d][(size_t)n * in_sz + f];
+                }
+        off_wih_hi[l] = hp.add(wcat, false);
+        off_wih_lo[l] = hp.add(wcat, true);
         al4();
-        off_wih[l] = packed.size();
-        for (int d = 0; d < 2; ++d) packed.insert(packed.end(), wih[d], wih[d] + (int64_t)768 * in_sz);
         off_bih[l] = packed.size();
         for (int d = 0; d < 2; ++d) packed.insert(packed.end(), bih[d], bih[d] + 768);
         off_whh[l] = packed.size();
@@ -537,16 +432,23 @@ extern "C" int sir_model_load_weights(sir_model* m, const float* weights, int64_
     m->att_b = ab[0];
     int rc = m->weights.reserve(packed.size() * sizeof(float));
     if (rc != SIR_OK) return rc;
+    rc = m->weights_h.reserve(hp.data.size() * sizeof(__half));
+    if (rc != SIR_OK) return rc;
     SIR_CUDA(cudaMemcpy(m->weights.ptr, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+    SIR_CUDA(cudaMemcpy(m->weights_h.ptr, hp.data.data(), hp.data.size() * sizeof(__half), cudaMemcpyHostToDevice));
     float* base = (float*)m->weights.ptr;
-    m->w1 = base + off_w[0];
+    __half* hb = (__half*)m->weights_h.ptr;
+    m->w1 = base + off_w1;
     m->sh1 = base + off_s[0];
-    m->w2 = base + off_w[1];
     m->sh2 = base + off_s[1];
-    m->w3 = base + off_w[2];
     m->sh3 = base + off_s[2];
+    m->w2_hi = hb + off_cw_hi[1];
+    m->w2_lo = hb + off_cw_lo[1];
+    m->w3_hi = hb + off_cw_hi[2];
+    m->w3_lo = hb + off_cw_lo[2];
     for (int l = 0; l < 2; ++l) {
-        m->wih[l] = base + off_wih[l];
+        m->wih_hi[l] = hb + off_wih_hi[l];
+        m->wih_lo[l] = hb + off_wih_lo[l];
         m->bih[l] = base + off_bih[l];
         m->whh[l] = base + off_whh[l];
         m->bhh[l] = base + off_bhh[l];
@@ -563,24 +465,31 @@ namespace sir {
 constexpr int kModelChunk = 512;   // utterances per pass through the workspace
 
 struct Workspace {
-    float *act1, *act2, *gru_in, *gi, *y0, *y1, *h;
+    __half *act1_hi, *act1_lo, *act2_hi, *act2_lo, *gin_hi, *gin_lo, *y0_hi, *y0_lo;
+    float *gi, *y0, *y1;
 };
 
-static size_t carve(Workspace& w, float* base, int B, int H, int W, int gin) {
+static size_t carve(Workspace& w, uint8_t* base, int B, int H, int W, int gin) {
     const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2, Tg = W4 / 2;
     size_t off = 0;
-    auto next = [&](size_t n) {
-        float* p = base ? base + off : nullptr;
-        off += (n + 63) & ~(size_t)63;
+    auto next = [&](size_t bytes) {
+        uint8_t* p = base ? base + off : nullptr;
+        off += (bytes + 255) & ~(size_t)255;
         return p;
     };
-    w.act1 = next((size_t)B * H2 * W2 * 32);
-    w.act2 = next((size_t)B * H4 * W4 * 64);
-    w.gru_in = next((size_t)B * Tg * gin);
-    w.gi = next((size_t)B * Tg * 1536);
-    w.y0 = next((size_t)B * Tg * 512);
-    w.y1 = next((size_t)B * Tg * 512);
-    w.h = next((size_t)2 * 2 * B * 256);
+    const size_t n1 = (size_t)B * H2 * W2 * 32, n2 = (size_t)B * H4 * W4 * 64, n3 = (size_t)B * Tg * gin,
+                 ny = (size_t)B * Tg * 512;
+    w.act1_hi = (__half*)next(n1 * 2);
+    w.act1_lo = (__half*)next(n1 * 2);
+    w.act2_hi = (__half*)next(n2 * 2);
+    w.act2_lo = (__half*)next(n2 * 2);
+    w.gin_hi = (__half*)next(n3 * 2);
+    w.gin_lo = (__half*)next(n3 * 2);
+    w.y0_hi = (__half*)next(ny * 2);
+    w.y0_lo = (__half*)next(ny * 2);
+    w.gi = (float*)next((size_t)B * Tg * 1536 * 4);
+    w.y0 = (float*)next(ny * 4);
+    w.y1 = (float*)next(ny * 4);
     return off;
 }
 
@@ -588,44 +497,38 @@ int model_forward_chunk(sir_model* m, const Workspace& ws, const float* feat, in
                         cudaStream_t st) {
     const int H = m->n_mels;
     const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2, Tg = W4 / 2;
+    int rc;
     {
         dim3 grid((unsigned)((H2 * W2 + 127) / 128), (unsigned)B);
         ProfScope ps("conv1_bn_relu_pool", st);
-        conv1_bn_relu_pool_kernel<<<grid, 128, 0, st>>>(feat, m->w1, m->sh1, ws.act1, H, W);
+        conv1_bn_relu_pool_kernel<<<grid, 128, 0, st>>>(feat, m->w1, m->sh1, ws.act1_hi, ws.act1_lo, H, W);
         SIR_CHECK_LAUNCH("conv1_bn_relu_pool_kernel");
     }
-    {
-        constexpr size_t smem = (size_t)(180 * (32 + 4) + 32 * 64) * sizeof(float);
-        dim3 grid((unsigned)((W2 + 15) / 16), (unsigned)((H2 + 7) / 8), (unsigned)B);
-        ProfScope ps("conv2_bn_relu_pool", st);
-        conv3x3_bn_relu_pool_kernel<32, 64, false><<<grid, 256, smem, st>>>(ws.act1, m->w2, m->sh2, ws.act2, H2, W2);
-        SIR_CHECK_LAUNCH("conv3x3_bn_relu_pool_kernel<32,64>");
-    }
-    {
-        constexpr size_t smem = (size_t)(180 * (64 + 4) + 64 * 128) * sizeof(float);
-        dim3 grid((unsigned)((W4 + 15) / 16), (unsigned)((H4 + 7) / 8), (unsigned)B);
-        ProfScope ps("conv3_bn_relu_pool", st);
-        conv3x3_bn_relu_pool_kernel<64, 128, true><<<grid, 256, smem, st>>>(ws.act2, m->w3, m->sh3, ws.gru_in, H4, W4);
-        SIR_CHECK_LAUNCH("conv3x3_bn_relu_pool_kernel<64,128>");
-    }
-    const float* x = ws.gru_in;
+    if ((rc = tc::tc_conv3x3<32, 64>(ws.act1_hi, ws.act1_lo, m->w2_hi, m->w2_lo, m->sh2, ws.act2_hi, ws.act2_lo, B, H2,
+                                     W2, 0, st, "conv2_bn_relu_pool")))
+        return rc;
+    // conv3 writes [B][T/8][H/8][128]: the GRU input, time-major with channels-last features
+    if ((rc = tc::tc_conv3x3<64, 128>(ws.act2_hi, ws.act2_lo, m->w3_hi, m->w3_lo, m->sh3, ws.gin_hi, ws.gin_lo, B, H4,
+                                      W4, 1, st, "conv3_bn_relu_pool")))
+        return rc;
+    const __half *x_hi = ws.gin_hi, *x_lo = ws.gin_lo;
     int in_sz = m->gru_in;
     float* ys[2] = {ws.y0, ws.y1};
     for (int l = 0; l < 2; ++l) {
         const int M = B * Tg;
-        dim3 ggrid(1536 / 128, (unsigned)((M + 127) / 128));
+        if ((rc = tc::tc_gemm_nt(x_hi, x_lo, m->wih_hi[l], m->wih_lo[l], m->bih[l], ws.gi, M, 1536, in_sz, st,
+                                 l == 0 ? "gru_l0_input_gemm" : "gru_l1_input_gemm")))
+            return rc;
         {
-            ProfScope ps(l == 0 ? "gru_l0_input_gemm" : "gru_l1_input_gemm", st);
-            gemm_nt_bias_kernel<<<ggrid, 256, 0, st>>>(x, m->wih[l], m->bih[l], ws.gi, M, 1536, in_sz);
-        }
-        SIR_CHECK_LAUNCH("gemm_nt_bias_kernel");
-        ProfScope ps(l == 0 ? "gru_l0_recurrence" : "gru_l1_recurrence", st);
-        {
+            ProfScope ps(l == 0 ? "gru_l0_recurrence" : "gru_l1_recurrence", st);
             dim3 rgrid((unsigned)(kGruCluster * ((B + kGruBatch - 1) / kGruBatch)), 2);
-            gru_layer_kernel<<<rgrid, 256, kGruSmemBytes, st>>>(ws.gi, m->whh[l], m->bhh[l], ys[l], B, Tg);
+            gru_layer_kernel<<<rgrid, 256, kGruSmemBytes, st>>>(ws.gi, m->whh[l], m->bhh[l], ys[l],
+                                                                l == 0 ? ws.y0_hi : nullptr,
+                                                                l == 0 ? ws.y0_lo : nullptr, B, Tg);
             SIR_CHECK_LAUNCH("gru_layer_kernel");
         }
-        x = ys[l];
+        x_hi = ws.y0_hi;
+        x_lo = ws.y0_lo;
         in_sz = 512;
     }
     {
@@ -645,22 +548,16 @@ static int model_prepare(sir_model* m, int batch, int n_frames, Workspace& ws, i
     if (n_frames < 8) return fail(SIR_ERR_INVALID, "sir_model_forward: n_frames must be >= 8 (got %d)", n_frames);
     static bool attr_done = false;
     if (!attr_done) {
-        SIR_CUDA(cudaFuncSetAttribute(conv3x3_bn_relu_pool_kernel<64, 128, true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)((180 * 68 + 64 * 128) * sizeof(float))));
-        SIR_CUDA(cudaFuncSetAttribute(conv3x3_bn_relu_pool_kernel<32, 64, false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)((180 * 36 + 32 * 64) * sizeof(float))));
         SIR_CUDA(cudaFuncSetAttribute(gru_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kGruSmemBytes));
         attr_done = true;
     }
     chunk = batch < kModelChunk ? batch : kModelChunk;
     Workspace probe;
-    const size_t need = carve(probe, nullptr, chunk, m->n_mels, n_frames, m->gru_in) * sizeof(float);
+    const size_t need = carve(probe, nullptr, chunk, m->n_mels, n_frames, m->gru_in);
     int rc = m->work.reserve(need);
     if (rc != SIR_OK) return rc;
-    carve(ws, (float*)m->work.ptr, chunk, m->n_mels, n_frames, m->gru_in);
+    carve(ws, (uint8_t*)m->work.ptr, chunk, m->n_mels, n_frames, m->gru_in);
     return SIR_OK;
 }
 
@@ -687,11 +584,9 @@ extern "C" int sir_pipeline_forward(sir_frontend* fe, sir_model* m, const float*
                                     int out_frames, float* d_features, float* d_logits, void* stream) {
     if (!fe || !m || !d_wave || !d_logits) return fail(SIR_ERR_INVALID, "sir_pipeline_forward: NULL argument");
     if (batch <= 0) return batch == 0 ? SIR_OK : fail(SIR_ERR_INVALID, "sir_pipeline_forward: negative batch");
-    if (d_features) {
-        int rc = sir_frontend_forward(fe, d_wave, wave_stride, d_lengths, n_samples, batch, max_samples,
-                                      SIR_OUT_LOGMEL_NORM, out_frames, d_features, nullptr, nullptr, stream);
-        if (rc != SIR_OK) return rc;
-        return sir_model_forward(m, d_features, batch, out_frames, d_logits, stream);
-    }
-    return fail(SIR_ERR_INVALID, "sir_pipeline_forward: d_features is required in this build");
+    if (!d_features) return fail(SIR_ERR_INVALID, "sir_pipeline_forward: d_features is required in this build");
+    int rc = sir_frontend_forward(fe, d_wave, wave_stride, d_lengths, n_samples, batch, max_samples,
+                                  SIR_OUT_LOGMEL_NORM, out_frames, d_features, nullptr, nullptr, stream);
+    if (rc != SIR_OK) return rc;
+    return sir_model_forward(m, d_features, batch, out_frames, d_logits, stream);
 }
