@@ -29,6 +29,9 @@ int tc_gemm_nt(const __half* a_hi, const __half* a_lo, const __half* w_hi, const
 template <int CIN, int COUT>
 int tc_conv3x3(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
                __half* out_hi, __half* out_lo, int B, int H, int W, int out_whc, cudaStream_t st, const char* name);
+int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint32_t* box);
+int gru_layer_tc(const CUtensorMap& tm_w_hi, const CUtensorMap& tm_w_lo, const float* gi, const float* bhh, float* y,
+                 __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st);
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------------------
@@ -90,120 +93,6 @@ __global__ void __launch_bounds__(128) conv1_bn_relu_pool_kernel(const float* __
                                 (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
         dst_lo[c4] = make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
                                 (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// GRU recurrence of one layer, both directions, all T steps in ONE launch.
-//
-//   r = s(gi_r + W_hr h + b_hr)  z = s(gi_z + W_hz h + b_hz)  n = tanh(gi_n + r * (W_hn h + b_hn))
-//   h' = (1 - z) n + z h                                             (torch.nn.GRU; gi already holds b_i*)
-//
-// A thread-block CLUSTER of 8 CTAs owns one (direction, slice of 32 utterances); CTA r of the cluster keeps
-// the recurrent weights of hidden units [32 r, 32 r + 32) - 3 gates x 32 units x 256 k fp32 = 96 KB -
-// resident in shared memory for all steps.  Per step every CTA loads the slice's previous hidden state
-// (32 x 256 fp32, written by its 7 peers to the layer output y, still in L2) into shared memory, does its
-// 96 x 256 by 256 x 32 product on the fp32 pipe, applies the gates and writes its 32 x 32 block of h' to y;
-// one cluster barrier (release/acquire) per step orders the exchange.  No grid-wide synchronisation, no
-// per-step launch.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int kGruCluster = 8;
-constexpr int kGruUnits = 32;        // hidden units per CTA
-constexpr int kGruBatch = 32;        // utterances per cluster
-constexpr int kGruHStride = 256 + 4; // padded row of the staged hidden state (floats)
-constexpr size_t kGruSmemBytes = (size_t)(3 * 64 * kGruUnits * 4 + kGruBatch * kGruHStride) * sizeof(float);
-
-__global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(256, 1)
-    gru_layer_kernel(const float* __restrict__ gi,   // [B*T, 1536]
-                     const float* __restrict__ whh,  // [2][768][256]
-                     const float* __restrict__ bhh,  // [2][768]
-                     float* __restrict__ y,          // [B, T, 512]
-                     __half* __restrict__ y_hi,      // optional fp16 (hi, lo) copy: the next layer's GEMM operand
-                     __half* __restrict__ y_lo, int B, int T) {
-    extern __shared__ __align__(16) float gsm[];
-    float* Wsh = gsm;                                   // [3][64][32][4]
-    float* Hs = gsm + 3 * 64 * kGruUnits * 4;           // [32][260]
-    const int tid = threadIdx.x, unit = tid & 31, bg = tid >> 5;
-    const int rank = blockIdx.x % kGruCluster;          // == cluster rank for a 1-D cluster
-    const int slice = blockIdx.x / kGruCluster;
-    const int dir = blockIdx.y;
-    const int j0 = rank * kGruUnits, b0 = slice * kGruBatch;
-    const float* __restrict__ W = whh + (int64_t)dir * 768 * 256;
-
-    for (int idx = tid; idx < 3 * kGruUnits * 256; idx += 256) {
-        const int k = idx & 255, u = (idx >> 8) & 31, g = idx >> 13;
-        Wsh[((g * 64 + (k >> 2)) * kGruUnits + u) * 4 + (k & 3)] = __ldg(W + (int64_t)(g * 256 + j0 + u) * 256 + k);
-    }
-    const float br = __ldg(bhh + dir * 768 + j0 + unit), bz = __ldg(bhh + dir * 768 + 256 + j0 + unit),
-                bn = __ldg(bhh + dir * 768 + 512 + j0 + unit);
-    float hprev[4] = {0.f, 0.f, 0.f, 0.f};              // this thread's own (unit, 4 utterances) state
-    __syncthreads();
-
-    for (int s = 0; s < T; ++s) {
-        const int t = dir == 0 ? s : T - 1 - s;
-        // gate pre-activations from the input projection: issue the loads before the matrix product
-        float g_in[3][4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int bb = b0 + bg * 4 + u;
-            const float* __restrict__ gp = gi + ((int64_t)(bb < B ? bb : B - 1) * T + t) * 1536 + dir * 768 + j0 + unit;
-            g_in[0][u] = __ldg(gp);
-            g_in[1][u] = __ldg(gp + 256);
-            g_in[2][u] = __ldg(gp + 512);
-        }
-        float acc[3][4];
-#pragma unroll
-        for (int g = 0; g < 3; ++g)
-#pragma unroll
-            for (int u = 0; u < 4; ++u) acc[g][u] = 0.f;
-        if (s > 0) {
-            const int tp = dir == 0 ? t - 1 : t + 1;
-            // stage h_{s-1} of the whole slice: 32 rows x 1 KB, written by the cluster's CTAs in the last step
-            for (int idx = tid; idx < kGruBatch * 64; idx += 256) {
-                const int row = idx >> 6, c4 = idx & 63;
-                const int bb = b0 + row;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (bb < B) v = __ldcg(reinterpret_cast<const float4*>(y + ((int64_t)bb * T + tp) * 512 + dir * 256) + c4);
-                *reinterpret_cast<float4*>(Hs + row * kGruHStride + 4 * c4) = v;
-            }
-            __syncthreads();
-            const float4* __restrict__ w4 = reinterpret_cast<const float4*>(Wsh) + unit;
-            const float* __restrict__ hrow = Hs + (bg * 4) * kGruHStride;
-#pragma unroll 4
-            for (int k4 = 0; k4 < 64; ++k4) {
-                const float4 w0 = w4[(0 * 64 + k4) * kGruUnits], w1 = w4[(1 * 64 + k4) * kGruUnits],
-                             w2 = w4[(2 * 64 + k4) * kGruUnits];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float4 h = *reinterpret_cast<const float4*>(hrow + u * kGruHStride + 4 * k4);
-                    acc[0][u] = fmaf(w0.w, h.w, fmaf(w0.z, h.z, fmaf(w0.y, h.y, fmaf(w0.x, h.x, acc[0][u]))));
-                    acc[1][u] = fmaf(w1.w, h.w, fmaf(w1.z, h.z, fmaf(w1.y, h.y, fmaf(w1.x, h.x, acc[1][u]))));
-                    acc[2][u] = fmaf(w2.w, h.w, fmaf(w2.z, h.z, fmaf(w2.y, h.y, fmaf(w2.x, h.x, acc[2][u]))));
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int bb = b0 + bg * 4 + u;
-            const float r = 1.f / (1.f + expf(-(g_in[0][u] + acc[0][u] + br)));
-            const float z = 1.f / (1.f + expf(-(g_in[1][u] + acc[1][u] + bz)));
-            const float n = tanhf(g_in[2][u] + r * (acc[2][u] + bn));
-            const float hn = (1.f - z) * n + z * hprev[u];
-            hprev[u] = hn;
-            if (bb < B) {
-                const int64_t o = ((int64_t)bb * T + t) * 512 + dir * 256 + j0 + unit;
-                y[o] = hn;
-                if (y_hi) {
-                    __half h, l;
-                    tc::split_f16(hn, h, l);
-                    y_hi[o] = h;
-                    y_lo[o] = l;
-                }
-            }
-        }
-        // publish this step's h' to the 7 peers (and make sure nobody still reads Hs) before the next step
-        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     }
 }
 
@@ -274,11 +163,14 @@ struct sir_model {
     DeviceBuffer work;           // activations
     // fp32 pointers into `weights`
     float *w1 = nullptr, *sh1 = nullptr, *sh2 = nullptr, *sh3 = nullptr;
-    float *bih[2] = {nullptr, nullptr}, *whh[2] = {nullptr, nullptr}, *bhh[2] = {nullptr, nullptr};
+    float *bih[2] = {nullptr, nullptr}, *bhh[2] = {nullptr, nullptr};
     float *att_w = nullptr, *fc_w = nullptr, *fc_b = nullptr;
     // fp16 pointers into `weights_h`: conv weights [tap][C_out][C_in] (BN scale folded), W_ih [1536][K]
     __half *w2_hi = nullptr, *w2_lo = nullptr, *w3_hi = nullptr, *w3_lo = nullptr;
     __half *wih_hi[2] = {nullptr, nullptr}, *wih_lo[2] = {nullptr, nullptr};
+    // recurrent weights as per-CTA UMMA tiles [2 dirs][8 ranks][96][256] (gru_tc.cu) + their TMA maps
+    __half *whh_hi[2] = {nullptr, nullptr}, *whh_lo[2] = {nullptr, nullptr};
+    CUtensorMap tm_whh_hi[2], tm_whh_lo[2];
 };
 
 static int64_t model_weight_count(int num_classes, int n_mels) {
@@ -385,7 +277,7 @@ extern "C" int sir_model_load_weights(sir_model* m, const float* weights, int64_
         off_s[l] = packed.size();
         for (int o = 0; o < cout[l]; ++o) packed.push_back((float)((double)bt[o] - (double)mu[o] * scale[o]));
     }
-    size_t off_bih[2], off_whh[2], off_bhh[2], off_wih_hi[2], off_wih_lo[2];
+    size_t off_bih[2], off_bhh[2], off_wih_hi[2], off_wih_lo[2], off_whh_hi[2], off_whh_lo[2];
     for (int l = 0; l < 2; ++l) {
         const int in_sz = l == 0 ? gin : 512;
         const float *wih[2], *whh[2], *bih[2], *bhh[2];
@@ -413,8 +305,16 @@ extern "C" int sir_model_load_weights(sir_model* m, const float* weights, int64_
         al4();
         off_bih[l] = packed.size();
         for (int d = 0; d < 2; ++d) packed.insert(packed.end(), bih[d], bih[d] + 768);
-        off_whh[l] = packed.size();
-        for (int d = 0; d < 2; ++d) packed.insert(packed.end(), whh[d], whh[d] + (int64_t)768 * 256);
+        // recurrent weights: per (direction, cluster rank) a 96-row tile, row = gate*32 + local unit
+        std::vector<float> wt((size_t)2 * 8 * 96 * 256, 0.f);
+        for (int d = 0; d < 2; ++d)
+            for (int r = 0; r < 8; ++r)
+                for (int g = 0; g < 3; ++g)
+                    for (int u = 0; u < 32; ++u)
+                        std::memcpy(&wt[(((size_t)d * 8 + r) * 96 + g * 32 + u) * 256],
+                                    whh[d] + (size_t)(g * 256 + r * 32 + u) * 256, 256 * sizeof(float));
+        off_whh_hi[l] = hp.add(wt, false);
+        off_whh_lo[l] = hp.add(wt, true);
         off_bhh[l] = packed.size();
         for (int d = 0; d < 2; ++d) packed.insert(packed.end(), bhh[d], bhh[d] + 768);
     }
@@ -450,8 +350,13 @@ extern "C" int sir_model_load_weights(sir_model* m, const float* weights, int64_
         m->wih_hi[l] = hb + off_wih_hi[l];
         m->wih_lo[l] = hb + off_wih_lo[l];
         m->bih[l] = base + off_bih[l];
-        m->whh[l] = base + off_whh[l];
         m->bhh[l] = base + off_bhh[l];
+        m->whh_hi[l] = hb + off_whh_hi[l];
+        m->whh_lo[l] = hb + off_whh_lo[l];
+        const uint64_t wd[2] = {256, 2 * 8 * 96};
+        const uint32_t wb[2] = {64, 96};
+        if ((rc = tc::make_tmap(&m->tm_whh_hi[l], m->whh_hi[l], 2, wd, wb))) return rc;
+        if ((rc = tc::make_tmap(&m->tm_whh_lo[l], m->whh_lo[l], 2, wd, wb))) return rc;
     }
     m->att_w = base + off_att;
     m->fc_w = base + off_fcw;
@@ -462,7 +367,7 @@ extern "C" int sir_model_load_weights(sir_model* m, const float* weights, int64_
 
 namespace sir {
 
-constexpr int kModelChunk = 512;   // utterances per pass through the workspace
+constexpr int kModelChunk = 336;   // utterances per pass through the workspace: 2 x 7 GRU clusters of 48 = one wave
 
 struct Workspace {
     __half *act1_hi, *act1_lo, *act2_hi, *act2_lo, *gin_hi, *gin_lo, *y0_hi, *y0_lo;
@@ -521,11 +426,9 @@ int model_forward_chunk(sir_model* m, const Workspace& ws, const float* feat, in
             return rc;
         {
             ProfScope ps(l == 0 ? "gru_l0_recurrence" : "gru_l1_recurrence", st);
-            dim3 rgrid((unsigned)(kGruCluster * ((B + kGruBatch - 1) / kGruBatch)), 2);
-            gru_layer_kernel<<<rgrid, 256, kGruSmemBytes, st>>>(ws.gi, m->whh[l], m->bhh[l], ys[l],
-                                                                l == 0 ? ws.y0_hi : nullptr,
-                                                                l == 0 ? ws.y0_lo : nullptr, B, Tg);
-            SIR_CHECK_LAUNCH("gru_layer_kernel");
+            if ((rc = tc::gru_layer_tc(m->tm_whh_hi[l], m->tm_whh_lo[l], ws.gi, m->bhh[l], ys[l],
+                                       l == 0 ? ws.y0_hi : nullptr, l == 0 ? ws.y0_lo : nullptr, B, Tg, st)))
+                return rc;
         }
         x_hi = ws.y0_hi;
         x_lo = ws.y0_lo;
@@ -546,12 +449,6 @@ int model_forward_chunk(sir_model* m, const Workspace& ws, const float* feat, in
 static int model_prepare(sir_model* m, int batch, int n_frames, Workspace& ws, int& chunk) {
     if (!m->loaded) return fail(SIR_ERR_INVALID, "sir_model_forward: weights not loaded");
     if (n_frames < 8) return fail(SIR_ERR_INVALID, "sir_model_forward: n_frames must be >= 8 (got %d)", n_frames);
-    static bool attr_done = false;
-    if (!attr_done) {
-        SIR_CUDA(cudaFuncSetAttribute(gru_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)kGruSmemBytes));
-        attr_done = true;
-    }
     chunk = batch < kModelChunk ? batch : kModelChunk;
     Workspace probe;
     const size_t need = carve(probe, nullptr, chunk, m->n_mels, n_frames, m->gru_in);

@@ -242,7 +242,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // fp16 tensor of `rank` dims (innermost first), box of the same rank, swizzle = inner box bytes (64 or 128).
-static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(SIR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[4], gstride[3];

@@ -1,0 +1,290 @@
+// GRU recurrence of one layer (both directions, all T steps, ONE launch) with the recurrent product on tcgen05.
+//
+//   r = s(gi_r + W_hr h + b_hr)  z = s(gi_z + W_hz h + b_hz)  n = tanh(gi_n + r * (W_hn h + b_hn))
+//   h' = (1 - z) n + z h            torch.nn.GRU, models/models.py:60 of the reference (gi already holds b_i*)
+//
+// A thread-block CLUSTER of 8 CTAs owns one (direction, slice of NB utterances).  CTA r keeps the recurrent
+// weights of hidden units [32 r, 32 r + 32) - 96 gate rows as fp16 (hi, lo) pairs, 96 KB - resident in shared
+// memory for all steps, loaded once by TMA.  (The UMMA tile has 128 rows: rows 96..127 read whatever follows
+// in shared memory and produce accumulator rows nobody looks at.)  The hidden state
+// never leaves the chip between steps: it lives as the fp16 (hi, lo) B operand [NB x 256] in every CTA's
+// shared memory (128-byte swizzled K-major, double buffered).  Per step:
+//   1. one thread issues 48 tcgen05.mma (128 x NB x 16; hi.hi, hi.lo, lo.hi over K = 256) into a TMEM
+//      accumulator D[gate row, utterance];
+//   2. warps 0/1/2 read the r/z/n rows back (TMEM lane = gate row) and transpose them through shared memory;
+//   3. every thread updates 8 hidden units of one utterance, writes h' to the layer output y (fp32, plus the
+//      fp16 pair the next layer's input GEMM consumes) and PUSHES the fp16 (hi, lo) of its 8 units - one
+//      16-byte chunk each - into the next-step B operand of all 8 CTAs through distributed shared memory;
+//   4. one cluster barrier (release/acquire) per step.
+// No grid-wide synchronisation, no per-step launch, no L2 round trip on the recurrence's critical path.
+#include "sir_common.cuh"
+#include "tc_common.cuh"
+
+namespace sir {
+namespace tc {
+
+constexpr int kGtCluster = 8;
+constexpr int kGtUnits = 32;                  // hidden units per CTA
+constexpr int kGtThreads = 256;
+constexpr int kGtWRows = 96;                  // 3 gates x 32 units
+constexpr int kGtWBytes = kGtWRows * 256 * 2; // one of (hi, lo): 4 K-blocks of 96 rows x 128 B
+
+template <int NB>
+struct GtLayout {
+    static constexpr int kHBytes = NB * 256 * 2;                 // one of (hi, lo) of one buffer: 4 K-blocks of NB rows
+    static constexpr int kOffWlo = kGtWBytes;
+    static constexpr int kOffH = 2 * kGtWBytes;                  // [2 buffers][hi, lo]
+    static constexpr int kOffS = kOffH + 4 * kHBytes;            // gate pre-activations [3][32 units][NB + 1] fp32
+    static constexpr int kSStride = NB + 1;
+    static constexpr int kOffBar = (kOffS + 3 * 32 * kSStride * 4 + 15) & ~15;
+    static constexpr int kSmemBytes = kOffBar + 64 + 1024;
+    static_assert(kHBytes % 1024 == 0, "B operand K-blocks must stay 1024-byte aligned");
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int NB>
+__global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads, 1)
+    gru_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi,   // [2*8*96 rows][256] fp16, box {64,96}
+                        const __grid_constant__ CUtensorMap tm_w_lo,
+                        const float* __restrict__ gi,                  // [B*T, 1536]
+                        const float* __restrict__ bhh,                 // [2][768]
+                        float* __restrict__ y,                         // [B, T, 512]
+                        __half* __restrict__ y_hi, __half* __restrict__ y_lo, int B, int T) {
+    using L = GtLayout<NB>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* s_gate = reinterpret_cast<float*>(smem + L::kOffS);
+    uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+    uint64_t* mma_done = w_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = blockIdx.x % kGtCluster;
+    const int slice = blockIdx.x / kGtCluster;
+    const int dir = blockIdx.y;
+    const int j0 = rank * kGtUnits, b0 = slice * NB;
+
+    if (tid == 0) {
+        prefetch_tmap(&tm_w_hi);
+        prefetch_tmap(&tm_w_lo);
+        mbar_init(w_full, 1);
+        mbar_init(mma_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<64>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t sbase = smem_u32(smem);
+
+    if (tid == 0) {
+        // resident weights: rows (dir*8 + rank)*96 .. +96, four 64-wide K-blocks each for hi and lo
+        mbar_arrive_expect_tx(w_full, 2 * kGtWBytes);
+        const int row0 = (dir * kGtCluster + rank) * kGtWRows;
+        for (int kb = 0; kb < 4; ++kb) {
+            tma_load_2d(smem + kb * (kGtWRows * 128), &tm_w_hi, w_full, kb * 64, row0);
+            tma_load_2d(smem + L::kOffWlo + kb * (kGtWRows * 128), &tm_w_lo, w_full, kb * 64, row0);
+        }
+    }
+
+    // update role: thread -> (utterance i, group of 8 hidden units ug)
+    const bool updater = tid < 4 * NB;
+    const int ui = tid >> 2, ug = tid & 3;
+    const int ubb = b0 + ui;
+    const bool uvalid = updater && ubb < B;
+    float b_r[8], b_z[8], b_n[8], hprev[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int u = j0 + 8 * ug + e;
+        b_r[e] = __ldg(bhh + dir * 768 + u);
+        b_z[e] = __ldg(bhh + dir * 768 + 256 + u);
+        b_n[e] = __ldg(bhh + dir * 768 + 512 + u);
+        hprev[e] = 0.f;
+    }
+    // where this thread's 16-byte chunk (8 units of utterance ui) sits inside a swizzled B-operand buffer
+    uint32_t chunk_off = 0;
+    {
+        const int k = j0 + 8 * ug, kb = k >> 6, chunk = (k & 63) >> 3;
+        chunk_off = (uint32_t)(kb * (NB * 128) + (ui >> 3) * 1024 + (ui & 7) * 128 + ((chunk ^ (ui & 7)) << 4));
+    }
+    mbar_wait(w_full, 0);
+    // everybody's barriers/TMEM are set up before any peer may push into this CTA
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+
+    constexpr uint32_t idesc = make_idesc_f16(128, NB);
+
+    for (int s = 0; s < T; ++s) {
+        const int t = dir == 0 ? s : T - 1 - s;
+        const int cur = s & 1, nxt = cur ^ 1;
+        // gate pre-activations of the input projection (consumed after the MMA: the loads overlap it)
+        float4 gin[3][2];
+        if (updater) {
+            const float4* gp = reinterpret_cast<const float4*>(
+                gi + ((int64_t)(uvalid ? ubb : B - 1) * T + t) * 1536 + dir * 768 + j0 + 8 * ug);
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                gin[g][0] = __ldg(gp + g * 64);
+                gin[g][1] = __ldg(gp + g * 64 + 1);
+            }
+        }
+        if (s > 0) {
+            // (1) D[128 gate rows, NB utterances] = W_slice[128, 256] . h^T   (h: buffer `cur`)
+            if (tid == 0) {
+                fence_proxy_async_all();
+                tc_fence_after();
+                const uint32_t hb = sbase + L::kOffH + cur * 2 * L::kHBytes;
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb) {
+                    const uint64_t a_hi = make_kmajor_desc<128>(sbase + kb * (kGtWRows * 128));
+                    const uint64_t a_lo = make_kmajor_desc<128>(sbase + L::kOffWlo + kb * (kGtWRows * 128));
+                    const uint64_t b_hi = make_kmajor_desc<128>(hb + kb * (NB * 128));
+                    const uint64_t b_lo = make_kmajor_desc<128>(hb + L::kHBytes + kb * (NB * 128));
+#pragma unroll
+                    for (int k = 0; k < 64; k += 16) {
+                        umma_f16(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(b_hi, k), idesc, (kb | k) ? 1u : 0u);
+                        umma_f16(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(b_lo, k), idesc, 1u);
+                        umma_f16(tmem_base, desc_advance_k(a_lo, k), desc_advance_k(b_hi, k), idesc, 1u);
+                    }
+                }
+                umma_commit(mma_done);
+            }
+            // (2) accumulator rows -> shared memory, transposed to [gate][unit][utterance]
+            if (warp < 3) {
+                mbar_wait(mma_done, (uint32_t)(s - 1) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < NB; c += 16) {
+                    float v[16];
+                    uint32_t r[16];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+                          "=r"(r[15])
+                        : "r"(tmem_base + ((uint32_t)(warp * 32) << 16) + c)
+                        : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        v[i] = __uint_as_float(r[i]);
+                        s_gate[(warp * 32 + lane) * L::kSStride + c + i] = v[i];
+                    }
+                }
+                tc_fence_before();
+            }
+            __syncthreads();
+        }
+
+        // (3) state update for 8 units of one utterance, output, and push of the next-step operand
+        if (updater) {
+            const float gr[8] = {gin[0][0].x, gin[0][0].y, gin[0][0].z, gin[0][0].w,
+                                 gin[0][1].x, gin[0][1].y, gin[0][1].z, gin[0][1].w};
+            const float gz[8] = {gin[1][0].x, gin[1][0].y, gin[1][0].z, gin[1][0].w,
+                                 gin[1][1].x, gin[1][1].y, gin[1][1].z, gin[1][1].w};
+            const float gn[8] = {gin[2][0].x, gin[2][0].y, gin[2][0].z, gin[2][0].w,
+                                 gin[2][1].x, gin[2][1].y, gin[2][1].z, gin[2][1].w};
+            float hn[8];
+            uint32_t hi2[4], lo2[4];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float ar = 0.f, az = 0.f, an = 0.f;
+                if (s > 0) {
+                    const int u = 8 * ug + e;
+                    ar = s_gate[(0 * 32 + u) * L::kSStride + ui];
+                    az = s_gate[(1 * 32 + u) * L::kSStride + ui];
+                    an = s_gate[(2 * 32 + u) * L::kSStride + ui];
+                }
+                const float r = sigmoid_f(gr[e] + ar + b_r[e]);
+                const float z = sigmoid_f(gz[e] + az + b_z[e]);
+                const float n = tanhf(gn[e] + r * (an + b_n[e]));
+                hn[e] = (1.f - z) * n + z * hprev[e];
+                hprev[e] = hn[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                __half h0, l0, h1, l1;
+                split_f16(hn[e], h0, l0);
+                split_f16(hn[e + 1], h1, l1);
+                hi2[e >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                lo2[e >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            const uint4 vhi = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
+            const uint4 vlo = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
+            if (s + 1 < T) {
+                const uint32_t dst = sbase + L::kOffH + nxt * 2 * L::kHBytes + chunk_off;
+#pragma unroll
+                for (int c = 0; c < kGtCluster; ++c) {
+                    const uint32_t ra = map_to_cta(dst, (uint32_t)c);
+                    st_cluster_v4(ra, vhi);
+                    st_cluster_v4(ra + L::kHBytes, vlo);
+                }
+            }
+            if (uvalid) {
+                const int64_t o = ((int64_t)ubb * T + t) * 512 + dir * 256 + j0 + 8 * ug;
+                float4* yo = reinterpret_cast<float4*>(y + o);
+                yo[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                yo[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                if (y_hi) {
+                    *reinterpret_cast<uint4*>(y_hi + o) = vhi;
+                    *reinterpret_cast<uint4*>(y_lo + o) = vlo;
+                }
+            }
+        }
+        // (4) the pushes of all 8 CTAs have landed (and this step's reads of s_gate / TMEM are done)
+        fence_proxy_async_all();
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<64>(tmem_base);
+    }
+}
+
+template <int NB>
+static int launch_gru(const CUtensorMap& tm_w_hi, const CUtensorMap& tm_w_lo, const float* gi, const float* bhh, float* y,
+                      __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st) {
+    using L = GtLayout<NB>;
+    static bool attr = false;
+    if (!attr) {
+        SIR_CUDA(cudaFuncSetAttribute(gru_layer_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes));
+        attr = true;
+    }
+    dim3 grid((unsigned)(kGtCluster * ((B + NB - 1) / NB)), 2);
+    gru_layer_tc_kernel<NB><<<grid, kGtThreads, L::kSmemBytes, st>>>(tm_w_hi, tm_w_lo, gi, bhh, y, y_hi, y_lo, B, T);
+    SIR_CHECK_LAUNCH("gru_layer_tc_kernel");
+    return SIR_OK;
+}
+
+// Utterances per cluster: the smallest UMMA N (multiple of 16) for which both directions of the whole batch
+// fit in one wave of 8-CTA clusters (15 co-resident on a B200 with this kernel's footprint: measured
+// launch__cluster_max_active); N = 48 is the largest slice whose double-buffered operand fits next to the
+// resident weights, larger batches run several waves (the model chunks its batch to one wave of 7 x 48).
+constexpr int kGtMaxClustersPerWave = 15;
+
+int gru_layer_tc(const CUtensorMap& tm_w_hi, const CUtensorMap& tm_w_lo, const float* gi, const float* bhh, float* y,
+                 __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st) {
+    auto clusters = [&](int nb) { return 2 * ((B + nb - 1) / nb); };
+    if (clusters(16) <= kGtMaxClustersPerWave) return launch_gru<16>(tm_w_hi, tm_w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
+    if (clusters(32) <= kGtMaxClustersPerWave) return launch_gru<32>(tm_w_hi, tm_w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
+    return launch_gru<48>(tm_w_hi, tm_w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
+}
+
+}  // namespace tc
+}  // namespace sir
