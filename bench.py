@@ -59,47 +59,77 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled in-process through NVML (pynvml) every few ms, so that even a
+    20 ms timed region gets samples; `mark()` brackets the timed region, samples inside it are reported."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def start(self):
+    def __init__(self, index, period_s=0.002):
+        self.index, self.period, self.rows, self.marks = index, period_s, [], []
+        self.handle = self.thread = None
+        self.stop_flag = threading.Event()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if visible:
+                ids = [v for v in visible.split(",") if v.strip() != ""]
+                if index < len(ids) and ids[index].strip().isdigit():
+                    phys = int(ids[index])
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001 - NVML missing: report it, never fail the bench
+            self.error = f"nvml unavailable: {e}"
+
+    def _sample(self):
+        nv = self.nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        try:
+            reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:  # noqa: BLE001
+            reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.rows.append((time.perf_counter(), sm, reasons))
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        while not self.stop_flag.is_set():
+            try:
+                self._sample()
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.handle is not None:
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+
+    def mark(self):
+        """Call at the start and end of every timed region (host time; the regions are device-synchronised)."""
+        if self.handle is not None:
+            try:
+                self._sample()
+            except Exception:  # noqa: BLE001
+                pass
+        self.marks.append(time.perf_counter())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
-            if len(r) < 6:
-                continue
-            try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-            except ValueError:
-                continue
-            for n, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.handle is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [getattr(self, "error", "nvml unavailable")],
+                    "samples": 0}
+        self.stop_flag.set()
+        self.thread.join(timeout=1.0)
+        spans = list(zip(self.marks[0::2], self.marks[1::2]))
+        inside = [r for r in self.rows if any(a <= r[0] <= b for a, b in spans)] or self.rows
+        sm = [r[1] for r in inside]
+        bits = 0
+        for r in inside:
+            bits |= r[2]
+        reasons = sorted(n for n, m in self.REASONS if bits & m)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "source": "NVML in-process, samples inside the timed regions (value + e2e)"}
 
 
 def synth_batch(native_synth, seed, batch):
@@ -110,51 +140,68 @@ def synth_batch(native_synth, seed, batch):
     return (np.tile(base, (reps, 1)) * gains)[:batch]
 
 
-def cpu_reference_arm(native_synth, n_utts, threads=None):
-    """The reference's CPU path on `n_utts` utterances -> (utt/s, seconds, description)."""
-    from oracle.torch_port import ClassifierPort, FeaturePort, load_numpy_state
-    if threads:
-        torch.set_num_threads(threads)
-    waves = torch.from_numpy(synth_batch(native_synth, 99, n_utts))
-    fp = FeaturePort()
-    model = load_numpy_state(ClassifierPort(NUM_CLASSES).eval(), native_synth.make_weights(1234))
-    t0 = time.perf_counter()
-    feats = fp.batch_padded(waves, target=OUT_FRAMES)          # one call per utterance, like the reference loop
-    t1 = time.perf_counter()
-    with torch.no_grad():
-        logits = model(feats)
-    t2 = time.perf_counter()
-    return n_utts / (t2 - t0), (t1 - t0, t2 - t1), int(logits.argmax(1)[0])
+class CpuArm:
+    """The reference's CPU path (oracle/torch_port.py: the torchaudio / torch.nn calls the reference makes) on the
+    host cores: per-utterance feature loop like scripts/precompute_features.py:124-130, then CNNAudioGRU.eval()
+    fp32 forward in one batch.  Test/bench infrastructure only - never on the product path."""
+
+    def __init__(self, native_synth, n_utts, threads=None):
+        from oracle.torch_port import ClassifierPort, FeaturePort, load_numpy_state
+        self.threads = threads or (os.cpu_count() or 1)
+        torch.set_num_threads(self.threads)
+        self.n = n_utts
+        self.waves = torch.from_numpy(synth_batch(native_synth, 99, n_utts))
+        self.fp = FeaturePort()
+        self.model = load_numpy_state(ClassifierPort(NUM_CLASSES).eval(), native_synth.make_weights(1234))
+
+    def step(self):
+        """One pass over the n_utts batch -> (feature seconds, forward seconds)."""
+        t0 = time.perf_counter()
+        feats = self.fp.batch_padded(self.waves, target=OUT_FRAMES)   # one call per utterance, like the reference loop
+        t1 = time.perf_counter()
+        with torch.no_grad():
+            self.model(feats)
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+
+    def run_for(self, min_seconds, min_steps=2, max_steps=200):
+        feat_s = fwd_s = 0.0
+        steps = 0
+        while steps < min_steps or (feat_s + fwd_s < min_seconds and steps < max_steps):
+            a, b = self.step()
+            feat_s, fwd_s, steps = feat_s + a, fwd_s + b, steps + 1
+        return steps, feat_s, fwd_s
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, rank 0 only.
+    One step = the full configs[1] batch (256 utterances x 3 s)."""
     if rank != 0:
         return
     native_synth = importlib.import_module("speech-intent-recognizer_b200.utils.synth")
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    per_step = 64
-    for _ in range(args.warmup):
-        cpu_reference_arm(native_synth, 16)
+    arm = CpuArm(native_synth, BATCH_PER_GPU)
+    for _ in range(min(args.warmup, 3)):
+        arm.step()
     t0 = time.perf_counter()
     feat_s = fwd_s = 0.0
     for _ in range(args.steps):
-        _, (a, b), _ = cpu_reference_arm(native_synth, per_step)
+        a, b = arm.step()
         feat_s += a
         fwd_s += b
     total = feat_s + fwd_s
-    value = per_step * args.steps / total
+    value = arm.n * args.steps / total
     line = {
         "impl": "reference", "metric": "utterances/sec (features+forward)", "value": value, "unit": "utt/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1]: 256 utt x 3 s @16 kHz, config.yaml model (64 mel, 200 frames, 31 classes)",
-                   "sample_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{per_step} utterances x 3 s per step: per-utterance torchaudio MelSpectrogram+"
-                                   f"AmplitudeToDB+normalise loop ({feat_s / args.steps:.2f} s) + CNNAudioGRU fp32 "
-                                   f"forward in one batch ({fwd_s / args.steps:.2f} s); wall {time.perf_counter() - t0:.1f} s",
-                         "host_cpus": cores, "torch": torch.__version__},
+                   "batch_per_step": arm.n},
+        "cpu_baseline": {"value": value, "unit": "utt/s", "cores": arm.threads, "kind": "port",
+                         "sample": f"{args.steps} steps x {arm.n} utterances x 3 s: per-utterance torchaudio "
+                                   f"MelSpectrogram+AmplitudeToDB+normalise loop ({feat_s / args.steps:.3f} s/step) + "
+                                   f"CNNAudioGRU fp32 forward in one batch ({fwd_s / args.steps:.3f} s/step); "
+                                   f"wall {time.perf_counter() - t0:.1f} s",
+                         "host_cpus": os.cpu_count() or 1, "torch": torch.__version__},
         "e2e": {"value": value, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -168,6 +215,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="utterances per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work spent on the cpu_baseline sample")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -223,11 +271,13 @@ def main():
     launches0 = native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     e0.record(stream)
     for i in range(args.steps):
         logits = step_device(dev_waves[i % n_rot], feats)
     e1.record(stream)
     barrier()
+    sampler.mark()
     dev_ms = e0.elapsed_time(e1)
     launches = native.launch_count() - launches0
 
@@ -238,6 +288,7 @@ def main():
         dev_in.copy_(host, non_blocking=True)
         host_logits.copy_(step_device(dev_in, feats), non_blocking=True)
     barrier()
+    sampler.mark()
     t0 = time.perf_counter()
     for i in range(args.steps):
         dev_in.copy_(host, non_blocking=True)
@@ -245,6 +296,7 @@ def main():
         torch.cuda.current_stream().synchronize()              # the caller reads the step's result
     barrier()
     e2e_s = time.perf_counter() - t0
+    sampler.mark()
     clocks = sampler.stop()
 
     # ---- per-stage device times: separate pass with events around every stage ------------------------------
@@ -305,14 +357,15 @@ def main():
             "roofline": roofline, "frontend_roofline": fr, "stages": stage_out,
         }
         if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
-            cpu_reference_arm(native_synth, 8)
-            v, (fs, ws), _ = cpu_reference_arm(native_synth, 64)
-            line["cpu_baseline"] = {"value": v, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"64 of the 256 utterances: per-utterance torchaudio feature loop "
-                                              f"{fs:.2f} s + CNNAudioGRU fp32 batched forward {ws:.2f} s",
-                                    "host_cpus": cores}
+            arm = CpuArm(native_synth, B)
+            arm.step()
+            n_steps, fs, ws = arm.run_for(args.cpu_seconds)
+            line["cpu_baseline"] = {"value": arm.n * n_steps / (fs + ws), "unit": "utt/s", "cores": arm.threads,
+                                    "kind": "port",
+                                    "sample": f"{n_steps} passes over the {arm.n}-utterance batch ({fs + ws:.1f} s of CPU "
+                                              f"work): per-utterance torchaudio feature loop {fs / n_steps:.3f} s + "
+                                              f"CNNAudioGRU fp32 batched forward {ws / n_steps:.3f} s per pass",
+                                    "host_cpus": os.cpu_count() or 1}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
