@@ -114,8 +114,9 @@ void sir_model_destroy(sir_model* m);
 /* sir_model_load_weights  <->  nn.Module.load_state_dict          scripts/evaluate.py:48, test_model.py:42
  * `weights` is ONE contiguous fp32 buffer (host or device pointer) holding the state_dict tensors in the
  * order of speech-intent-recognizer_b200/utils/synth.py:state_dict_spec (conv/bn 1..3, gru l0, l0_reverse,
- * l1, l1_reverse as weight_ih, weight_hh, bias_ih, bias_hh, attention, fc).  BatchNorm is folded for
- * inference (eval mode, eps = bn_eps).  Synchronises the stream. */
+ * l1, l1_reverse as weight_ih, weight_hh, bias_ih, bias_hh, attention, fc).  The buffer is copied into the
+ * handle and repacked ON THE DEVICE (one kernel; BatchNorm folded for inference with eps = bn_eps), all ordered
+ * on `stream`: a device source is never synchronised with the host. */
 int sir_model_load_weights(sir_model* m, const float* weights, int64_t count, float bn_eps, void* stream);
 int64_t sir_model_weight_count(const sir_model* m);
 
@@ -125,6 +126,47 @@ int64_t sir_model_weight_count(const sir_model* m);
  * n_frames >= 8. */
 int sir_model_forward(sir_model* m, const float* d_features, int batch, int n_frames, float* d_logits,
                       void* stream);
+
+/* ---- training step --------------------------------------------------------------------------------------
+ * The device work of scripts/train.py:80-116 (model.train() forward, CrossEntropyLoss, backward, Adam, GradScaler
+ * unscale / inf-skip).  Parameters, gradients and Adam moments are FLAT fp32 device buffers owned by the caller,
+ * in the same state_dict order as sir_model_load_weights (gradient slots of the BatchNorm running statistics are
+ * written as zeros).  The data-parallel job all-reduces d_grads (one NCCL call) between sir_model_backward and
+ * sir_adam_step.
+ *
+ * sir_model_train_forward  <->  CNNAudioGRU.forward in train mode      models/models.py:41-68 under model.train()
+ *   BatchNorm uses batch statistics and updates running_mean / running_var inside d_params (momentum, unbiased
+ *   variance; num_batches_tracked stays with the caller); the inter-layer GRU dropout (p = 0.5) keeps the elements
+ *   of d_dropout_keep ([batch * n_frames/8 * 512] bytes, 1 = keep) or, when that is NULL, draws them from
+ *   Philox4x32-10 keyed on (seed, offset).  Activations are kept inside the handle for sir_model_backward;
+ *   d_features must stay alive until then.  n_frames % 8 == 0, n_mels == 64.
+ */
+int sir_model_train_forward(sir_model* m, float* d_params, const float* d_features, int batch, int n_frames,
+                            const uint8_t* d_dropout_keep, uint64_t seed, uint64_t offset, float bn_momentum,
+                            float bn_eps, float* d_logits, void* stream);
+
+/* sir_model_backward  <->  loss.backward() through the model            scripts/train.py:99,107
+ *   d_dlogits [batch, num_classes] -> d_grads [sir_model_weight_count] (overwritten, not accumulated). */
+int sir_model_backward(sir_model* m, const float* d_params, const float* d_dlogits, float* d_grads, void* stream);
+
+/* sir_cross_entropy  <->  nn.CrossEntropyLoss()(output, label) + its backward    scripts/train.py:96,106,243
+ *   d_loss[0] = mean_b( logsumexp(logits_b) - logits_b[label_b] );
+ *   d_dlogits (may be NULL) = scale * (softmax(logits) - onehot(label)) / batch   (scale = the GradScaler loss scale) */
+int sir_cross_entropy(const float* d_logits, const int64_t* d_labels, int batch, int num_classes, float scale,
+                      float* d_loss, float* d_dlogits, void* stream);
+
+/* sir_grad_nonfinite: *d_flag = 1.0f if any of the `count` gradients is inf/nan (left untouched otherwise)
+ *   <->  the inf check of GradScaler.unscale_/step   scripts/train.py:100 */
+int sir_grad_nonfinite(const float* d_grads, int64_t count, float* d_flag, void* stream);
+
+/* sir_adam_step  <->  scaler.step(optimizer) with optim.Adam(lr, weight_decay)   scripts/train.py:100,246-250
+ *   torch.optim.Adam semantics (coupled L2: g = grad * inv_scale + weight_decay * p, bias-corrected moments, no
+ *   amsgrad) over `n_segments` (<= 4) ranges of the flat buffers, `segments` = HOST array of (offset, count)
+ *   pairs - the parameter ranges between the BatchNorm running statistics.  The whole update is skipped when
+ *   *d_found_inf != 0 (d_found_inf may be NULL). */
+int sir_adam_step(float* d_params, const float* d_grads, float* d_exp_avg, float* d_exp_avg_sq, const int64_t* segments,
+                  int n_segments, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                  float inv_scale, const float* d_found_inf, void* stream);
 
 /* sir_gemm_nt_split_f16: C[M,N] = A[M,K] W[N,K]^T + bias[N] on the 5th-gen tensor cores (tcgen05, TMEM
  * accumulators, TMA-staged operands) with the 3-pass fp16 hi/lo operand split that keeps fp32-level accuracy.

@@ -38,6 +38,13 @@ SIGNATURES = {
     "sir_model_load_weights": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "sir_model_weight_count": (c_int64, [c_void_p]),
     "sir_model_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "sir_model_train_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_uint64, c_uint64, c_float,
+                                        c_float, c_void_p, c_void_p]),
+    "sir_model_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sir_cross_entropy": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "sir_grad_nonfinite": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "sir_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int, c_float, c_float, c_float,
+                              c_float, c_float, c_int, c_float, c_void_p, c_void_p]),
     "sir_gemm_nt_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "sir_pipeline_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p]),
@@ -228,6 +235,32 @@ class Model:
         check(load_library().sir_model_forward(self._h, ptr(feat), B, T, ptr(logits), stream_ptr()), "sir_model_forward")
         return logits
 
+    # -- training step pieces (flat fp32 parameter / gradient buffers owned by the caller) ---------------------
+    def train_forward(self, flat_params: torch.Tensor, feat: torch.Tensor, dropout_keep: torch.Tensor = None, seed: int = 0,
+                      offset: int = 0, bn_momentum: float = 0.1, bn_eps: float = 1e-5) -> torch.Tensor:
+        """Train-mode forward; ``feat`` (contiguous, CUDA) must stay alive until ``backward``."""
+        require_cuda(flat_params, "flat_params")
+        require_cuda(feat, "features")
+        assert flat_params.is_contiguous() and feat.is_contiguous() and flat_params.numel() >= self.weight_count()
+        B, M, T = feat.shape
+        if dropout_keep is not None:
+            require_cuda(dropout_keep, "dropout_keep", torch.uint8)
+            assert dropout_keep.is_contiguous() and dropout_keep.numel() == B * (T // 8) * 512
+        logits = torch.empty((B, self.num_classes), device=feat.device, dtype=torch.float32)
+        check(load_library().sir_model_train_forward(self._h, ptr(flat_params), ptr(feat), B, T, ptr(dropout_keep), int(seed),
+                                                     int(offset), float(bn_momentum), float(bn_eps), ptr(logits),
+                                                     stream_ptr()), "sir_model_train_forward")
+        return logits
+
+    def backward(self, flat_params: torch.Tensor, dlogits: torch.Tensor, flat_grads: torch.Tensor):
+        """``dlogits [B, C]`` -> every parameter gradient, written into ``flat_grads[:weight_count]``."""
+        require_cuda(dlogits, "dlogits")
+        require_cuda(flat_grads, "flat_grads")
+        assert dlogits.is_contiguous() and flat_grads.is_contiguous() and flat_grads.numel() >= self.weight_count()
+        check(load_library().sir_model_backward(self._h, ptr(flat_params), ptr(dlogits), ptr(flat_grads), stream_ptr()),
+              "sir_model_backward")
+        return flat_grads
+
     def pipeline(self, fe: Frontend, wave, lengths=None, max_samples=0, out_frames=200, features=None):
         require_cuda(wave, "wave")
         B, L = wave.shape
@@ -239,3 +272,35 @@ class Model:
                                                   int(max_samples or 0), out_frames, ptr(features), ptr(logits),
                                                   stream_ptr()), "sir_pipeline_forward")
         return logits, features
+
+
+def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, scale: float = 1.0, loss_out: torch.Tensor = None,
+                  need_grad: bool = True):
+    """Mean cross-entropy and ``scale * d loss / d logits`` in one launch -> ``(loss[1], dlogits | None)``."""
+    require_cuda(logits, "logits")
+    require_cuda(labels, "labels", torch.int64)
+    logits, labels = logits.contiguous(), labels.contiguous()
+    B, C = logits.shape
+    loss = loss_out if loss_out is not None else torch.empty(1, device=logits.device, dtype=torch.float32)
+    dlogits = torch.empty_like(logits) if need_grad else None
+    check(load_library().sir_cross_entropy(ptr(logits), ptr(labels), B, C, float(scale), ptr(loss), ptr(dlogits),
+                                           stream_ptr()), "sir_cross_entropy")
+    return loss, dlogits
+
+
+def grad_nonfinite(grads: torch.Tensor, count: int, flag: torch.Tensor):
+    """``flag[0] = 1.0`` if any of ``grads[:count]`` is inf/nan (flag must be zeroed by the caller)."""
+    require_cuda(grads, "grads")
+    require_cuda(flag, "flag")
+    check(load_library().sir_grad_nonfinite(ptr(grads), int(count), ptr(flag), stream_ptr()), "sir_grad_nonfinite")
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, segments, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, step=1,
+              inv_scale=1.0, found_inf: torch.Tensor = None):
+    """Fused unscale + torch.optim.Adam update over ``segments`` = [(offset, count), ...] of the flat buffers."""
+    for t, n in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        require_cuda(t, n)
+    seg = (c_int64 * (2 * len(segments)))(*[int(v) for pair in segments for v in pair])
+    check(load_library().sir_adam_step(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), seg, len(segments), float(lr),
+                                       float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
+                                       float(inv_scale), ptr(found_inf), stream_ptr()), "sir_adam_step")

@@ -18,21 +18,9 @@
 #include <cstring>
 #include <vector>
 
-#include "sir_common.cuh"
-#include "tc_common.cuh"
+#include "model.cuh"
 
 namespace sir {
-
-namespace tc {
-int tc_gemm_nt(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo, const float* bias,
-               float* C, int M, int N, int K, cudaStream_t st, const char* name);
-template <int CIN, int COUT>
-int tc_conv3x3(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
-               __half* out_hi, __half* out_lo, int B, int H, int W, int out_whc, cudaStream_t st, const char* name);
-int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint32_t* box);
-int gru_layer_tc(const CUtensorMap& tm_w_hi, const CUtensorMap& tm_w_lo, const float* gi, const float* bhh, float* y,
-                 __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st);
-}  // namespace tc
 
 // ---------------------------------------------------------------------------------------------------------
 // conv1 (C_in = 1): one thread per pooled pixel, all 32 output channels; output NHWC [B, H/2, W/2, 32] as
@@ -101,7 +89,8 @@ __global__ void __launch_bounds__(128) conv1_bn_relu_pool_kernel(const float* __
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) attention_fc_kernel(const float* __restrict__ y,      // [B, T, 512]
                                                            const float* __restrict__ att_w,  // [512]
-                                                           float att_b, const float* __restrict__ fc_w,  // [C][512]
+                                                           const float* __restrict__ att_b_ptr,
+                                                           const float* __restrict__ fc_w,  // [C][512]
                                                            const float* __restrict__ fc_b, float* __restrict__ logits,
                                                            int T, int C) {
     extern __shared__ float sm[];
@@ -109,6 +98,7 @@ __global__ void __launch_bounds__(128) attention_fc_kernel(const float* __restri
     float* ctx = sm + T;          // [512]
     __shared__ float s_red[2];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float att_b = __ldg(att_b_ptr);
     const float* __restrict__ yb = y + (int64_t)b * T * 512;
     for (int t = warp; t < T; t += 4) {
         float s = 0.f;
@@ -149,38 +139,174 @@ __global__ void __launch_bounds__(128) attention_fc_kernel(const float* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Device-side weight repack: flat state_dict-order fp32 parameters -> the layouts the kernels consume.  One
+// launch; runs once per load in eval mode (BatchNorm folded into the conv weights + a shift) and once per
+// step in training mode (raw conv weights; BatchNorm is applied with batch statistics by its own kernels).
+// ---------------------------------------------------------------------------------------------------------
+struct RepackParams {
+    const float* flat;
+    FlatOffsets off;
+    int fold;
+    float eps;
+    int C, gin, H8;
+    float *w1, *sh[3], *bih[2], *bhh[2], *bhh_perm[2], *att_w, *att_b, *fc_w, *fc_b;
+    __half *cw_hi[2], *cw_lo[2], *cwt_hi[2], *cwt_lo[2], *wih_hi[2], *wih_lo[2], *whh_hi[2], *whh_lo[2];
+    int64_t job_end[16];
+    int n_jobs;
+};
+
+__device__ __forceinline__ double bn_scale(const RepackParams& p, int l, int o) {
+    return (double)p.flat[p.off.bn_g[l] + o] / sqrt((double)p.flat[p.off.bn_v[l] + o] + (double)p.eps);
+}
+
+__device__ __forceinline__ void store_split(__half* hi, __half* lo, int64_t i, float x) {
+    __half h, l;
+    tc::split_f16(x, h, l);
+    hi[i] = h;
+    lo[i] = l;
+}
+
+__global__ void __launch_bounds__(256) repack_weights_kernel(const RepackParams p) {
+    const int64_t total = p.job_end[p.n_jobs - 1];
+    const int cin[3] = {1, 32, 64}, cout[3] = {32, 64, 128};
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        int job = 0;
+        while (g >= p.job_end[job]) ++job;
+        const int64_t i = g - (job ? p.job_end[job - 1] : 0);
+        const float* f = p.flat;
+        switch (job) {
+            case 0: {                                   // conv1 [32][9]
+                const int o = (int)(i / 9);
+                const float w = f[p.off.conv_w[0] + i];
+                p.w1[i] = p.fold ? (float)((double)w * bn_scale(p, 0, o)) : w;
+                break;
+            }
+            case 1: {                                   // BN shifts (eval): beta - mean * scale
+                int l = 0, o = (int)i;
+                while (o >= cout[l]) o -= cout[l++];
+                p.sh[l][o] = (float)((double)f[p.off.bn_b[l] + o] - (double)f[p.off.bn_m[l] + o] * bn_scale(p, l, o));
+                break;
+            }
+            case 2:
+            case 3: {                                   // conv2 / conv3 [tap][C_out][C_in]
+                const int l = job - 1, ci_n = cin[l], co_n = cout[l];
+                const int ci = (int)(i % ci_n), co = (int)((i / ci_n) % co_n), tap = (int)(i / ((int64_t)ci_n * co_n));
+                const float w = f[p.off.conv_w[l] + ((int64_t)co * ci_n + ci) * 9 + tap];
+                store_split(p.cw_hi[l - 1], p.cw_lo[l - 1], i, p.fold ? (float)((double)w * bn_scale(p, l, co)) : w);
+                break;
+            }
+            case 4:
+            case 5: {                                   // data-gradient weights [tap'][C_in][C_out], tap' = 8 - tap
+                const int l = job - 3, ci_n = cin[l], co_n = cout[l];
+                const int co = (int)(i % co_n), ci = (int)((i / co_n) % ci_n), tap = (int)(i / ((int64_t)ci_n * co_n));
+                const float w = f[p.off.conv_w[l] + ((int64_t)co * ci_n + ci) * 9 + (8 - tap)];
+                store_split(p.cwt_hi[l - 1], p.cwt_lo[l - 1], i, w);
+                break;
+            }
+            case 6:
+            case 7: {                                   // W_ih, both directions stacked along N; layer 0's columns
+                const int l = job - 6;                  // go from c * H8 + h (models.py:55-57) to h * 128 + c
+                const int in_sz = l == 0 ? p.gin : 512;
+                const int fp = (int)(i % in_sz);
+                const int n = (int)((i / in_sz) % 768), d = (int)(i / ((int64_t)in_sz * 768));
+                int fsrc = fp;
+                if (l == 0) {
+                    const int hh = fp / 128, c = fp % 128;
+                    fsrc = c * p.H8 + hh;
+                }
+                store_split(p.wih_hi[l], p.wih_lo[l], i, f[p.off.wih[l][d] + (int64_t)n * in_sz + fsrc]);
+                break;
+            }
+            case 8:
+            case 9: {                                   // W_hh as per-(direction, cluster rank) tiles, row = gate*32 + unit
+                const int l = job - 8;
+                const int k = (int)(i % 256), row = (int)((i / 256) % 96), r = (int)((i / (256 * 96)) % 8),
+                          d = (int)(i / (256 * 96 * 8));
+                const int gate = row / 32, u = row % 32;
+                store_split(p.whh_hi[l], p.whh_lo[l], i, f[p.off.whh[l][d] + (int64_t)(gate * 256 + r * 32 + u) * 256 + k]);
+                break;
+            }
+            case 10: {                                  // biases [layer][dir][768] (+ b_hh in the tile order above)
+                const int n = (int)(i % 768), d = (int)((i / 768) % 2), l = (int)(i / 1536);
+                p.bih[l][d * 768 + n] = f[p.off.bih[l][d] + n];
+                const float bh = f[p.off.bhh[l][d] + n];
+                p.bhh[l][d * 768 + n] = bh;
+                const int gate = n / 256, r = (n % 256) / 32, u = n % 32;
+                p.bhh_perm[l][d * 768 + r * 96 + gate * 32 + u] = bh;
+                break;
+            }
+            default: {                                  // attention + fc
+                if (i < 512) p.att_w[i] = f[p.off.att_w + i];
+                else if (i == 512) p.att_b[0] = f[p.off.att_b];
+                else if (i < 513 + (int64_t)p.C * 512) p.fc_w[i - 513] = f[p.off.fc_w + i - 513];
+                else p.fc_b[i - 513 - (int64_t)p.C * 512] = f[p.off.fc_b + i - 513 - (int64_t)p.C * 512];
+                break;
+            }
+        }
+    }
+}
+
+int model_repack(sir_model* m, const float* d_flat, bool fold_bn, float bn_eps, cudaStream_t st) {
+    RepackParams p{};
+    p.flat = d_flat;
+    p.off = m->off;
+    p.fold = fold_bn ? 1 : 0;
+    p.eps = bn_eps;
+    p.C = m->num_classes;
+    p.gin = m->gru_in;
+    p.H8 = m->n_mels / 8;
+    p.w1 = m->w1;
+    p.sh[0] = m->sh1;
+    p.sh[1] = m->sh2;
+    p.sh[2] = m->sh3;
+    p.cw_hi[0] = m->w2_hi;
+    p.cw_lo[0] = m->w2_lo;
+    p.cw_hi[1] = m->w3_hi;
+    p.cw_lo[1] = m->w3_lo;
+    p.cwt_hi[0] = m->w2t_hi;
+    p.cwt_lo[0] = m->w2t_lo;
+    p.cwt_hi[1] = m->w3t_hi;
+    p.cwt_lo[1] = m->w3t_lo;
+    for (int l = 0; l < 2; ++l) {
+        p.bih[l] = m->bih[l];
+        p.bhh[l] = m->bhh[l];
+        p.bhh_perm[l] = m->bhh_perm[l];
+        p.wih_hi[l] = m->wih_hi[l];
+        p.wih_lo[l] = m->wih_lo[l];
+        p.whh_hi[l] = m->whh_hi[l];
+        p.whh_lo[l] = m->whh_lo[l];
+    }
+    p.att_w = m->att_w;
+    p.att_b = m->att_b;
+    p.fc_w = m->fc_w;
+    p.fc_b = m->fc_b;
+    const int64_t counts[12] = {288, 224, 9 * 64 * 32, 9 * 128 * 64, fold_bn ? 0 : 9 * 64 * 32, fold_bn ? 0 : 9 * 128 * 64,
+                                (int64_t)1536 * m->gru_in, 1536 * 512, 2 * 8 * 96 * 256, 2 * 8 * 96 * 256, 2 * 1536,
+                                513 + (int64_t)m->num_classes * 513};
+    int64_t acc = 0;
+    for (int j = 0; j < 12; ++j) {
+        acc += counts[j];
+        p.job_end[j] = acc;
+    }
+    p.n_jobs = 12;
+    repack_weights_kernel<<<148 * 8, 256, 0, st>>>(p);
+    SIR_CHECK_LAUNCH("repack_weights_kernel");
+    return SIR_OK;
+}
+
+int launch_attention_fc(const sir_model* m, const float* y, float* logits, int B, int T, cudaStream_t st) {
+    const size_t smem = (size_t)(T + 512) * sizeof(float);
+    ProfScope ps("attention_fc", st);
+    attention_fc_kernel<<<(unsigned)B, 128, smem, st>>>(y, m->att_w, m->att_b, m->fc_w, m->fc_b, logits, T, m->num_classes);
+    SIR_CHECK_LAUNCH("attention_fc_kernel");
+    return SIR_OK;
+}
+
 }  // namespace sir
 
 // ---- C ABI ------------------------------------------------------------------------------------------------
 using namespace sir;
-
-struct sir_model {
-    int num_classes = 31, n_mels = 64, gru_in = 1024;
-    bool loaded = false;
-    float att_b = 0.f;
-    DeviceBuffer weights;        // repacked fp32 parameters
-    DeviceBuffer weights_h;      // fp16 (hi, lo) operands of the tensor-core contractions
-    DeviceBuffer work;           // activations
-    // fp32 pointers into `weights`
-    float *w1 = nullptr, *sh1 = nullptr, *sh2 = nullptr, *sh3 = nullptr;
-    float *bih[2] = {nullptr, nullptr}, *bhh[2] = {nullptr, nullptr};
-    float *att_w = nullptr, *fc_w = nullptr, *fc_b = nullptr;
-    // fp16 pointers into `weights_h`: conv weights [tap][C_out][C_in] (BN scale folded), W_ih [1536][K]
-    __half *w2_hi = nullptr, *w2_lo = nullptr, *w3_hi = nullptr, *w3_lo = nullptr;
-    __half *wih_hi[2] = {nullptr, nullptr}, *wih_lo[2] = {nullptr, nullptr};
-    // recurrent weights as per-CTA UMMA tiles [2 dirs][8 ranks][96][256] (gru_tc.cu) + their TMA maps
-    __half *whh_hi[2] = {nullptr, nullptr}, *whh_lo[2] = {nullptr, nullptr};
-    CUtensorMap tm_whh_hi[2], tm_whh_lo[2];
-};
-
-static int64_t model_weight_count(int num_classes, int n_mels) {
-    const int64_t gin = 128 * (n_mels / 8);
-    int64_t n = 32 * 9 + 4 * 32 + 64 * 32 * 9 + 4 * 64 + 128 * 64 * 9 + 4 * 128;
-    n += 2 * (768 * gin + 768 * 256 + 768 + 768);
-    n += 2 * (768 * 512 + 768 * 256 + 768 + 768);
-    n += 512 + 1 + (int64_t)num_classes * 512 + num_classes;
-    return n;
-}
 
 extern "C" int sir_model_create(sir_model** out, int num_classes, int n_mels) {
     if (!out) return fail(SIR_ERR_INVALID, "sir_model_create: out is NULL");
@@ -195,172 +321,106 @@ extern "C" int sir_model_create(sir_model** out, int num_classes, int n_mels) {
     m->num_classes = num_classes;
     m->n_mels = n_mels;
     m->gru_in = 128 * (n_mels / 8);
+    m->off = make_offsets(num_classes, n_mels);
+    // carve the repacked-weight buffers (sizes depend on the architecture only)
+    const int gin = m->gru_in, C = num_classes;
+    size_t nf = 0, nh = 0;
+    auto f32 = [&](size_t n) {
+        const size_t o = nf;
+        nf += (n + 3) & ~(size_t)3;
+        return o;
+    };
+    auto f16 = [&](size_t n) {
+        const size_t o = nh;
+        nh += (n + 63) & ~(size_t)63;           // 128-byte aligned sections (TMA global addresses)
+        return o;
+    };
+    const size_t o_w1 = f32(288), o_s1 = f32(32), o_s2 = f32(64), o_s3 = f32(128);
+    size_t o_bih[2], o_bhh[2], o_bhp[2];
+    for (int l = 0; l < 2; ++l) {
+        o_bih[l] = f32(1536);
+        o_bhh[l] = f32(1536);
+        o_bhp[l] = f32(1536);
+    }
+    const size_t o_aw = f32(512), o_ab = f32(1), o_fw = f32((size_t)C * 512), o_fb = f32(C);
+    const size_t h_w2h = f16(9 * 64 * 32), h_w2l = f16(9 * 64 * 32), h_w3h = f16(9 * 128 * 64), h_w3l = f16(9 * 128 * 64);
+    const size_t h_w2th = f16(9 * 64 * 32), h_w2tl = f16(9 * 64 * 32), h_w3th = f16(9 * 128 * 64),
+                 h_w3tl = f16(9 * 128 * 64);
+    size_t h_ih[2][2], h_hh[2][2];
+    for (int l = 0; l < 2; ++l) {
+        const size_t n = (size_t)1536 * (l == 0 ? gin : 512);
+        h_ih[l][0] = f16(n);
+        h_ih[l][1] = f16(n);
+        h_hh[l][0] = f16(2 * 8 * 96 * 256);
+        h_hh[l][1] = f16(2 * 8 * 96 * 256);
+    }
+    int rc = m->packed.reserve(nf * sizeof(float));
+    if (rc == SIR_OK) rc = m->halves.reserve(nh * sizeof(__half) + 256);
+    if (rc != SIR_OK) {
+        sir_model_destroy(m);
+        return rc;
+    }
+    float* base = (float*)m->packed.ptr;
+    __half* hb = (__half*)m->halves.ptr;
+    m->w1 = base + o_w1;
+    m->sh1 = base + o_s1;
+    m->sh2 = base + o_s2;
+    m->sh3 = base + o_s3;
+    m->att_w = base + o_aw;
+    m->att_b = base + o_ab;
+    m->fc_w = base + o_fw;
+    m->fc_b = base + o_fb;
+    m->w2_hi = hb + h_w2h;
+    m->w2_lo = hb + h_w2l;
+    m->w3_hi = hb + h_w3h;
+    m->w3_lo = hb + h_w3l;
+    m->w2t_hi = hb + h_w2th;
+    m->w2t_lo = hb + h_w2tl;
+    m->w3t_hi = hb + h_w3th;
+    m->w3t_lo = hb + h_w3tl;
+    for (int l = 0; l < 2; ++l) {
+        m->bih[l] = base + o_bih[l];
+        m->bhh[l] = base + o_bhh[l];
+        m->bhh_perm[l] = base + o_bhp[l];
+        m->wih_hi[l] = hb + h_ih[l][0];
+        m->wih_lo[l] = hb + h_ih[l][1];
+        m->whh_hi[l] = hb + h_hh[l][0];
+        m->whh_lo[l] = hb + h_hh[l][1];
+        const uint64_t wd[2] = {256, 2 * 8 * 96};
+        const uint32_t wb[2] = {64, 96};
+        if ((rc = tc::make_tmap(&m->tm_whh_hi[l], m->whh_hi[l], 2, wd, wb)) ||
+            (rc = tc::make_tmap(&m->tm_whh_lo[l], m->whh_lo[l], 2, wd, wb))) {
+            sir_model_destroy(m);
+            return rc;
+        }
+    }
     *out = m;
     return SIR_OK;
 }
 
 extern "C" void sir_model_destroy(sir_model* m) {
     if (!m) return;
-    m->weights.release();
-    m->weights_h.release();
+    m->flat.release();
+    m->packed.release();
+    m->halves.release();
     m->work.release();
+    m->train_ws.release();
     delete m;
 }
 
-extern "C" int64_t sir_model_weight_count(const sir_model* m) {
-    return m ? model_weight_count(m->num_classes, m->n_mels) : 0;
-}
-
-namespace {
-
-struct HalfPack {                       // host staging of the fp16 (hi, lo) arrays, 128-byte aligned sections
-    std::vector<__half> data;
-    size_t add(const std::vector<float>& v, bool lo) {
-        while (data.size() % 64) data.push_back(__float2half_rn(0.f));
-        const size_t off = data.size();
-        for (float x : v) {
-            x = std::fmin(std::fmax(x, -65504.f), 65504.f);
-            const __half h = __float2half_rn(x);
-            data.push_back(lo ? __float2half_rn(x - __half2float(h)) : h);
-        }
-        return off;
-    }
-};
-
-}  // namespace
+extern "C" int64_t sir_model_weight_count(const sir_model* m) { return m ? m->off.total : 0; }
 
 extern "C" int sir_model_load_weights(sir_model* m, const float* weights, int64_t count, float bn_eps, void* stream) {
     if (!m || !weights) return fail(SIR_ERR_INVALID, "sir_model_load_weights: NULL argument");
-    const int64_t want = model_weight_count(m->num_classes, m->n_mels);
-    if (count != want)
-        return fail(SIR_ERR_INVALID, "sir_model_load_weights: expected %lld floats, got %lld", (long long)want,
+    if (count != m->off.total)
+        return fail(SIR_ERR_INVALID, "sir_model_load_weights: expected %lld floats, got %lld", (long long)m->off.total,
                     (long long)count);
     cudaStream_t st = (cudaStream_t)stream;
-    SIR_CUDA(cudaStreamSynchronize(st));
-    std::vector<float> h((size_t)count);
-    SIR_CUDA(cudaMemcpy(h.data(), weights, (size_t)count * sizeof(float), cudaMemcpyDefault));
-    const int gin = m->gru_in, C = m->num_classes, H8 = m->n_mels / 8;
-    const float* p = h.data();               // walk the flat buffer in state_dict_spec order
-    auto take = [&](int64_t n) {
-        const float* r = p;
-        p += n;
-        return r;
-    };
-    const int cin[3] = {1, 32, 64}, cout[3] = {32, 64, 128};
-    std::vector<float> packed;
-    HalfPack hp;
-    auto al4 = [&]() {
-        while (packed.size() % 4) packed.push_back(0.f);
-    };
-    size_t off_w1 = 0, off_s[3], off_cw_hi[3] = {0, 0, 0}, off_cw_lo[3] = {0, 0, 0};
-    for (int l = 0; l < 3; ++l) {
-        const float* w = take((int64_t)cout[l] * cin[l] * 9);
-        const float *g = take(cout[l]), *bt = take(cout[l]), *mu = take(cout[l]), *var = take(cout[l]);
-        std::vector<double> scale(cout[l]);
-        for (int o = 0; o < cout[l]; ++o) scale[o] = (double)g[o] / std::sqrt((double)var[o] + (double)bn_eps);
-        if (l == 0) {                                 // [32][9] fp32
-            al4();
-            off_w1 = packed.size();
-            for (int o = 0; o < 32; ++o)
-                for (int k = 0; k < 9; ++k) packed.push_back((float)((double)w[o * 9 + k] * scale[o]));
-        } else {                                      // [tap][cout][cin] -> fp16 hi/lo, K (= cin) contiguous
-            std::vector<float> wt((size_t)9 * cout[l] * cin[l]);
-            for (int k = 0; k < 9; ++k)
-                for (int o = 0; o < cout[l]; ++o)
-                    for (int i = 0; i < cin[l]; ++i)
-                        wt[((size_t)k * cout[l] + o) * cin[l] + i] =
-                            (float)((double)w[((int64_t)o * cin[l] + i) * 9 + k] * scale[o]);
-            off_cw_hi[l] = hp.add(wt, false);
-            off_cw_lo[l] = hp.add(wt, true);
-        }
-        al4();
-        off_s[l] = packed.size();
-        for (int o = 0; o < cout[l]; ++o) packed.push_back((float)((double)bt[o] - (double)mu[o] * scale[o]));
-    }
-    size_t off_bih[2], off_bhh[2], off_wih_hi[2], off_wih_lo[2], off_whh_hi[2], off_whh_lo[2];
-    for (int l = 0; l < 2; ++l) {
-        const int in_sz = l == 0 ? gin : 512;
-        const float *wih[2], *whh[2], *bih[2], *bhh[2];
-        for (int d = 0; d < 2; ++d) {
-            wih[d] = take((int64_t)768 * in_sz);
-            whh[d] = take((int64_t)768 * 256);
-            bih[d] = take(768);
-            bhh[d] = take(768);
-        }
-        // both directions stacked along N; layer 0's columns are re-ordered from the reference's
-        // c * H8 + h (models/models.py:55-57) to h * 128 + c, the channels-last order conv3 writes
-        std::vector<float> wcat((size_t)1536 * in_sz);
-        for (int d = 0; d < 2; ++d)
-            for (int n = 0; n < 768; ++n)
-                for (int f = 0; f < in_sz; ++f) {
-                    int fp = f;
-                    if (l == 0) {
-                        const int c = f / H8, hh = f % H8;
-                        fp = hh * 128 + c;
-                    }
-                    wcat[((size_t)d * 768 + n) * in_sz + fp] = wih[d][(size_t)n * in_sz + f];
-                }
-        off_wih_hi[l] = hp.add(wcat, false);
-        off_wih_lo[l] = hp.add(wcat, true);
-        al4();
-        off_bih[l] = packed.size();
-        for (int d = 0; d < 2; ++d) packed.insert(packed.end(), bih[d], bih[d] + 768);
-        // recurrent weights: per (direction, cluster rank) a 96-row tile, row = gate*32 + local unit
-        std::vector<float> wt((size_t)2 * 8 * 96 * 256, 0.f);
-        for (int d = 0; d < 2; ++d)
-            for (int r = 0; r < 8; ++r)
-                for (int g = 0; g < 3; ++g)
-                    for (int u = 0; u < 32; ++u)
-                        std::memcpy(&wt[(((size_t)d * 8 + r) * 96 + g * 32 + u) * 256],
-                                    whh[d] + (size_t)(g * 256 + r * 32 + u) * 256, 256 * sizeof(float));
-        off_whh_hi[l] = hp.add(wt, false);
-        off_whh_lo[l] = hp.add(wt, true);
-        off_bhh[l] = packed.size();
-        for (int d = 0; d < 2; ++d) packed.insert(packed.end(), bhh[d], bhh[d] + 768);
-    }
-    const float* aw = take(512);
-    const float* ab = take(1);
-    const float* fw = take((int64_t)C * 512);
-    const float* fb = take(C);
-    al4();
-    const size_t off_att = packed.size();
-    packed.insert(packed.end(), aw, aw + 512);
-    const size_t off_fcw = packed.size();
-    packed.insert(packed.end(), fw, fw + (int64_t)C * 512);
-    const size_t off_fcb = packed.size();
-    packed.insert(packed.end(), fb, fb + C);
-    m->att_b = ab[0];
-    int rc = m->weights.reserve(packed.size() * sizeof(float));
+    int rc = m->flat.reserve((size_t)count * sizeof(float));
     if (rc != SIR_OK) return rc;
-    rc = m->weights_h.reserve(hp.data.size() * sizeof(__half));
-    if (rc != SIR_OK) return rc;
-    SIR_CUDA(cudaMemcpy(m->weights.ptr, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
-    SIR_CUDA(cudaMemcpy(m->weights_h.ptr, hp.data.data(), hp.data.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    float* base = (float*)m->weights.ptr;
-    __half* hb = (__half*)m->weights_h.ptr;
-    m->w1 = base + off_w1;
-    m->sh1 = base + off_s[0];
-    m->sh2 = base + off_s[1];
-    m->sh3 = base + off_s[2];
-    m->w2_hi = hb + off_cw_hi[1];
-    m->w2_lo = hb + off_cw_lo[1];
-    m->w3_hi = hb + off_cw_hi[2];
-    m->w3_lo = hb + off_cw_lo[2];
-    for (int l = 0; l < 2; ++l) {
-        m->wih_hi[l] = hb + off_wih_hi[l];
-        m->wih_lo[l] = hb + off_wih_lo[l];
-        m->bih[l] = base + off_bih[l];
-        m->bhh[l] = base + off_bhh[l];
-        m->whh_hi[l] = hb + off_whh_hi[l];
-        m->whh_lo[l] = hb + off_whh_lo[l];
-        const uint64_t wd[2] = {256, 2 * 8 * 96};
-        const uint32_t wb[2] = {64, 96};
-        if ((rc = tc::make_tmap(&m->tm_whh_hi[l], m->whh_hi[l], 2, wd, wb))) return rc;
-        if ((rc = tc::make_tmap(&m->tm_whh_lo[l], m->whh_lo[l], 2, wd, wb))) return rc;
-    }
-    m->att_w = base + off_att;
-    m->fc_w = base + off_fcw;
-    m->fc_b = base + off_fcb;
+    // host or device source; ordered on `st` with the repack and with later forwards
+    SIR_CUDA(cudaMemcpyAsync(m->flat.ptr, weights, (size_t)count * sizeof(float), cudaMemcpyDefault, st));
+    if ((rc = model_repack(m, (const float*)m->flat.ptr, true, bn_eps, st))) return rc;
     m->loaded = true;
     return SIR_OK;
 }
@@ -409,12 +469,12 @@ int model_forward_chunk(sir_model* m, const Workspace& ws, const float* feat, in
         conv1_bn_relu_pool_kernel<<<grid, 128, 0, st>>>(feat, m->w1, m->sh1, ws.act1_hi, ws.act1_lo, H, W);
         SIR_CHECK_LAUNCH("conv1_bn_relu_pool_kernel");
     }
-    if ((rc = tc::tc_conv3x3<32, 64>(ws.act1_hi, ws.act1_lo, m->w2_hi, m->w2_lo, m->sh2, ws.act2_hi, ws.act2_lo, B, H2,
-                                     W2, 0, st, "conv2_bn_relu_pool")))
+    if ((rc = tc::tc_conv3x3<32, 64>(ws.act1_hi, ws.act1_lo, m->w2_hi, m->w2_lo, m->sh2, ws.act2_hi, ws.act2_lo, nullptr, B,
+                                     H2, W2, 0, st, "conv2_bn_relu_pool")))
         return rc;
     // conv3 writes [B][T/8][H/8][128]: the GRU input, time-major with channels-last features
-    if ((rc = tc::tc_conv3x3<64, 128>(ws.act2_hi, ws.act2_lo, m->w3_hi, m->w3_lo, m->sh3, ws.gin_hi, ws.gin_lo, B, H4,
-                                      W4, 1, st, "conv3_bn_relu_pool")))
+    if ((rc = tc::tc_conv3x3<64, 128>(ws.act2_hi, ws.act2_lo, m->w3_hi, m->w3_lo, m->sh3, ws.gin_hi, ws.gin_lo, nullptr, B,
+                                      H4, W4, 1, st, "conv3_bn_relu_pool")))
         return rc;
     const __half *x_hi = ws.gin_hi, *x_lo = ws.gin_lo;
     int in_sz = m->gru_in;
@@ -434,13 +494,7 @@ int model_forward_chunk(sir_model* m, const Workspace& ws, const float* feat, in
         x_lo = ws.y0_lo;
         in_sz = 512;
     }
-    {
-        const size_t smem = (size_t)(Tg + 512) * sizeof(float);
-        ProfScope ps("attention_fc", st);
-        attention_fc_kernel<<<(unsigned)B, 128, smem, st>>>(ws.y1, m->att_w, m->att_b, m->fc_w, m->fc_b, logits, Tg,
-                                                             m->num_classes);
-        SIR_CHECK_LAUNCH("attention_fc_kernel");
-    }
+    if ((rc = launch_attention_fc(m, ws.y1, logits, B, Tg, st))) return rc;
     return SIR_OK;
 }
 

@@ -26,6 +26,7 @@
 
 #include "frontend_tables.h"
 #include "logmel_frame.cuh"
+#include "philox.cuh"
 #include "sir_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -321,32 +322,6 @@ __global__ void amplitude_to_db_kernel(const float* __restrict__ in, float* __re
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = 10.0f * log10f(fmaxf(in[i], 1e-10f));
 }
-
-__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-    c[0] = n0;
-    c[1] = n1;
-    c[2] = n2;
-    c[3] = n3;
-}
-
-__device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t index, uint32_t block, uint32_t (&c)[4]) {
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    c[0] = (uint32_t)index;
-    c[1] = (uint32_t)(index >> 32);
-    c[2] = block;
-    c[3] = 0u;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        philox_round(c, k0, k1);
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-}
-
-__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
 // One thread per utterance: the draws of scripts/dataset.py:105,166-171 + torchaudio mask_along_axis.
 __global__ void specaugment_sample_kernel(uint64_t seed, uint64_t first_index, int batch, int n_mels, int n_frames,

@@ -29,7 +29,7 @@ namespace sir {
 namespace tc {
 
 constexpr int kTcThreads = 192;
-enum { kModeGemm = 0, kModeConv = 1 };
+enum { kModeGemm = 0, kModeConv = 1, kModeConvRaw = 2 };   // ConvRaw: no pool / shift / ReLU, fp32 NHWC output
 
 struct TcParams {
     int num_kblocks;
@@ -43,6 +43,8 @@ struct TcParams {
     __half* out_hi;
     __half* out_lo;
     int out_whc;        // 0: [B][H2][W2][C]   1: [B][W2][H2][C]  (the GRU input order: time-major, then mel, then channel)
+    int kc;             // CONV: k-blocks per tap (C_in / BLOCK_K)
+    float* raw_out;     // CONV_RAW: fp32 [B][H][W][BLOCK_N]
 };
 
 template <int MODE, int BLOCK_N, int BLOCK_K, int STAGES>
@@ -114,11 +116,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     tma_load_2d(st + 2 * L::kABytes, &tm_b_hi, &full[s], kb * BLOCK_K, n0);
                     tma_load_2d(st + 2 * L::kABytes + L::kBBytes, &tm_b_lo, &full[s], kb * BLOCK_K, n0);
                 } else {
-                    const int kh = kb / 3, kw = kb - kh * 3;
-                    tma_load_4d(st, &tm_a_hi, &full[s], 0, x0 + kw - 1, y0 + kh - 1, img);
-                    tma_load_4d(st + L::kABytes, &tm_a_lo, &full[s], 0, x0 + kw - 1, y0 + kh - 1, img);
-                    tma_load_2d(st + 2 * L::kABytes, &tm_b_hi, &full[s], 0, kb * BLOCK_N);
-                    tma_load_2d(st + 2 * L::kABytes + L::kBBytes, &tm_b_lo, &full[s], 0, kb * BLOCK_N);
+                    const int tap = kb / p.kc, c0 = (kb - tap * p.kc) * BLOCK_K;
+                    const int kh = tap / 3, kw = tap - kh * 3;
+                    tma_load_4d(st, &tm_a_hi, &full[s], c0, x0 + kw - 1, y0 + kh - 1, img);
+                    tma_load_4d(st + L::kABytes, &tm_a_lo, &full[s], c0, x0 + kw - 1, y0 + kh - 1, img);
+                    tma_load_2d(st + 2 * L::kABytes, &tm_b_hi, &full[s], c0, tap * BLOCK_N);
+                    tma_load_2d(st + 2 * L::kABytes + L::kBBytes, &tm_b_lo, &full[s], c0, tap * BLOCK_N);
                 }
             }
         }
@@ -166,6 +169,21 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         dst[i] = make_float4(v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z,
                                              v[4 * i + 3] + b4.w);
                     }
+                }
+            }
+        } else if constexpr (MODE == kModeConvRaw) {
+            // rows of this warp: dy = 2q + (lane >> 4), x = lane & 15; every thread stores its pixel's channels
+            const int y = y0 + 2 * q + (lane >> 4), x = x0 + (lane & 15);
+            const bool inside = y < p.H && x < p.W;
+            float* dst_row = p.raw_out + (((int64_t)img * p.H + y) * p.W + x) * BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                float v[32];
+                tmem_ld_32x32(trow + c, v);
+                if (inside) {
+                    float4* dst = reinterpret_cast<float4*>(dst_row + c);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
             }
         } else {
@@ -306,22 +324,27 @@ int tc_gemm_nt(const __half* a_hi, const __half* a_lo, const __half* w_hi, const
     return launch_tc<kModeGemm, 128, 64, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, st, name);
 }
 
-// 3x3 conv (s1, p1) + shift + ReLU + 2x2 max-pool on channels-last fp16 hi/lo activations [B,H,W,CIN];
-// weights [9][COUT][CIN] hi/lo (BN scale folded); output [B,H/2,W/2,COUT] (or [B,W/2,H/2,COUT]) hi/lo.
+// 3x3 conv (s1, p1) on channels-last fp16 hi/lo activations [B,H,W,CIN]; weights [9][COUT][CIN] hi/lo.
+//   raw_out == nullptr : + shift + ReLU + 2x2 max-pool -> [B,H/2,W/2,COUT] (or [B,W/2,H/2,COUT]) hi/lo  (eval forward)
+//   raw_out != nullptr : plain convolution -> fp32 [B,H,W,COUT]  (training forward before BatchNorm, and the
+//                        data gradient of a convolution = the same stencil with flipped, transposed weights)
 template <int CIN, int COUT>
 int tc_conv3x3(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
-               __half* out_hi, __half* out_lo, int B, int H, int W, int out_whc, cudaStream_t st, const char* name) {
+               __half* out_hi, __half* out_lo, float* raw_out, int B, int H, int W, int out_whc, cudaStream_t st,
+               const char* name) {
+    constexpr int BK = CIN < 64 ? CIN : 64;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     const uint64_t adims[4] = {(uint64_t)CIN, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    const uint32_t abox[4] = {(uint32_t)CIN, 16, 8, 1};
+    const uint32_t abox[4] = {(uint32_t)BK, 16, 8, 1};
     const uint64_t bdims[2] = {(uint64_t)CIN, (uint64_t)(9 * COUT)};
-    const uint32_t bbox[2] = {(uint32_t)CIN, (uint32_t)COUT};
+    const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)COUT};
     int rc;
     if ((rc = make_tmap(&ta_hi, in_hi, 4, adims, abox)) || (rc = make_tmap(&ta_lo, in_lo, 4, adims, abox)) ||
         (rc = make_tmap(&tb_hi, w_hi, 2, bdims, bbox)) || (rc = make_tmap(&tb_lo, w_lo, 2, bdims, bbox)))
         return rc;
     TcParams p{};
-    p.num_kblocks = 9;
+    p.kc = CIN / BK;
+    p.num_kblocks = 9 * p.kc;
     p.H = H;
     p.W = W;
     p.tiles_x = (W + 15) / 16;
@@ -329,15 +352,24 @@ int tc_conv3x3(const __half* in_hi, const __half* in_lo, const __half* w_hi, con
     p.out_hi = out_hi;
     p.out_lo = out_lo;
     p.out_whc = out_whc;
+    p.raw_out = raw_out;
     const int tiles_y = (H + 7) / 8;
     dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)B);
-    return launch_tc<kModeConv, COUT, CIN, (CIN == 32 ? 4 : 3)>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, st, name);
+    if (raw_out) return launch_tc<kModeConvRaw, COUT, BK, (BK == 32 ? 4 : 3)>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, st, name);
+    if constexpr (CIN <= 64 && COUT >= 64)
+        return launch_tc<kModeConv, COUT, BK, (BK == 32 ? 4 : 3)>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, st, name);
+    else
+        return fail(SIR_ERR_UNSUPPORTED, "tc_conv3x3<%d,%d>: pooled epilogue not instantiated", CIN, COUT);
 }
 
-template int tc_conv3x3<32, 64>(const __half*, const __half*, const __half*, const __half*, const float*, __half*,
-                                __half*, int, int, int, int, cudaStream_t, const char*);
-template int tc_conv3x3<64, 128>(const __half*, const __half*, const __half*, const __half*, const float*, __half*,
-                                 __half*, int, int, int, int, cudaStream_t, const char*);
+#define SIR_INST_CONV(CIN, COUT)                                                                                       \
+    template int tc_conv3x3<CIN, COUT>(const __half*, const __half*, const __half*, const __half*, const float*,      \
+                                       __half*, __half*, float*, int, int, int, int, cudaStream_t, const char*);
+SIR_INST_CONV(32, 64)     // conv2 forward
+SIR_INST_CONV(64, 128)    // conv3 forward
+SIR_INST_CONV(128, 64)    // conv3 data gradient
+SIR_INST_CONV(64, 32)     // conv2 data gradient
+#undef SIR_INST_CONV
 
 int split_f16_async(const float* in, __half* hi, __half* lo, int64_t n, cudaStream_t st) {
     if (n <= 0) return SIR_OK;

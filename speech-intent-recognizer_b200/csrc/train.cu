@@ -1,0 +1,1175 @@
+// Training step of CNNAudioGRU for sm_100a: train-mode forward (BatchNorm with batch statistics, inter-layer GRU
+// dropout), hand-written backward of every layer, cross-entropy, and a fused unscale + Adam update over flat
+// parameter / gradient buffers.
+//
+// Replaces the device work of scripts/train.py:80-116 of the reference (model.train() forward, CrossEntropyLoss,
+// loss.backward(), optim.Adam(weight_decay) step, GradScaler scale / unscale / inf-skip); the data-parallel
+// gradient all-reduce the reference lacks is ONE torch.distributed all-reduce over the flat gradient buffer
+// this file fills (host side: scripts/train.py of this repo).
+//
+// Arithmetic is fp32-equivalent everywhere: the dense contractions of the forward, the recomputed recurrent
+// pre-activations and the convolution data gradients run on tcgen05 as 3-pass fp16 hi/lo splits (gemm_tc.cu);
+// weight gradients and the GRU input/recurrent gradients are fp32 CUDA-core contractions; reductions that feed
+// BatchNorm statistics accumulate in fp64.  Loss scaling is therefore numerically a no-op but is kept so that
+// the reference's GradScaler semantics (collective inf/nan skip) carry over.
+//
+// Layouts: activations are channels-last; the GRU input is [B, T, h, c] for the tensor-core operand and
+// [B, T, c * H8 + h] (the reference's feature order, models/models.py:55-57) for the weight-gradient operand, so
+// gradients land in the reference's parameter layout.
+#include <cmath>
+
+#include "model.cuh"
+#include "philox.cuh"
+
+namespace sir {
+
+constexpr float kDropoutP = 0.5f;        // nn.GRU(dropout=0.5), models/models.py:27
+
+// =========================================================================================================
+// forward pieces
+// =========================================================================================================
+
+// conv1 (C_in = 1) without BatchNorm: z[b, y, x, 0..31], one thread per pixel.
+__global__ void __launch_bounds__(128) conv1_raw_kernel(const float* __restrict__ feat, const float* __restrict__ w1,
+                                                        float* __restrict__ z, int H, int W) {
+    __shared__ float s_w[288];
+    for (int i = threadIdx.x; i < 288; i += 128) s_w[i] = w1[i];
+    __syncthreads();
+    const int pix = blockIdx.x * 128 + threadIdx.x;
+    if (pix >= H * W) return;
+    const int b = blockIdx.y, y = pix / W, x = pix - y * W;
+    const float* __restrict__ img = feat + (int64_t)b * H * W;
+    float patch[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int gy = y + kh - 1, gx = x + kw - 1;
+            patch[kh * 3 + kw] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(img + (int64_t)gy * W + gx) : 0.f;
+        }
+    float4* dst = reinterpret_cast<float4*>(z + ((int64_t)b * H * W + pix) * 32);
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+        float r[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const float* w = s_w + (c4 * 4 + cc) * 9;
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) a = fmaf(w[k], patch[k], a);
+            r[cc] = a;
+        }
+        dst[c4] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+}
+
+// Per-channel sum / sum of squares of z[N][C] into fp64 accumulators acc[0..C) / acc[C..2C).
+template <int C>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ z, int64_t N, double* __restrict__ acc) {
+    constexpr int ROWS = 256 / C;
+    __shared__ double s1[256], s2[256];
+    const int c = threadIdx.x % C, r = threadIdx.x / C;
+    double d1 = 0.0, d2 = 0.0;
+    float f1 = 0.f, f2 = 0.f;
+    int pending = 0;
+    for (int64_t n = (int64_t)blockIdx.x * ROWS + r; n < N; n += (int64_t)gridDim.x * ROWS) {
+        const float v = z[n * C + c];
+        f1 += v;
+        f2 = fmaf(v, v, f2);
+        if (++pending == 16) {
+            d1 += (double)f1;
+            d2 += (double)f2;
+            f1 = f2 = 0.f;
+            pending = 0;
+        }
+    }
+    s1[threadIdx.x] = d1 + (double)f1;
+    s2[threadIdx.x] = d2 + (double)f2;
+    __syncthreads();
+    if (threadIdx.x < C) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < ROWS; ++k) {
+            a += s1[k * C + threadIdx.x];
+            b += s2[k * C + threadIdx.x];
+        }
+        atomicAdd(acc + threadIdx.x, a);
+        atomicAdd(acc + C + threadIdx.x, b);
+    }
+}
+
+// mean / invstd for the normalisation, running statistics update (momentum, unbiased variance), accumulator reset.
+__global__ void bn_finalize_kernel(double* __restrict__ acc, int C, double N, float eps, float momentum,
+                                   float* __restrict__ stats, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var) {
+    const int c = threadIdx.x;
+    if (c >= C) return;
+    const double mean = acc[c] / N;
+    const double var = fmax(acc[C + c] / N - mean * mean, 0.0);
+    stats[c] = (float)mean;
+    stats[C + c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        const double unbiased = N > 1.0 ? var * N / (N - 1.0) : var;
+        running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
+        running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unbiased);
+    }
+    acc[c] = 0.0;
+    acc[C + c] = 0.0;
+}
+
+// index helpers for pooled tensors.  LAYOUT 0: [B][H2][W2][C] everywhere.  LAYOUT 1 (conv3 -> GRU input): fp16
+// operands as [B][W2][H2][C], fp32 / gradient tensors in the reference's feature order [B][W2][C * H2 + y2].
+template <int C, int LAYOUT>
+__device__ __forceinline__ int64_t pooled_half_index(int b, int y2, int x2, int c, int H2, int W2) {
+    return LAYOUT == 0 ? (((int64_t)b * H2 + y2) * W2 + x2) * C + c : (((int64_t)b * W2 + x2) * H2 + y2) * C + c;
+}
+template <int C, int LAYOUT>
+__device__ __forceinline__ int64_t pooled_f32_index(int b, int y2, int x2, int c, int H2, int W2) {
+    return LAYOUT == 0 ? (((int64_t)b * H2 + y2) * W2 + x2) * C + c : ((int64_t)b * W2 + x2) * ((int64_t)C * H2) + c * H2 + y2;
+}
+
+// BatchNorm (batch statistics) + ReLU + MaxPool2d(2): z [B,H,W,C] -> pooled activations (fp16 pair + fp32).
+template <int C, int LAYOUT>
+__global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const float* __restrict__ z, const float* __restrict__ stats,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, __half* __restrict__ out_hi,
+                                                               __half* __restrict__ out_lo, float* __restrict__ out_f, int B,
+                                                               int H, int W) {
+    const int H2 = H / 2, W2 = W / 2;
+    const int64_t total = (int64_t)B * H2 * W2 * C;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int c = (int)(i % C);
+        int64_t cell = i / C;
+        const int x2 = (int)(cell % W2);
+        cell /= W2;
+        const int y2 = (int)(cell % H2), b = (int)(cell / H2);
+        const float mean = stats[c], k = stats[C + c] * gamma[c], bt = beta[c];
+        const float* zp = z + (((int64_t)b * H + 2 * y2) * W + 2 * x2) * C + c;
+        const float u0 = (zp[0] - mean) * k + bt, u1 = (zp[C] - mean) * k + bt;
+        const float u2 = (zp[(int64_t)W * C] - mean) * k + bt, u3 = (zp[(int64_t)W * C + C] - mean) * k + bt;
+        const float a = fmaxf(fmaxf(fmaxf(u0, u1), fmaxf(u2, u3)), 0.f);
+        __half h, l;
+        tc::split_f16(a, h, l);
+        const int64_t hi = pooled_half_index<C, LAYOUT>(b, y2, x2, c, H2, W2);
+        out_hi[hi] = h;
+        out_lo[hi] = l;
+        out_f[pooled_f32_index<C, LAYOUT>(b, y2, x2, c, H2, W2)] = a;
+    }
+}
+
+// Inter-layer GRU dropout (train mode): y * keep / (1 - p); keep comes from the caller's mask or from Philox.
+__global__ void gru_dropout_kernel(const float* __restrict__ y, int64_t n, const uint8_t* __restrict__ keep_in,
+                                   uint64_t seed, uint64_t offset, uint8_t* __restrict__ keep_out, float* __restrict__ yd,
+                                   __half* __restrict__ yd_hi, __half* __restrict__ yd_lo) {
+    const float scale = 1.f / (1.f - kDropoutP);
+    for (int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i4 < n; i4 += (int64_t)gridDim.x * blockDim.x * 4) {
+        uint32_t r[4] = {0, 0, 0, 0};
+        if (!keep_in) philox4x32_10(seed, offset + (uint64_t)(i4 >> 2), 0x44524F50u, r);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t i = i4 + e;
+            if (i >= n) break;
+            const uint8_t keep = keep_in ? keep_in[i] : (uint8_t)(u01(r[e]) >= kDropoutP);
+            const float v = keep ? y[i] * scale : 0.f;
+            keep_out[i] = keep;
+            yd[i] = v;
+            __half h, l;
+            tc::split_f16(v, h, l);
+            yd_hi[i] = h;
+            yd_lo[i] = l;
+        }
+    }
+}
+
+// =========================================================================================================
+// loss
+// =========================================================================================================
+
+// CrossEntropyLoss (mean) + its gradient: dlogits = scale * (softmax - onehot) / B.  One CTA, warp per utterance.
+__global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                                                            int B, int C, float scale, float* __restrict__ loss,
+                                                            float* __restrict__ dlogits) {
+    __shared__ float s_part[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float part = 0.f;
+    for (int b = warp; b < B; b += 8) {
+        const float* row = logits + (int64_t)b * C;
+        float mx = -INFINITY;
+        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int c = lane; c < C; c += 32) sum += expf(row[c] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const int y = (int)labels[b];
+        const float lse = mx + logf(sum);
+        if (lane == 0) part += lse - row[y];
+        if (dlogits) {
+            const float g = scale / (float)B;
+            for (int c = lane; c < C; c += 32)
+                dlogits[(int64_t)b * C + c] = g * (expf(row[c] - lse) - (c == y ? 1.f : 0.f));
+        }
+    }
+    if (lane == 0) s_part[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += s_part[w];
+        loss[0] = t / (float)B;
+    }
+}
+
+// =========================================================================================================
+// backward: attention pooling + classifier head
+// =========================================================================================================
+__global__ void __launch_bounds__(128) attention_fc_bwd_kernel(const float* __restrict__ y, const float* __restrict__ att_w,
+                                                               const float* __restrict__ att_b_ptr,
+                                                               const float* __restrict__ fc_w,
+                                                               const float* __restrict__ dlogits, float* __restrict__ dy,
+                                                               float* __restrict__ ds_out, float* __restrict__ ctx_out, int T,
+                                                               int C) {
+    extern __shared__ float sm[];
+    float* score = sm;                 // [T]  -> softmax weights
+    float* g = sm + T;                 // [T]
+    float* dctx = sm + 2 * T;          // [512]
+    float* dl = sm + 2 * T + 512;      // [C]
+    __shared__ float s_red[2];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float att_b = __ldg(att_b_ptr);
+    const float* __restrict__ yb = y + (int64_t)b * T * 512;
+    for (int c = tid; c < C; c += 128) dl[c] = dlogits[(int64_t)b * C + c];
+    for (int t = warp; t < T; t += 4) {
+        float s = 0.f;
+        for (int k = lane; k < 512; k += 32) s = fmaf(yb[(int64_t)t * 512 + k], __ldg(att_w + k), s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) score[t] = s + att_b;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float mx = -INFINITY;
+        for (int t = lane; t < T; t += 32) mx = fmaxf(mx, score[t]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int t = lane; t < T; t += 32) sum += expf(score[t] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) {
+            s_red[0] = mx;
+            s_red[1] = 1.f / sum;
+        }
+    }
+    __syncthreads();
+    const float mx = s_red[0], inv = s_red[1];
+    __syncthreads();
+    for (int t = tid; t < T; t += 128) score[t] = expf(score[t] - mx) * inv;       // softmax weights
+    __syncthreads();
+    for (int k = tid; k < 512; k += 128) {
+        float c = 0.f;
+        for (int t = 0; t < T; ++t) c = fmaf(yb[(int64_t)t * 512 + k], score[t], c);
+        ctx_out[(int64_t)b * 512 + k] = c;
+        float d = 0.f;
+        for (int cc = 0; cc < C; ++cc) d = fmaf(dl[cc], __ldg(fc_w + (int64_t)cc * 512 + k), d);
+        dctx[k] = d;
+    }
+    __syncthreads();
+    for (int t = warp; t < T; t += 4) {
+        float s = 0.f;
+        for (int k = lane; k < 512; k += 32) s = fmaf(yb[(int64_t)t * 512 + k], dctx[k], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) g[t] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float gb = 0.f;
+        for (int t = lane; t < T; t += 32) gb = fmaf(score[t], g[t], gb);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gb += __shfl_xor_sync(0xffffffffu, gb, o);
+        if (lane == 0) s_red[0] = gb;
+    }
+    __syncthreads();
+    const float gbar = s_red[0];
+    __syncthreads();
+    for (int t = tid; t < T; t += 128) {
+        const float ds = score[t] * (g[t] - gbar);
+        g[t] = ds;
+        ds_out[(int64_t)b * T + t] = ds;
+    }
+    __syncthreads();
+    for (int i = tid; i < T * 512; i += 128) {
+        const int t = i >> 9, k = i & 511;
+        dy[(int64_t)b * T * 512 + i] = score[t] * dctx[k] + g[t] * __ldg(att_w + k);
+    }
+}
+
+// d fc.weight, d fc.bias, d attention.weight, d attention.bias (deterministic loops over the batch).
+__global__ void head_param_grad_kernel(const float* __restrict__ dlogits, const float* __restrict__ ctx,
+                                       const float* __restrict__ ds, const float* __restrict__ y, int B, int T, int C,
+                                       float* __restrict__ d_fc_w, float* __restrict__ d_fc_b, float* __restrict__ d_att_w,
+                                       float* __restrict__ d_att_b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_fcw = C * 512;
+    if (i < n_fcw) {
+        const int c = i >> 9, k = i & 511;
+        float a = 0.f;
+        for (int b = 0; b < B; ++b) a = fmaf(dlogits[(int64_t)b * C + c], ctx[(int64_t)b * 512 + k], a);
+        d_fc_w[i] = a;
+    } else if (i < n_fcw + C) {
+        const int c = i - n_fcw;
+        float a = 0.f;
+        for (int b = 0; b < B; ++b) a += dlogits[(int64_t)b * C + c];
+        d_fc_b[c] = a;
+    } else if (i < n_fcw + C + 512) {
+        const int k = i - n_fcw - C;
+        float a = 0.f;
+        for (int r = 0; r < B * T; ++r) a = fmaf(ds[r], y[(int64_t)r * 512 + k], a);
+        d_att_w[k] = a;
+    } else if (i == n_fcw + C + 512) {
+        float a = 0.f;
+        for (int r = 0; r < B * T; ++r) a += ds[r];
+        d_att_b[0] = a;
+    }
+}
+
+// =========================================================================================================
+// backward: GRU
+// =========================================================================================================
+
+// h_{t-1} of every (direction, b, t) as the operand of the recomputed recurrent projection and of dW_hh.
+__global__ void gru_hprev_kernel(const float* __restrict__ y, int B, int T, float* __restrict__ hprevf,
+                                 __half* __restrict__ hp_hi, __half* __restrict__ hp_lo) {
+    const int64_t per_dir = (int64_t)B * T * 256;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per_dir; i += (int64_t)gridDim.x * blockDim.x) {
+        const int d = (int)(i / per_dir);
+        const int64_t r = i - d * per_dir;
+        const int u = (int)(r & 255);
+        const int64_t bt = r >> 8;
+        const int t = (int)(bt % T);
+        const int tp = d == 0 ? t - 1 : t + 1;
+        const float v = (tp >= 0 && tp < T) ? y[(bt - t + tp) * 512 + d * 256 + u] : 0.f;
+        hprevf[i] = v;
+        __half h, l;
+        tc::split_f16(v, h, l);
+        hp_hi[i] = h;
+        hp_lo[i] = l;
+    }
+}
+
+// BPTT of one layer, both directions, ONE launch.  An 8-CTA cluster owns (direction, 16 utterances); CTA r keeps
+// W_hh[:, 32r .. 32r+32) resident in shared memory; per step every CTA turns dh of its 32 units into the gate
+// gradients, pushes them into all 8 peers through distributed shared memory, and after one cluster barrier
+// computes its slice of W_hh^T dgh for the next (earlier) time step.
+constexpr int kGbNB = 16, kGbThreads = 256, kGbCluster = 8, kGbWStride = 772;
+constexpr int kGbSmemBytes = (32 * kGbWStride + 2 * kGbNB * 768 + kGbNB * 33) * 4;
+
+__device__ __forceinline__ uint32_t gb_map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void gb_st_cluster_v2(uint32_t addr, float a, float b) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float gb_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __cluster_dims__(kGbCluster, 1, 1) __launch_bounds__(kGbThreads, 1)
+    gru_layer_bwd_kernel(const float* __restrict__ whh_f,     // W_hh forward direction [768][256] (flat parameters)
+                         const float* __restrict__ whh_r,     // W_hh reverse direction
+                         const float* __restrict__ gi,        // [B*T, 1536] input projection (+ b_ih)
+                         const float* __restrict__ gh,        // [2][B*T, 768] recurrent projection (+ b_hh), tile order
+                         const float* __restrict__ y,         // [B, T, 512] layer output
+                         const float* __restrict__ dy,        // [B, T, 512] gradient w.r.t. the layer output
+                         float* __restrict__ dgi,             // [B*T, 1536]
+                         float* __restrict__ dgh,             // [2][B*T, 768] natural gate order
+                         int B, int T) {
+    extern __shared__ __align__(16) float gsm[];
+    float* s_w = gsm;                                    // [32 units][772]
+    float* s_dgh = gsm + 32 * kGbWStride;                // [2][16][768]
+    float* s_dh = s_dgh + 2 * kGbNB * 768;               // [16][33]
+    const int tid = threadIdx.x;
+    const int rank = blockIdx.x % kGbCluster, slice = blockIdx.x / kGbCluster, dir = blockIdx.y;
+    const int j0 = rank * 32, b0 = slice * kGbNB;
+    const float* __restrict__ whh = dir == 0 ? whh_f : whh_r;
+    for (int i = tid; i < 768 * 32; i += kGbThreads) {
+        const int u = i & 31, g = i >> 5;
+        s_w[u * kGbWStride + g] = __ldg(whh + (int64_t)g * 256 + j0 + u);
+    }
+    for (int i = tid; i < kGbNB * 33; i += kGbThreads) s_dh[i] = 0.f;
+    // phase-A role: utterance ab, units j0 + 2*aug, +1
+    const int ab = tid >> 4, aug = tid & 15;
+    const int abb = b0 + ab;
+    const bool avalid = abb < B;
+    const int abc = avalid ? abb : B - 1;
+    // phase-B role: unit bu, utterances bq and bq + 8
+    const int bu = tid & 31, bq = tid >> 5;
+    const uint32_t s_dgh_addr = (uint32_t)__cvta_generic_to_shared(s_dgh);
+    const int64_t BT = (int64_t)B * T;
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+
+    for (int s = 0; s < T; ++s) {
+        const int t = dir == 0 ? T - 1 - s : s;          // reverse of the forward processing order
+        const int tp = dir == 0 ? t - 1 : t + 1;         // where h_{prev} lives
+        const int buf = s & 1;
+        const int64_t row = (int64_t)abc * T + t;
+        // ---- phase A: gate gradients of this CTA's units ------------------------------------------------------
+        {
+            const float* gip = gi + row * 1536 + dir * 768 + j0 + 2 * aug;
+            const float* ghp = gh + ((int64_t)dir * BT + row) * 768 + rank * 96 + 2 * aug;
+            const float2 gir = *reinterpret_cast<const float2*>(gip), giz = *reinterpret_cast<const float2*>(gip + 256),
+                         gin = *reinterpret_cast<const float2*>(gip + 512);
+            const float2 ghr = *reinterpret_cast<const float2*>(ghp), ghz = *reinterpret_cast<const float2*>(ghp + 32),
+                         ghn = *reinterpret_cast<const float2*>(ghp + 64);
+            float2 hp = make_float2(0.f, 0.f);
+            if (tp >= 0 && tp < T) hp = *reinterpret_cast<const float2*>(y + ((int64_t)abc * T + tp) * 512 + dir * 256 + j0 + 2 * aug);
+            const float2 dyv = *reinterpret_cast<const float2*>(dy + row * 512 + dir * 256 + j0 + 2 * aug);
+            float o_r[2], o_z[2], o_n[2], o_hn[2];
+            const float a_gir[2] = {gir.x, gir.y}, a_giz[2] = {giz.x, giz.y}, a_gin[2] = {gin.x, gin.y};
+            const float a_ghr[2] = {ghr.x, ghr.y}, a_ghz[2] = {ghz.x, ghz.y}, a_ghn[2] = {ghn.x, ghn.y};
+            const float a_hp[2] = {hp.x, hp.y}, a_dy[2] = {dyv.x, dyv.y};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float dh = avalid ? a_dy[e] + s_dh[ab * 33 + 2 * aug + e] : 0.f;
+                const float r = gb_sigmoid(a_gir[e] + a_ghr[e]);
+                const float z = gb_sigmoid(a_giz[e] + a_ghz[e]);
+                const float n = tanhf(a_gin[e] + r * a_ghn[e]);
+                const float dn = dh * (1.f - z);
+                const float dz = dh * (a_hp[e] - n);
+                const float dpn = dn * (1.f - n * n);
+                const float dr = dpn * a_ghn[e];
+                o_r[e] = dr * r * (1.f - r);
+                o_z[e] = dz * z * (1.f - z);
+                o_n[e] = dpn;
+                o_hn[e] = dpn * r;
+                s_dh[ab * 33 + 2 * aug + e] = z * dh;
+            }
+            if (avalid) {
+                float* dgip = dgi + row * 1536 + dir * 768 + j0 + 2 * aug;
+                *reinterpret_cast<float2*>(dgip) = make_float2(o_r[0], o_r[1]);
+                *reinterpret_cast<float2*>(dgip + 256) = make_float2(o_z[0], o_z[1]);
+                *reinterpret_cast<float2*>(dgip + 512) = make_float2(o_n[0], o_n[1]);
+                float* dghp = dgh + ((int64_t)dir * BT + row) * 768 + j0 + 2 * aug;
+                *reinterpret_cast<float2*>(dghp) = make_float2(o_r[0], o_r[1]);
+                *reinterpret_cast<float2*>(dghp + 256) = make_float2(o_z[0], o_z[1]);
+                *reinterpret_cast<float2*>(dghp + 512) = make_float2(o_hn[0], o_hn[1]);
+            }
+            if (s + 1 < T) {
+                const uint32_t local = s_dgh_addr + (uint32_t)(((buf * kGbNB + ab) * 768 + j0 + 2 * aug) * 4);
+#pragma unroll
+                for (int c = 0; c < kGbCluster; ++c) {
+                    const uint32_t ra = gb_map_to_cta(local, (uint32_t)c);
+                    gb_st_cluster_v2(ra, o_r[0], o_r[1]);
+                    gb_st_cluster_v2(ra + 256 * 4, o_z[0], o_z[1]);
+                    gb_st_cluster_v2(ra + 512 * 4, o_hn[0], o_hn[1]);
+                }
+            }
+        }
+        if (s + 1 == T) break;
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        // ---- phase B: dh_prev[b][u] += sum_g W_hh[g][j0+u] * dgh[b][g] ----------------------------------------
+        {
+            const float4* w4 = reinterpret_cast<const float4*>(s_w + bu * kGbWStride);
+            const float4* d0 = reinterpret_cast<const float4*>(s_dgh + (buf * kGbNB + bq) * 768);
+            const float4* d1 = reinterpret_cast<const float4*>(s_dgh + (buf * kGbNB + bq + 8) * 768);
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+            for (int g4 = 0; g4 < 192; ++g4) {
+                const float4 w = w4[g4], x0 = d0[g4], x1 = d1[g4];
+                a0 = fmaf(w.x, x0.x, a0);
+                a0 = fmaf(w.y, x0.y, a0);
+                a0 = fmaf(w.z, x0.z, a0);
+                a0 = fmaf(w.w, x0.w, a0);
+                a1 = fmaf(w.x, x1.x, a1);
+                a1 = fmaf(w.y, x1.y, a1);
+                a1 = fmaf(w.z, x1.z, a1);
+                a1 = fmaf(w.w, x1.w, a1);
+            }
+            s_dh[bq * 33 + bu] += a0;
+            s_dh[(bq + 8) * 33 + bu] += a1;
+        }
+        __syncthreads();
+    }
+    // keep this CTA's shared memory alive until every peer has finished pushing into it
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// C[M,N] = op(A) B + beta C on the fp32 CUDA cores; B stored [K][N]; TA: A stored [K][M], else [M][K].
+template <bool TA>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
+                                                    float* __restrict__ Cm, int ldc, int M, int N, int K, float beta) {
+    __shared__ __align__(16) float As[16][68], Bs[16][68];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        if (TA) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int e = tid + i * 256, kk = e >> 6, mm = e & 63;
+                As[kk][mm] = (k0 + kk < K && m0 + mm < M) ? A[(int64_t)(k0 + kk) * lda + m0 + mm] : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int e = tid + i * 256, mm = e >> 4, kk = e & 15;
+                As[kk][mm] = (k0 + kk < K && m0 + mm < M) ? A[(int64_t)(m0 + mm) * lda + k0 + kk] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * 256, kk = e >> 6, nn = e & 63;
+            Bs[kk][nn] = (k0 + kk < K && n0 + nn < N) ? Bm[(int64_t)(k0 + kk) * ldb + n0 + nn] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float* c = Cm + (int64_t)m * ldc + n;
+            *c = beta != 0.f ? acc[i][j] + beta * *c : acc[i][j];
+        }
+    }
+}
+
+// out[n] = sum over rows of X[rows][ld] column n (bias gradients); one thread per column, coalesced rows.
+__global__ void colsum_kernel(const float* __restrict__ X, int ld, int rows, int cols, float* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= cols) return;
+    float a0 = 0.f, a1 = 0.f;
+    int r = 0;
+    for (; r + 1 < rows; r += 2) {
+        a0 += X[(int64_t)r * ld + n];
+        a1 += X[(int64_t)(r + 1) * ld + n];
+    }
+    if (r < rows) a0 += X[(int64_t)r * ld + n];
+    out[n] = a0 + a1;
+}
+
+__global__ void dropout_bwd_kernel(float* __restrict__ d, const uint8_t* __restrict__ keep, int64_t n) {
+    const float scale = 1.f / (1.f - kDropoutP);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        d[i] = keep[i] ? d[i] * scale : 0.f;
+}
+
+// =========================================================================================================
+// backward: conv stages
+// =========================================================================================================
+struct PoolArg {
+    float zhat[4];
+    int arg;
+    bool on;
+};
+
+template <int C>
+__device__ __forceinline__ PoolArg pool_argmax(const float* __restrict__ zp, int W, float mean, float invstd, float gamma,
+                                               float beta) {
+    PoolArg r;
+    const float zv[4] = {zp[0], zp[C], zp[(int64_t)W * C], zp[(int64_t)W * C + C]};
+    float best = -INFINITY;
+    r.arg = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        r.zhat[p] = (zv[p] - mean) * invstd;
+        const float u = (zv[p] - mean) * (invstd * gamma) + beta;     // same expression as the forward
+        if (u > best) {
+            best = u;
+            r.arg = p;
+        }
+    }
+    r.on = best > 0.f;
+    return r;
+}
+
+// pass 1: sum du and sum du * zhat per channel (du = gradient w.r.t. the BatchNorm output through pool + ReLU)
+template <int C, int LAYOUT>
+__global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(const float* __restrict__ z, const float* __restrict__ dpool,
+                                                                 const float* __restrict__ stats,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, int B, int H, int W,
+                                                                 double* __restrict__ acc) {
+    constexpr int ROWS = 256 / C;
+    __shared__ double s1[256], s2[256];
+    const int H2 = H / 2, W2 = W / 2;
+    const int c = threadIdx.x % C, r = threadIdx.x / C;
+    const float mean = stats[c], invstd = stats[C + c], gm = gamma[c], bt = beta[c];
+    const int64_t cells = (int64_t)B * H2 * W2;
+    double d1 = 0.0, d2 = 0.0;
+    float f1 = 0.f, f2 = 0.f;
+    int pending = 0;
+    for (int64_t cell = (int64_t)blockIdx.x * ROWS + r; cell < cells; cell += (int64_t)gridDim.x * ROWS) {
+        const int x2 = (int)(cell % W2);
+        const int64_t q = cell / W2;
+        const int y2 = (int)(q % H2), b = (int)(q / H2);
+        const PoolArg pa = pool_argmax<C>(z + (((int64_t)b * H + 2 * y2) * W + 2 * x2) * C + c, W, mean, invstd, gm, bt);
+        if (pa.on) {
+            const float du = dpool[pooled_f32_index<C, LAYOUT>(b, y2, x2, c, H2, W2)];
+            f1 += du;
+            f2 = fmaf(du, pa.zhat[pa.arg], f2);
+        }
+        if (++pending == 16) {
+            d1 += (double)f1;
+            d2 += (double)f2;
+            f1 = f2 = 0.f;
+            pending = 0;
+        }
+    }
+    s1[threadIdx.x] = d1 + (double)f1;
+    s2[threadIdx.x] = d2 + (double)f2;
+    __syncthreads();
+    if (threadIdx.x < C) {
+        double a = 0.0, b2 = 0.0;
+        for (int k = 0; k < ROWS; ++k) {
+            a += s1[k * C + threadIdx.x];
+            b2 += s2[k * C + threadIdx.x];
+        }
+        atomicAdd(acc + threadIdx.x, a);
+        atomicAdd(acc + C + threadIdx.x, b2);
+    }
+}
+
+// pass 2: dz = gamma * invstd * (du - mean(du) - zhat * mean(du * zhat)); also d gamma, d beta.
+template <int C, int LAYOUT>
+__global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float* __restrict__ z, const float* __restrict__ dpool,
+                                                                const float* __restrict__ stats,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, int B, int H, int W,
+                                                                const double* __restrict__ acc, float* __restrict__ dz,
+                                                                __half* __restrict__ dz_hi, __half* __restrict__ dz_lo,
+                                                                float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+    const int H2 = H / 2, W2 = W / 2;
+    const double Npix = (double)B * H * W;
+    const int64_t total = (int64_t)B * H2 * W2 * C;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int c = (int)(i % C);
+        int64_t cell = i / C;
+        const int x2 = (int)(cell % W2);
+        cell /= W2;
+        const int y2 = (int)(cell % H2), b = (int)(cell / H2);
+        const float mean = stats[c], invstd = stats[C + c], gm = gamma[c], bt = beta[c];
+        const float m1 = (float)(acc[c] / Npix), m2 = (float)(acc[C + c] / Npix);
+        if (i < C) {
+            d_beta[c] = (float)acc[c];
+            d_gamma[c] = (float)acc[C + c];
+        }
+        const int64_t base = (((int64_t)b * H + 2 * y2) * W + 2 * x2) * C + c;
+        const PoolArg pa = pool_argmax<C>(z + base, W, mean, invstd, gm, bt);
+        const float du = pa.on ? dpool[pooled_f32_index<C, LAYOUT>(b, y2, x2, c, H2, W2)] : 0.f;
+        const float k = gm * invstd;
+        const int64_t offs[4] = {0, C, (int64_t)W * C, (int64_t)W * C + C};
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const float v = k * ((p == pa.arg ? du : 0.f) - m1 - pa.zhat[p] * m2);
+            dz[base + offs[p]] = v;
+            if (dz_hi) {
+                __half h, l;
+                tc::split_f16(v, h, l);
+                dz_hi[base + offs[p]] = h;
+                dz_lo[base + offs[p]] = l;
+            }
+        }
+    }
+}
+
+// Weight gradient of a 3x3 convolution: partial[chunk][tap][co][ci] = sum over the chunk's pixels of
+// dz[pix][co] * a[pix shifted by the tap][ci].  grid (9, chunks); a chunk is `rows_per_chunk` image rows.
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ a, int B, int H,
+                                                         int W, int rows_per_chunk, float* __restrict__ partial) {
+    constexpr int P = 16, TCO = COUT / 16, TCI = CIN / 16;
+    __shared__ __align__(16) float s_dz[P][COUT];
+    __shared__ __align__(16) float s_a[P][CIN];
+    const int tap = blockIdx.x, kh = tap / 3, kw = tap - kh * 3;
+    const int tid = threadIdx.x, tco = tid >> 4, tci = tid & 15;
+    float acc[TCO][TCI] = {};
+    const int64_t rows = (int64_t)B * H;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+    for (int64_t row = r0; row < r1; ++row) {
+        const int b = (int)(row / H), y = (int)(row % H);
+        const int ya = y + kh - 1;
+        const bool row_ok = ya >= 0 && ya < H;
+        for (int x0 = 0; x0 < W; x0 += P) {
+            for (int e = tid; e < P * COUT / 4; e += 256) {
+                const int p = e / (COUT / 4), c4 = e % (COUT / 4);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (x0 + p < W) v = *reinterpret_cast<const float4*>(dz + ((row * W) + x0 + p) * COUT + c4 * 4);
+                *reinterpret_cast<float4*>(&s_dz[p][c4 * 4]) = v;
+            }
+            for (int e = tid; e < P * CIN / 4; e += 256) {
+                const int p = e / (CIN / 4), c4 = e % (CIN / 4);
+                const int xa = x0 + p + kw - 1;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row_ok && x0 + p < W && xa >= 0 && xa < W)
+                    v = *reinterpret_cast<const float4*>(a + (((int64_t)b * H + ya) * W + xa) * CIN + c4 * 4);
+                *reinterpret_cast<float4*>(&s_a[p][c4 * 4]) = v;
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int p = 0; p < P; ++p) {
+                float dv[TCO], av[TCI];
+#pragma unroll
+                for (int i = 0; i < TCO; ++i) dv[i] = s_dz[p][tco * TCO + i];
+#pragma unroll
+                for (int j = 0; j < TCI; ++j) av[j] = s_a[p][tci * TCI + j];
+#pragma unroll
+                for (int i = 0; i < TCO; ++i)
+#pragma unroll
+                    for (int j = 0; j < TCI; ++j) acc[i][j] = fmaf(dv[i], av[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+    float* out = partial + ((int64_t)blockIdx.y * 9 + tap) * COUT * CIN;
+#pragma unroll
+    for (int i = 0; i < TCO; ++i)
+#pragma unroll
+        for (int j = 0; j < TCI; ++j) out[(tco * TCO + i) * CIN + tci * TCI + j] = acc[i][j];
+}
+
+// conv1 (C_in = 1): partial[block][tap][co]; lane = output channel, warps stride over pixels.
+__global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ feat, int B,
+                                                          int H, int W, float* __restrict__ partial) {
+    __shared__ float s_acc[8][9][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc[9] = {};
+    const int64_t rows = (int64_t)B * H;
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int b = (int)(row / H), y = (int)(row % H);
+        const float* img = feat + (int64_t)b * H * W;
+        for (int x = warp; x < W; x += 8) {
+            const float d = dz[(row * W + x) * 32 + lane];
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int ya = y + kh - 1, xa = x + kw - 1;
+                    const float v = (ya >= 0 && ya < H && xa >= 0 && xa < W) ? __ldg(img + (int64_t)ya * W + xa) : 0.f;
+                    acc[kh * 3 + kw] = fmaf(d, v, acc[kh * 3 + kw]);
+                }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s_acc[warp][k][lane] = acc[k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 288; i += 256) {
+        const int k = i / 32, co = i % 32;
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += s_acc[w][k][co];
+        partial[(int64_t)blockIdx.x * 288 + k * 32 + co] = t;
+    }
+}
+
+// dW[(co * CIN + ci) * 9 + tap] = sum_chunk partial[chunk][tap][co][ci]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int cin, int cout, float* __restrict__ dw) {
+    const int n = 9 * cin * cout;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a0 = 0.f, a1 = 0.f;
+    int c = 0;
+    for (; c + 1 < chunks; c += 2) {
+        a0 += partial[(int64_t)c * n + i];
+        a1 += partial[(int64_t)(c + 1) * n + i];
+    }
+    if (c < chunks) a0 += partial[(int64_t)c * n + i];
+    const int ci = i % cin, co = (i / cin) % cout, tap = i / (cin * cout);
+    dw[((int64_t)co * cin + ci) * 9 + tap] = a0 + a1;
+}
+
+// =========================================================================================================
+// optimizer
+// =========================================================================================================
+struct AdamSegments {
+    int64_t offset[4], count[4];
+    int n;
+};
+
+// torch.optim.Adam (coupled L2 weight decay, no amsgrad) on flat buffers, fused with the GradScaler unscale and
+// inf/nan skip: g = grad * inv_scale + wd * p.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            AdamSegments seg, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
+                            float inv_scale, const float* __restrict__ found_inf) {
+    if (found_inf && *found_inf != 0.f) return;
+    int64_t total = 0;
+    for (int s = 0; s < seg.n; ++s) total += seg.count[s];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i;
+        int s = 0;
+        while (r >= seg.count[s]) r -= seg.count[s++];
+        const int64_t j = seg.offset[s] + r;
+        const float pv = p[j];
+        const float gr = fmaf(wd, pv, g[j] * inv_scale);
+        const float mv = beta1 * m[j] + (1.f - beta1) * gr;
+        const float vv = beta2 * v[j] + (1.f - beta2) * gr * gr;
+        m[j] = mv;
+        v[j] = vv;
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;
+        p[j] = pv - (lr / bc1) * (mv / denom);
+    }
+}
+
+__global__ void grad_nonfinite_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ flag) {
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        bad |= !isfinite(g[i]);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *flag = 1.f;
+}
+
+// =========================================================================================================
+// host orchestration
+// =========================================================================================================
+template <bool TA>
+static int sgemm(const float* A, int lda, const float* Bm, int ldb, float* Cm, int ldc, int M, int N, int K, float beta,
+                 cudaStream_t st) {
+    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
+    sgemm_kernel<TA><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, Cm, ldc, M, N, K, beta);
+    SIR_CHECK_LAUNCH("sgemm_kernel");
+    return SIR_OK;
+}
+
+static inline unsigned blocks_for(int64_t n, int per_block = 256, int cap = 148 * 16) {
+    const int64_t b = (n + per_block - 1) / per_block;
+    return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+static size_t carve_train(TrainSaved& t, uint8_t* base, int B, int H, int W, int gin) {
+    const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, T = W / 8;
+    size_t off = 0;
+    auto next = [&](size_t bytes) {
+        uint8_t* p = base ? base + off : nullptr;
+        off += (bytes + 255) & ~(size_t)255;
+        return p;
+    };
+    const size_t n_z1 = (size_t)B * H * W * 32, n_z2 = (size_t)B * H2 * W2 * 64, n_z3 = (size_t)B * H4 * W4 * 128;
+    const size_t n_a1 = (size_t)B * H2 * W2 * 32, n_a2 = (size_t)B * H4 * W4 * 64, n_g = (size_t)B * T * gin;
+    const size_t BT = (size_t)B * T, n_y = BT * 512;
+    t.bn_acc = (double*)next(3 * 2 * 256 * 8);     // first: fixed offset, so it stays zeroed when the batch size changes
+    t.z1 = (float*)next(n_z1 * 4);
+    t.z2 = (float*)next(n_z2 * 4);
+    t.z3 = (float*)next(n_z3 * 4);
+    t.a1f = (float*)next(n_a1 * 4);
+    t.a2f = (float*)next(n_a2 * 4);
+    t.ginf = (float*)next(n_g * 4);
+    t.a1_hi = (__half*)next(n_a1 * 2);
+    t.a1_lo = (__half*)next(n_a1 * 2);
+    t.a2_hi = (__half*)next(n_a2 * 2);
+    t.a2_lo = (__half*)next(n_a2 * 2);
+    t.gin_hi = (__half*)next(n_g * 2);
+    t.gin_lo = (__half*)next(n_g * 2);
+    for (int l = 0; l < 3; ++l) t.stats[l] = (float*)next(256 * 4);
+    for (int l = 0; l < 2; ++l) {
+        t.gi[l] = (float*)next(BT * 1536 * 4);
+        t.y[l] = (float*)next(n_y * 4);
+    }
+    t.y0d = (float*)next(n_y * 4);
+    t.y0d_hi = (__half*)next(n_y * 2);
+    t.y0d_lo = (__half*)next(n_y * 2);
+    t.ytmp_hi = (__half*)next(n_y * 2);
+    t.ytmp_lo = (__half*)next(n_y * 2);
+    t.keep = (uint8_t*)next(n_y);
+    // backward scratch
+    t.dy = (float*)next(n_y * 4);
+    t.dx = (float*)next(BT * (size_t)(gin > 512 ? gin : 512) * 4);
+    t.ds = (float*)next(BT * 4);
+    t.ctx = (float*)next((size_t)B * 512 * 4);
+    t.dgi = (float*)next(BT * 1536 * 4);
+    t.dgh = (float*)next(2 * BT * 768 * 4);
+    t.gh = (float*)next(2 * BT * 768 * 4);
+    t.hprevf = (float*)next(2 * BT * 256 * 4);
+    t.hprev_hi = (__half*)next(2 * BT * 256 * 2);
+    t.hprev_lo = (__half*)next(2 * BT * 256 * 2);
+    t.dz = (float*)next(n_z1 * 4);                 // largest raw conv output (layer 1); reused by layers 2, 3
+    t.dz_hi = (__half*)next(n_z2 * 2);
+    t.dz_lo = (__half*)next(n_z2 * 2);
+    t.dact = (float*)next(n_a1 * 4);               // data gradients w.r.t. a2 / a1
+    t.wg_partial = (float*)next((size_t)320 * 9 * 128 * 64 * 4);
+    return off;
+}
+
+constexpr int kWgradMaxChunks = 320;
+
+template <int C, int LAYOUT>
+static int bn_stage_forward(const float* z, int B, int H, int W, double* acc, float* stats, float* params,
+                            const FlatOffsets& off, int layer, float eps, float momentum, __half* out_hi, __half* out_lo,
+                            float* out_f, cudaStream_t st) {
+    const int64_t N = (int64_t)B * H * W;
+    bn_stats_kernel<C><<<blocks_for(N, 256 / C * 8, 148 * 4), 256, 0, st>>>(z, N, acc);
+    SIR_CHECK_LAUNCH("bn_stats_kernel");
+    bn_finalize_kernel<<<1, 128, 0, st>>>(acc, C, (double)N, eps, momentum, stats, params + off.bn_m[layer],
+                                         params + off.bn_v[layer]);
+    SIR_CHECK_LAUNCH("bn_finalize_kernel");
+    const int64_t total = (int64_t)B * (H / 2) * (W / 2) * C;
+    bn_relu_pool_fwd_kernel<C, LAYOUT><<<blocks_for(total), 256, 0, st>>>(z, stats, params + off.bn_g[layer],
+                                                                         params + off.bn_b[layer], out_hi, out_lo, out_f, B, H, W);
+    SIR_CHECK_LAUNCH("bn_relu_pool_fwd_kernel");
+    return SIR_OK;
+}
+
+template <int C, int LAYOUT>
+static int bn_stage_backward(const float* z, const float* dpool, int B, int H, int W, double* acc, const float* stats,
+                             const float* params, const FlatOffsets& off, int layer, float* dz, __half* dz_hi, __half* dz_lo,
+                             float* grads, cudaStream_t st) {
+    const int64_t cells = (int64_t)B * (H / 2) * (W / 2);
+    bn_pool_bwd_reduce_kernel<C, LAYOUT><<<blocks_for(cells, 256 / C * 8, 148 * 4), 256, 0, st>>>(
+        z, dpool, stats, params + off.bn_g[layer], params + off.bn_b[layer], B, H, W, acc);
+    SIR_CHECK_LAUNCH("bn_pool_bwd_reduce_kernel");
+    bn_pool_bwd_apply_kernel<C, LAYOUT><<<blocks_for(cells * C), 256, 0, st>>>(
+        z, dpool, stats, params + off.bn_g[layer], params + off.bn_b[layer], B, H, W, acc, dz, dz_hi, dz_lo,
+        grads + off.bn_g[layer], grads + off.bn_b[layer]);
+    SIR_CHECK_LAUNCH("bn_pool_bwd_apply_kernel");
+    return SIR_OK;
+}
+
+template <int CIN, int COUT>
+static int conv_wgrad(const float* dz, const float* a, int B, int H, int W, float* partial, float* dw, cudaStream_t st) {
+    const int64_t rows = (int64_t)B * H;
+    const int rpc = (int)((rows + kWgradMaxChunks - 1) / kWgradMaxChunks);
+    const int chunks = (int)((rows + rpc - 1) / rpc);
+    conv_wgrad_kernel<CIN, COUT><<<dim3(9, (unsigned)chunks), 256, 0, st>>>(dz, a, B, H, W, rpc, partial);
+    SIR_CHECK_LAUNCH("conv_wgrad_kernel");
+    wgrad_reduce_kernel<<<(9 * CIN * COUT + 255) / 256, 256, 0, st>>>(partial, chunks, CIN, COUT, dw);
+    SIR_CHECK_LAUNCH("wgrad_reduce_kernel");
+    return SIR_OK;
+}
+
+// Backward of one GRU layer: dy (w.r.t. the layer output) -> parameter gradients + dx (w.r.t. the layer input).
+static int gru_layer_backward(sir_model* m, int layer, const float* params, const float* x, int in_sz, float* dx, float* grads,
+                              cudaStream_t st) {
+    TrainSaved& t = m->ts;
+    const int B = t.B, T = t.W / 8;
+    const int BT = B * T;
+    int rc;
+    gru_hprev_kernel<<<blocks_for((int64_t)2 * BT * 256), 256, 0, st>>>(t.y[layer], B, T, t.hprevf, t.hprev_hi, t.hprev_lo);
+    SIR_CHECK_LAUNCH("gru_hprev_kernel");
+    for (int d = 0; d < 2; ++d) {
+        // gh = h_prev W_hh^T + b_hh, columns in the per-CTA tile order (rank * 96 + gate * 32 + unit)
+        if ((rc = tc::tc_gemm_nt(t.hprev_hi + (size_t)d * BT * 256, t.hprev_lo + (size_t)d * BT * 256,
+                                 m->whh_hi[layer] + (size_t)d * 768 * 256, m->whh_lo[layer] + (size_t)d * 768 * 256,
+                                 m->bhh_perm[layer] + d * 768, t.gh + (size_t)d * BT * 768, BT, 768, 256, st,
+                                 "gru_bwd_recurrent_gemm")))
+            return rc;
+    }
+    {
+        static bool attr = false;
+        if (!attr) {
+            SIR_CUDA(cudaFuncSetAttribute(gru_layer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSmemBytes));
+            attr = true;
+        }
+        dim3 grid((unsigned)(kGbCluster * ((B + kGbNB - 1) / kGbNB)), 2);
+        ProfScope ps(layer == 0 ? "gru_l0_bptt" : "gru_l1_bptt", st);
+        gru_layer_bwd_kernel<<<grid, kGbThreads, kGbSmemBytes, st>>>(params + m->off.whh[layer][0], params + m->off.whh[layer][1],
+                                                                     t.gi[layer], t.gh, t.y[layer], t.dy, t.dgi, t.dgh, B, T);
+        SIR_CHECK_LAUNCH("gru_layer_bwd_kernel");
+    }
+    for (int d = 0; d < 2; ++d) {
+        const float* dgi_d = t.dgi + d * 768;
+        const float* dgh_d = t.dgh + (size_t)d * BT * 768;
+        // dW_ih = dgi^T x ; dW_hh = dgh^T h_prev ; db = column sums
+        if ((rc = sgemm<true>(dgi_d, 1536, x, in_sz, grads + m->off.wih[layer][d], in_sz, 768, in_sz, BT, 0.f, st))) return rc;
+        if ((rc = sgemm<true>(dgh_d, 768, t.hprevf + (size_t)d * BT * 256, 256, grads + m->off.whh[layer][d], 256, 768, 256, BT,
+                              0.f, st)))
+            return rc;
+        colsum_kernel<<<3, 256, 0, st>>>(dgi_d, 1536, BT, 768, grads + m->off.bih[layer][d]);
+        SIR_CHECK_LAUNCH("colsum_kernel");
+        colsum_kernel<<<3, 256, 0, st>>>(dgh_d, 768, BT, 768, grads + m->off.bhh[layer][d]);
+        SIR_CHECK_LAUNCH("colsum_kernel");
+        // dx (+)= dgi W_ih
+        if (dx && (rc = sgemm<false>(dgi_d, 1536, params + m->off.wih[layer][d], in_sz, dx, in_sz, BT, in_sz, 768,
+                                     d == 0 ? 0.f : 1.f, st)))
+            return rc;
+    }
+    return SIR_OK;
+}
+
+}  // namespace sir
+
+// ---- C ABI ------------------------------------------------------------------------------------------------
+using namespace sir;
+
+extern "C" int sir_model_train_forward(sir_model* m, float* d_params, const float* d_features, int batch, int n_frames,
+                                       const uint8_t* d_dropout_keep, uint64_t seed, uint64_t offset, float bn_momentum,
+                                       float bn_eps, float* d_logits, void* stream) {
+    if (!m || !d_params || !d_features || !d_logits) return fail(SIR_ERR_INVALID, "sir_model_train_forward: NULL argument");
+    if (batch < 1) return fail(SIR_ERR_INVALID, "sir_model_train_forward: batch must be >= 1");
+    if (n_frames < 8 || n_frames % 8 != 0)
+        return fail(SIR_ERR_UNSUPPORTED, "sir_model_train_forward: n_frames must be a positive multiple of 8 (got %d)", n_frames);
+    if (m->n_mels != 64)
+        return fail(SIR_ERR_UNSUPPORTED, "sir_model_train_forward: the training path is built for n_mels = 64 (got %d)", m->n_mels);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = batch, H = m->n_mels, W = n_frames, T = W / 8, gin = m->gru_in;
+    TrainSaved probe;
+    const size_t need = carve_train(probe, nullptr, B, H, W, gin);
+    if (need > m->train_ws.bytes) {
+        int rc0 = m->train_ws.reserve(need);
+        if (rc0 != SIR_OK) return rc0;
+        SIR_CUDA(cudaMemsetAsync(m->train_ws.ptr, 0, need, st));
+    }
+    TrainSaved& t = m->ts;
+    carve_train(t, (uint8_t*)m->train_ws.ptr, B, H, W, gin);
+    t.B = B;
+    t.H = H;
+    t.W = W;
+    t.feat = d_features;
+    m->have_saved = false;
+    m->loaded = false;                               // the repacked weights below are not the folded eval weights
+    int rc;
+    if ((rc = model_repack(m, d_params, false, bn_eps, st))) return rc;
+    const FlatOffsets& o = m->off;
+    double* acc = t.bn_acc;
+    {
+        dim3 grid((unsigned)((H * W + 127) / 128), (unsigned)B);
+        conv1_raw_kernel<<<grid, 128, 0, st>>>(d_features, m->w1, t.z1, H, W);
+        SIR_CHECK_LAUNCH("conv1_raw_kernel");
+    }
+    if ((rc = bn_stage_forward<32, 0>(t.z1, B, H, W, acc, t.stats[0], d_params, o, 0, bn_eps, bn_momentum, t.a1_hi, t.a1_lo, t.a1f,
+                                      st)))
+        return rc;
+    if ((rc = tc::tc_conv3x3<32, 64>(t.a1_hi, t.a1_lo, m->w2_hi, m->w2_lo, nullptr, nullptr, nullptr, t.z2, B, H / 2, W / 2, 0, st,
+                                     "conv2_raw")))
+        return rc;
+    if ((rc = bn_stage_forward<64, 0>(t.z2, B, H / 2, W / 2, acc + 512, t.stats[1], d_params, o, 1, bn_eps, bn_momentum, t.a2_hi,
+                                      t.a2_lo, t.a2f, st)))
+        return rc;
+    if ((rc = tc::tc_conv3x3<64, 128>(t.a2_hi, t.a2_lo, m->w3_hi, m->w3_lo, nullptr, nullptr, nullptr, t.z3, B, H / 4, W / 4, 0, st,
+                                      "conv3_raw")))
+        return rc;
+    if ((rc = bn_stage_forward<128, 1>(t.z3, B, H / 4, W / 4, acc + 1024, t.stats[2], d_params, o, 2, bn_eps, bn_momentum, t.gin_hi,
+                                       t.gin_lo, t.ginf, st)))
+        return rc;
+    const int BT = B * T;
+    // layer 0
+    if ((rc = tc::tc_gemm_nt(t.gin_hi, t.gin_lo, m->wih_hi[0], m->wih_lo[0], m->bih[0], t.gi[0], BT, 1536, gin, st,
+                             "gru_l0_input_gemm")))
+        return rc;
+    if ((rc = tc::gru_layer_tc(m->tm_whh_hi[0], m->tm_whh_lo[0], t.gi[0], m->bhh[0], t.y[0], t.ytmp_hi, t.ytmp_lo, B, T, st)))
+        return rc;
+    gru_dropout_kernel<<<blocks_for((int64_t)BT * 512 / 4), 256, 0, st>>>(t.y[0], (int64_t)BT * 512, d_dropout_keep, seed, offset,
+                                                                         t.keep, t.y0d, t.y0d_hi, t.y0d_lo);
+    SIR_CHECK_LAUNCH("gru_dropout_kernel");
+    // layer 1
+    if ((rc = tc::tc_gemm_nt(t.y0d_hi, t.y0d_lo, m->wih_hi[1], m->wih_lo[1], m->bih[1], t.gi[1], BT, 1536, 512, st,
+                             "gru_l1_input_gemm")))
+        return rc;
+    if ((rc = tc::gru_layer_tc(m->tm_whh_hi[1], m->tm_whh_lo[1], t.gi[1], m->bhh[1], t.y[1], nullptr, nullptr, B, T, st)))
+        return rc;
+    if ((rc = launch_attention_fc(m, t.y[1], d_logits, B, T, st))) return rc;
+    m->have_saved = true;
+    return SIR_OK;
+}
+
+extern "C" int sir_model_backward(sir_model* m, const float* d_params, const float* d_dlogits, float* d_grads, void* stream) {
+    if (!m || !d_params || !d_dlogits || !d_grads) return fail(SIR_ERR_INVALID, "sir_model_backward: NULL argument");
+    if (!m->have_saved) return fail(SIR_ERR_INVALID, "sir_model_backward: no training forward to differentiate");
+    cudaStream_t st = (cudaStream_t)stream;
+    TrainSaved& t = m->ts;
+    const FlatOffsets& o = m->off;
+    const int B = t.B, H = t.H, W = t.W, T = W / 8, C = m->num_classes, BT = B * T;
+    int rc;
+    SIR_CUDA(cudaMemsetAsync(d_grads, 0, (size_t)o.total * sizeof(float), st));
+    // head
+    {
+        const size_t smem = (size_t)(2 * T + 512 + C) * sizeof(float);
+        attention_fc_bwd_kernel<<<(unsigned)B, 128, smem, st>>>(t.y[1], m->att_w, m->att_b, m->fc_w, d_dlogits, t.dy, t.ds, t.ctx, T, C);
+        SIR_CHECK_LAUNCH("attention_fc_bwd_kernel");
+        const int n = C * 512 + C + 512 + 1;
+        head_param_grad_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_dlogits, t.ctx, t.ds, t.y[1], B, T, C, d_grads + o.fc_w,
+                                                               d_grads + o.fc_b, d_grads + o.att_w, d_grads + o.att_b);
+        SIR_CHECK_LAUNCH("head_param_grad_kernel");
+    }
+    // GRU layer 1 (input: dropped-out layer-0 output), dropout, GRU layer 0 (input: conv features)
+    if ((rc = gru_layer_backward(m, 1, d_params, t.y0d, 512, t.dx, d_grads, st))) return rc;
+    dropout_bwd_kernel<<<blocks_for((int64_t)BT * 512), 256, 0, st>>>(t.dx, t.keep, (int64_t)BT * 512);
+    SIR_CHECK_LAUNCH("dropout_bwd_kernel");
+    SIR_CUDA(cudaMemcpyAsync(t.dy, t.dx, (size_t)BT * 512 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if ((rc = gru_layer_backward(m, 0, d_params, t.ginf, m->gru_in, t.dx, d_grads, st))) return rc;
+    // conv3 stage: dx is the gradient w.r.t. the GRU input in the reference's feature order
+    double* acc = t.bn_acc + 256;
+    if ((rc = bn_stage_backward<128, 1>(t.z3, t.dx, B, H / 4, W / 4, acc + 1024, t.stats[2], d_params, o, 2, t.dz, t.dz_hi, t.dz_lo,
+                                        d_grads, st)))
+        return rc;
+    if ((rc = conv_wgrad<64, 128>(t.dz, t.a2f, B, H / 4, W / 4, t.wg_partial, d_grads + o.conv_w[2], st))) return rc;
+    if ((rc = tc::tc_conv3x3<128, 64>(t.dz_hi, t.dz_lo, m->w3t_hi, m->w3t_lo, nullptr, nullptr, nullptr, t.dact, B, H / 4, W / 4, 0,
+                                      st, "conv3_dgrad")))
+        return rc;
+    // conv2 stage
+    if ((rc = bn_stage_backward<64, 0>(t.z2, t.dact, B, H / 2, W / 2, acc + 512, t.stats[1], d_params, o, 1, t.dz, t.dz_hi, t.dz_lo,
+                                       d_grads, st)))
+        return rc;
+    if ((rc = conv_wgrad<32, 64>(t.dz, t.a1f, B, H / 2, W / 2, t.wg_partial, d_grads + o.conv_w[1], st))) return rc;
+    if ((rc = tc::tc_conv3x3<64, 32>(t.dz_hi, t.dz_lo, m->w2t_hi, m->w2t_lo, nullptr, nullptr, nullptr, t.dact, B, H / 2, W / 2, 0,
+                                     st, "conv2_dgrad")))
+        return rc;
+    // conv1 stage (no data gradient: the features need none)
+    if ((rc = bn_stage_backward<32, 0>(t.z1, t.dact, B, H, W, acc, t.stats[0], d_params, o, 0, t.dz, nullptr, nullptr, d_grads, st)))
+        return rc;
+    {
+        const int nblk = (int)((int64_t)B * H < kWgradMaxChunks ? (int64_t)B * H : kWgradMaxChunks);
+        conv1_wgrad_kernel<<<nblk, 256, 0, st>>>(t.dz, t.feat, B, H, W, t.wg_partial);
+        SIR_CHECK_LAUNCH("conv1_wgrad_kernel");
+        wgrad_reduce_kernel<<<2, 256, 0, st>>>(t.wg_partial, nblk, 1, 32, d_grads + o.conv_w[0]);
+        SIR_CHECK_LAUNCH("wgrad_reduce_kernel");
+    }
+    // the backward reduce/apply pair leaves its accumulators dirty (apply reads them): clear for the next step
+    SIR_CUDA(cudaMemsetAsync(t.bn_acc + 256, 0, (size_t)(3 * 2 * 256 - 256) * sizeof(double), st));
+    return SIR_OK;
+}
+
+extern "C" int sir_cross_entropy(const float* d_logits, const int64_t* d_labels, int batch, int num_classes, float scale,
+                                 float* d_loss, float* d_dlogits, void* stream) {
+    if (!d_logits || !d_labels || !d_loss || batch < 1 || num_classes < 1)
+        return fail(SIR_ERR_INVALID, "sir_cross_entropy: bad arguments");
+    cross_entropy_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_logits, d_labels, batch, num_classes, scale, d_loss, d_dlogits);
+    SIR_CHECK_LAUNCH("cross_entropy_kernel");
+    return SIR_OK;
+}
+
+extern "C" int sir_grad_nonfinite(const float* d_grads, int64_t count, float* d_flag, void* stream) {
+    if (!d_grads || !d_flag || count < 0) return fail(SIR_ERR_INVALID, "sir_grad_nonfinite: bad arguments");
+    if (count == 0) return SIR_OK;
+    grad_nonfinite_kernel<<<blocks_for(count, 256 * 8, 148 * 4), 256, 0, (cudaStream_t)stream>>>(d_grads, count, d_flag);
+    SIR_CHECK_LAUNCH("grad_nonfinite_kernel");
+    return SIR_OK;
+}
+
+extern "C" int sir_adam_step(float* d_params, const float* d_grads, float* d_exp_avg, float* d_exp_avg_sq,
+                             const int64_t* segments, int n_segments, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, int step, float inv_scale, const float* d_found_inf, void* stream) {
+    if (!d_params || !d_grads || !d_exp_avg || !d_exp_avg_sq || !segments || n_segments < 1 || n_segments > 4 || step < 1)
+        return fail(SIR_ERR_INVALID, "sir_adam_step: bad arguments");
+    AdamSegments seg{};
+    seg.n = n_segments;
+    int64_t total = 0;
+    for (int s = 0; s < n_segments; ++s) {
+        seg.offset[s] = segments[2 * s];
+        seg.count[s] = segments[2 * s + 1];
+        if (seg.offset[s] < 0 || seg.count[s] < 0) return fail(SIR_ERR_INVALID, "sir_adam_step: negative segment");
+        total += seg.count[s];
+    }
+    if (total == 0) return SIR_OK;
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    adam_kernel<<<blocks_for(total, 256 * 4, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+        d_params, d_grads, d_exp_avg, d_exp_avg_sq, seg, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, inv_scale, d_found_inf);
+    SIR_CHECK_LAUNCH("adam_kernel");
+    return SIR_OK;
+}

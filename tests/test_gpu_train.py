@@ -1,0 +1,206 @@
+"""GPU parity tests of the training step (through the C ABI) against the golden step produced by the reference
+itself (tests/golden/train.npz) and against the oracle restatement (oracle/train_port.py) at config-4 batch size.
+
+Bars: logits within 1e-3 absolute; gradients within 1e-3 of each tensor's scale (fp32 everywhere, different
+summation orders); BatchNorm running statistics within 1e-5; Adam-updated parameters within 2 % of the step size.
+"""
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import train_port
+from oracle.torch_port import ClassifierPort, load_numpy_state
+from tests.util import LOGIT_ABS_TOL, ROOT, golden, golden_keep, sample_positions, synth, train_inputs
+
+pytestmark = pytest.mark.gpu
+native = importlib.import_module("speech-intent-recognizer_b200._native")
+models = importlib.import_module("speech-intent-recognizer_b200.models.models")
+train = importlib.import_module("speech-intent-recognizer_b200.scripts.train")
+
+GRAD_REL_TOL = 1e-3
+
+
+def make_model(seed=1234):
+    sd = synth.make_weights(seed)
+    m = models.CNNAudioGRU(31)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    return m.cuda(), sd
+
+
+def check_grads_against_golden(g, sd, grads_by_key):
+    pos = sample_positions(sd)
+    for k, gr in grads_by_key.items():
+        flat = gr.detach().cpu().numpy().reshape(-1).astype(np.float64)
+        if k == "attention.bias":
+            assert abs(flat[0]) < 1e-4
+            continue
+        rms = float(g[f"gnorm/{k}"]) / np.sqrt(flat.size)
+        scale = max(np.max(np.abs(g[f"gsamp/{k}"])), rms)
+        assert np.max(np.abs(flat[pos[k]] - g[f"gsamp/{k}"])) < GRAD_REL_TOL * scale, k
+        assert abs(np.sqrt((flat * flat).sum()) - float(g[f"gnorm/{k}"])) < GRAD_REL_TOL * float(g[f"gnorm/{k}"]), k
+        assert abs(flat.sum() - float(g[f"gsum/{k}"])) < GRAD_REL_TOL * float(g[f"gnorm/{k}"]) * np.sqrt(flat.size), k
+
+
+def check_params_against_golden(g, sd, model, lr):
+    pos = sample_positions(sd)
+    new = {k: v.detach().cpu().numpy().reshape(-1) for k, v in model.named_parameters()}
+    for k in new:
+        if k == "attention.bias":
+            continue
+        gs = np.abs(g[f"gsamp/{k}"])
+        solid = gs > 1e-3 * gs.max()                      # Adam's first step is lr * g / (|g| + eps): ill-conditioned at g ~ 0
+        diff = np.abs(new[k][pos[k]] - g[f"psamp/{k}"])
+        assert np.all(diff[solid] < 0.02 * lr), (k, diff[solid].max())
+        assert np.all(diff < 2.1 * lr), k
+
+
+def test_train_forward_backward_match_reference_golden():
+    g = golden("train")
+    x, labels = train_inputs()
+    model, sd = make_model(int(g["weight_seed"]))
+    model.train()
+    model._next_dropout_keep = torch.from_numpy(golden_keep(g)).cuda()
+    before = native.launch_count()
+    out = model(torch.from_numpy(x).cuda())
+    assert np.max(np.abs(out.detach().cpu().numpy() - g["logits"])) < LOGIT_ABS_TOL
+    loss = torch.nn.functional.cross_entropy(out, torch.from_numpy(labels).cuda())
+    assert abs(float(loss) - float(g["loss"])) < 1e-3
+    loss.backward()
+    assert native.launch_count() - before > 30
+    check_grads_against_golden(g, sd, {k: p.grad for k, p in model.named_parameters()})
+    for k, b in model.named_buffers():                                  # running statistics, momentum 0.1, unbiased var
+        if "num_batches" in k:
+            assert int(b) == 1
+        else:
+            assert np.max(np.abs(b.cpu().numpy() - g[f"buf/{k}"])) < 1e-5, k
+    # the reference's optimizer on top of our gradients (scripts/train.py:246-250, :107-108)
+    opt = torch.optim.Adam(model.parameters(), lr=float(g["lr"]), weight_decay=float(g["weight_decay"]))
+    opt.step()
+    check_params_against_golden(g, sd, model, float(g["lr"]))
+    # eval after a training step re-folds BatchNorm from the updated running statistics
+    model.eval()
+    ref = load_numpy_state(ClassifierPort(31), {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}).eval()
+    with torch.no_grad():
+        want = ref(torch.from_numpy(x))
+    assert np.max(np.abs(model(torch.from_numpy(x).cuda()).cpu().numpy() - want.numpy())) < LOGIT_ABS_TOL
+
+
+def test_fused_trainer_step_matches_reference_golden():
+    """DataParallelTrainer (fused CE, loss scaling, unscale + Adam) on one GPU == the reference's step."""
+    g = golden("train")
+    x, labels = train_inputs()
+    model, sd = make_model(int(g["weight_seed"]))
+    tr = train.DataParallelTrainer(model, lr=float(g["lr"]), weight_decay=float(g["weight_decay"]), use_amp=True)
+    keep = torch.from_numpy(golden_keep(g)).cuda()
+    loss = tr.step(torch.from_numpy(x).cuda(), torch.from_numpy(labels).cuda(), dropout_keep=keep)
+    assert abs(loss - float(g["loss"])) < 1e-3
+    assert tr.adam_steps == 1 and tr.skipped_steps == 0 and tr.scaler.scale == 65536.0
+    flat_grad = model._flat_grad[:model.weight_count()] / 65536.0
+    grads, off = {}, 0
+    named = dict(model._named_tensors())
+    for key, shape in model._spec():
+        n = int(np.prod(shape))
+        if key in dict(model.named_parameters()):
+            grads[key] = flat_grad[off:off + n]
+        off += n
+    check_grads_against_golden(g, sd, grads)
+    check_params_against_golden(g, sd, model, float(g["lr"]))
+    assert np.max(np.abs(named["bn2.running_var"].cpu().numpy() - g["buf/bn2.running_var"])) < 1e-5
+    # a non-finite gradient skips the update on this rank and backs the scale off
+    before = model._flat.clone()
+    bad = torch.from_numpy(x).cuda()
+    bad[0, 0, 0] = float("inf")
+    tr.step(bad, torch.from_numpy(labels).cuda(), dropout_keep=keep)
+    assert tr.skipped_steps == 1 and tr.adam_steps == 1 and tr.scaler.scale == 32768.0
+    segs = model.param_segments()
+    for o, n in segs:
+        assert torch.equal(model._flat[o:o + n], before[o:o + n])
+
+
+def test_config4_batch_gradients_match_oracle():
+    """Batch 16 x [64,200] (config.yaml batch_size): every gradient element against the CPU restatement."""
+    B = 16
+    x, labels = train_inputs(seed=77, batch=B)
+    rng = np.random.default_rng(5)
+    keep = (rng.random((B, 25, 512)) >= 0.5).astype(np.uint8)
+    model, sd = make_model(1234)
+    model.train()
+    model._next_dropout_keep = torch.from_numpy(keep).cuda()
+    out = model(torch.from_numpy(x).cuda())
+    loss = torch.nn.functional.cross_entropy(out, torch.from_numpy(labels).cuda())
+    loss.backward()
+    port = load_numpy_state(ClassifierPort(31), sd)
+    torch.set_num_threads(os.cpu_count() or 1)
+    want_loss, want_logits, want = train_port.loss_and_grads(port, torch.from_numpy(x), torch.from_numpy(labels),
+                                                            torch.from_numpy(keep))
+    assert np.max(np.abs(out.detach().cpu().numpy() - want_logits.numpy())) < LOGIT_ABS_TOL
+    assert abs(float(loss) - want_loss) < 1e-3
+    for k, p in model.named_parameters():
+        a, b = p.grad.cpu().numpy().astype(np.float64), want[k].numpy().astype(np.float64)
+        if k == "attention.bias":
+            assert abs(a[0]) < 1e-4
+            continue
+        assert np.max(np.abs(a - b)) < GRAD_REL_TOL * np.max(np.abs(b)), (k, np.max(np.abs(a - b)), np.max(np.abs(b)))
+
+
+def test_cross_entropy_and_adam_kernels_against_torch():
+    torch.manual_seed(3)
+    logits = (torch.randn(37, 31, device="cuda") * 6).requires_grad_()
+    labels = torch.randint(0, 31, (37,), device="cuda")
+    loss, dl = native.cross_entropy(logits.detach(), labels, scale=8.0)
+    want = torch.nn.functional.cross_entropy(logits, labels)
+    want.backward()
+    assert abs(float(loss) - float(want)) < 1e-5
+    assert torch.allclose(dl / 8.0, logits.grad, atol=1e-7, rtol=1e-5)
+    # Adam over two segments with a gap (the gap = BatchNorm running statistics must not move), 3 steps
+    n = 5000
+    p0 = torch.randn(n, device="cuda")
+    ref_p = p0.clone().requires_grad_()
+    opt = torch.optim.Adam([ref_p], lr=3e-3, weight_decay=1e-2, betas=(0.9, 0.999), eps=1e-8)
+    p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    segs = [(0, 2000), (2100, 2900)]
+    for step in range(1, 4):
+        gr = torch.randn(n, device="cuda")
+        ref_p.grad = gr.clone()
+        opt.step()
+        native.adam_step(p, gr * 4.0, m, v, segs, 3e-3, (0.9, 0.999), 1e-8, 1e-2, step=step, inv_scale=0.25)
+    assert torch.allclose(p[:2000], ref_p.detach()[:2000], atol=1e-6, rtol=1e-5)
+    assert torch.allclose(p[2100:], ref_p.detach()[2100:], atol=1e-6, rtol=1e-5)
+    assert torch.equal(p[2000:2100], p0[2000:2100])
+    flag = torch.ones(1, device="cuda")
+    snap = p.clone()
+    native.adam_step(p, gr, m, v, segs, 3e-3, step=4, found_inf=flag)
+    assert torch.equal(p, snap)
+    flag.zero_()
+    gr[123] = float("nan")
+    native.grad_nonfinite(gr, n, flag)
+    assert float(flag) == 1.0
+
+
+def test_train_epoch_mirror_runs_and_learns():
+    """scripts/train.py:72-118 mirror with torch's optimizer / criterion on top of the CUDA model."""
+    model, _ = make_model(1234)
+    x, labels = train_inputs(seed=9, batch=8)
+    loader = [(torch.from_numpy(x), torch.from_numpy(labels))] * 6
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    crit = torch.nn.CrossEntropyLoss()
+    first = train.train_epoch(model, loader[:1], opt, crit, "cuda")
+    for _ in range(3):
+        last = train.train_epoch(model, loader, opt, crit, "cuda")
+    assert last < 0.5 * first
+    vloss, acc = train.validate(model, loader[:1], crit, "cuda")
+    assert np.isfinite(vloss) and 0.0 <= acc <= 1.0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_data_parallel_two_gpus_equals_one_big_batch_of_gradients():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(ROOT, "tests", "dp_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "dp_check ok" in out.stdout

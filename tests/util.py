@@ -41,3 +41,29 @@ def golden_waves():
     assert sha(waves) == str(g["speech_sha"]), "synthetic speech generator drifted from the golden inputs"
     assert sha(noise) == str(g["noise_sha"]), "synthetic noise generator drifted from the golden inputs"
     return g, waves, lengths, noise
+
+
+# ---- training-step fixtures (shared with tests/golden/make_golden_train.py) -----------------------------------
+TRAIN_B, TRAIN_FRAMES, TRAIN_VALID, TRAIN_CLASSES = 6, 200, 94, 31
+TRAIN_SEED, TRAIN_N_SAMPLES = 20261018, 48
+
+
+def train_inputs(seed=TRAIN_SEED, batch=TRAIN_B):
+    """Normalised log-mel-like features: unit-variance noise with slow structure on the valid frames, zero tail."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((batch, 64, TRAIN_FRAMES)).astype(np.float32)
+    x += (0.8 * np.sin(np.linspace(0, 6, 64, dtype=np.float32))[None, :, None]
+          * rng.uniform(0.5, 1.5, (batch, 1, 1)).astype(np.float32))
+    x[:, :, TRAIN_VALID:] = 0.0
+    labels = rng.integers(0, TRAIN_CLASSES, size=batch).astype(np.int64)
+    return x, labels
+
+
+def sample_positions(sd, seed=TRAIN_SEED):
+    rng = np.random.default_rng(seed + 1)
+    return {k: np.sort(rng.choice(v.size, size=min(TRAIN_N_SAMPLES, v.size), replace=False)) for k, v in sd.items()}
+
+
+def golden_keep(g, batch=TRAIN_B, frames=TRAIN_FRAMES):
+    n = batch * (frames // 8) * 512
+    return np.unpackbits(g["keep_bits"])[:n].reshape(batch, frames // 8, 512).astype(np.uint8)
