@@ -176,6 +176,13 @@ int sir_adam_step(float* d_params, const float* d_grads, float* d_exp_avg, float
 int sir_gemm_nt_split_f16(const float* d_a, const float* d_w, const float* d_bias, float* d_c, int M, int N, int K,
                           void* stream);
 
+/* sir_conv3x3_nhwc_split_f16: 3x3 convolution (stride 1, zero padding 1, no bias) of channels-last fp32 tensors,
+ * d_in [B,H,W,C_in] * d_w [9 taps][C_out][C_in] -> d_out [B,H,W,C_out], as the implicit GEMM on tcgen05 behind
+ * conv2 / conv3 (models/models.py:12-15) and behind their data gradients; (C_in, C_out) in
+ * {(32,64), (64,128), (128,64), (64,32)}.  Exported stand-alone so that tests can check it against conv2d. */
+int sir_conv3x3_nhwc_split_f16(const float* d_in, const float* d_w, float* d_out, int B, int H, int W, int cin, int cout,
+                               void* stream);
+
 /* sir_pipeline_forward: frontend (SIR_OUT_LOGMEL_NORM, pad/trim to out_frames) + classifier in one call.
  * d_features may be NULL (features then live only in the model's workspace). */
 int sir_pipeline_forward(sir_frontend* fe, sir_model* m, const float* d_wave, int64_t wave_stride,

@@ -46,6 +46,7 @@ SIGNATURES = {
     "sir_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int, c_float, c_float, c_float,
                               c_float, c_float, c_int, c_float, c_void_p, c_void_p]),
     "sir_gemm_nt_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "sir_conv3x3_nhwc_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sir_pipeline_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p]),
 }
@@ -304,3 +305,16 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, segments, lr, betas=(0.9, 0.99
     check(load_library().sir_adam_step(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), seg, len(segments), float(lr),
                                        float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
                                        float(inv_scale), ptr(found_inf), stream_ptr()), "sir_adam_step")
+
+
+def conv3x3_nhwc_split_f16(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """``x [B,H,W,Cin]``, ``w [9,Cout,Cin]`` (tap-major) -> ``[B,H,W,Cout]``: the tcgen05 implicit-GEMM convolution."""
+    require_cuda(x, "x")
+    require_cuda(w, "w")
+    x, w = x.contiguous(), w.contiguous()
+    B, H, W, cin = x.shape
+    cout = w.shape[1]
+    out = torch.empty((B, H, W, cout), device=x.device, dtype=torch.float32)
+    check(load_library().sir_conv3x3_nhwc_split_f16(ptr(x), ptr(w), ptr(out), B, H, W, cin, cout, stream_ptr()),
+          "sir_conv3x3_nhwc_split_f16")
+    return out

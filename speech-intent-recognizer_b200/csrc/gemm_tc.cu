@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const int y = y0 + 2 * q + (lane >> 4), x = x0 + (lane & 15);
             const bool inside = y < p.H && x < p.W;
             float* dst_row = p.raw_out + (((int64_t)img * p.H + y) * p.W + x) * BLOCK_N;
+            const float os = p.shift ? __ldg(p.shift) : 1.f;        // raw mode: shift[0] is the output scale (device scalar)
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N; c += 32) {
                 float v[32];
@@ -183,7 +184,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (inside) {
                     float4* dst = reinterpret_cast<float4*>(dst_row + c);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    for (int i = 0; i < 8; ++i)
+                        dst[i] = make_float4(v[4 * i] * os, v[4 * i + 1] * os, v[4 * i + 2] * os, v[4 * i + 3] * os);
                 }
             }
         } else {
@@ -327,7 +329,9 @@ int tc_gemm_nt(const __half* a_hi, const __half* a_lo, const __half* w_hi, const
 // 3x3 conv (s1, p1) on channels-last fp16 hi/lo activations [B,H,W,CIN]; weights [9][COUT][CIN] hi/lo.
 //   raw_out == nullptr : + shift + ReLU + 2x2 max-pool -> [B,H/2,W/2,COUT] (or [B,W/2,H/2,COUT]) hi/lo  (eval forward)
 //   raw_out != nullptr : plain convolution -> fp32 [B,H,W,COUT]  (training forward before BatchNorm, and the
-//                        data gradient of a convolution = the same stencil with flipped, transposed weights)
+//                        data gradient of a convolution = the same stencil with flipped, transposed weights);
+//                        `shift`, if given, points at ONE device float the output is multiplied by (the inverse
+//                        of the power-of-two scale applied to the gradient operand before its fp16 split)
 template <int CIN, int COUT>
 int tc_conv3x3(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
                __half* out_hi, __half* out_lo, float* raw_out, int B, int H, int W, int out_whc, cudaStream_t st,
@@ -400,4 +404,32 @@ extern "C" int sir_gemm_nt_split_f16(const float* d_a, const float* d_w, const f
     if ((rc = tc::split_f16_async(d_a, a_hi, a_lo, (int64_t)na, st))) return rc;
     if ((rc = tc::split_f16_async(d_w, w_hi, w_lo, (int64_t)nw, st))) return rc;
     return tc::tc_gemm_nt(a_hi, a_lo, w_hi, w_lo, d_bias, d_c, M, N, K, st, "gemm_nt_split_f16");
+}
+
+// 3x3 convolution (stride 1, zero padding 1, no bias) on channels-last fp32 tensors through the same implicit-GEMM
+// kernel the classifier uses; exported so that tests can check every instantiation against torch's conv2d.
+extern "C" int sir_conv3x3_nhwc_split_f16(const float* d_in, const float* d_w, float* d_out, int B, int H, int W, int cin,
+                                          int cout, void* stream) {
+    if (!d_in || !d_w || !d_out || B < 1 || H < 1 || W < 1) return fail(SIR_ERR_INVALID, "sir_conv3x3_nhwc_split_f16: bad arguments");
+    static DeviceBuffer scratch;
+    const size_t na = (size_t)B * H * W * cin, nw = (size_t)9 * cout * cin;
+    const size_t na_pad = (na + 63) & ~(size_t)63, nw_pad = (nw + 63) & ~(size_t)63;
+    int rc = scratch.reserve((2 * na_pad + 2 * nw_pad) * sizeof(__half) + 1024);
+    if (rc != SIR_OK) return rc;
+    __half* a_hi = (__half*)scratch.ptr;
+    __half* a_lo = a_hi + na_pad;
+    __half* w_hi = a_lo + na_pad;
+    __half* w_lo = w_hi + nw_pad;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = tc::split_f16_async(d_in, a_hi, a_lo, (int64_t)na, st))) return rc;
+    if ((rc = tc::split_f16_async(d_w, w_hi, w_lo, (int64_t)nw, st))) return rc;
+    if (cin == 32 && cout == 64)
+        return tc::tc_conv3x3<32, 64>(a_hi, a_lo, w_hi, w_lo, nullptr, nullptr, nullptr, d_out, B, H, W, 0, st, "conv3x3_32_64");
+    if (cin == 64 && cout == 128)
+        return tc::tc_conv3x3<64, 128>(a_hi, a_lo, w_hi, w_lo, nullptr, nullptr, nullptr, d_out, B, H, W, 0, st, "conv3x3_64_128");
+    if (cin == 128 && cout == 64)
+        return tc::tc_conv3x3<128, 64>(a_hi, a_lo, w_hi, w_lo, nullptr, nullptr, nullptr, d_out, B, H, W, 0, st, "conv3x3_128_64");
+    if (cin == 64 && cout == 32)
+        return tc::tc_conv3x3<64, 32>(a_hi, a_lo, w_hi, w_lo, nullptr, nullptr, nullptr, d_out, B, H, W, 0, st, "conv3x3_64_32");
+    return fail(SIR_ERR_UNSUPPORTED, "sir_conv3x3_nhwc_split_f16: (C_in, C_out) = (%d, %d) is not instantiated", cin, cout);
 }

@@ -75,6 +75,7 @@ struct TrainSaved {
     float *dy, *dx, *ds, *ctx, *dgi, *dgh, *gh, *hprevf, *dz, *dact, *wg_partial;
     __half *hprev_hi, *hprev_lo, *dz_hi, *dz_lo;
     double* bn_acc;                     // [3 layers][2 (fwd, bwd)][2*128] accumulators, zero between uses
+    float* amax;                        // max |dz| per data-gradient convolution + the inverse split scales
 };
 
 }  // namespace sir

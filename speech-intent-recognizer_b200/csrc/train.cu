@@ -17,6 +17,8 @@
 // [B, T, c * H8 + h] (the reference's feature order, models/models.py:55-57) for the weight-gradient operand, so
 // gradients land in the reference's parameter layout.
 #include <cmath>
+#include <cstdlib>
+#include <vector>
 
 #include "model.cuh"
 #include "philox.cuh"
@@ -655,9 +657,10 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float* __r
                                                                 const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, int B, int H, int W,
                                                                 const double* __restrict__ acc, float* __restrict__ dz,
-                                                                __half* __restrict__ dz_hi, __half* __restrict__ dz_lo,
-                                                                float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+                                                                float* __restrict__ amax, float* __restrict__ d_gamma,
+                                                                float* __restrict__ d_beta) {
     const int H2 = H / 2, W2 = W / 2;
+    float local_max = 0.f;
     const double Npix = (double)B * H * W;
     const int64_t total = (int64_t)B * H2 * W2 * C;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
@@ -681,13 +684,36 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(const float* __r
         for (int p = 0; p < 4; ++p) {
             const float v = k * ((p == pa.arg ? du : 0.f) - m1 - pa.zhat[p] * m2);
             dz[base + offs[p]] = v;
-            if (dz_hi) {
-                __half h, l;
-                tc::split_f16(v, h, l);
-                dz_hi[base + offs[p]] = h;
-                dz_lo[base + offs[p]] = l;
-            }
+            local_max = fmaxf(local_max, fabsf(v));
         }
+    }
+    if (amax) {                                   // max |dz| of the tensor: sets the fp16 split's power-of-two scale
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+        if ((threadIdx.x & 31) == 0 && local_max > 0.f && isfinite(local_max))
+            atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(local_max));
+    }
+}
+
+// dz -> fp16 (hi, lo) operand of the data-gradient convolution, scaled by a power of two so that max |dz| lands
+// in [8192, 16384): gradients span many orders of magnitude (and carry the loss scale), fp16 does not.
+// inv_scale[0] receives 1 / scale for the convolution's epilogue.
+__global__ void scaled_split_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ amax,
+                                    __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ inv_scale) {
+    const float a = *amax;
+    int e = 0;
+    if (a > 0.f) {
+        frexpf(a, &e);                             // a = f * 2^e, f in [0.5, 1)
+        e = 14 - e;                                // a * 2^e in [8192, 16384)
+        e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    }
+    const float scale = ldexpf(1.f, e);
+    if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[0] = ldexpf(1.f, -e);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        __half h, l;
+        tc::split_f16(x[i] * scale, h, l);
+        hi[i] = h;
+        lo[i] = l;
     }
 }
 
@@ -838,6 +864,22 @@ __global__ void grad_nonfinite_kernel(const float* __restrict__ g, int64_t n, fl
 // =========================================================================================================
 // host orchestration
 // =========================================================================================================
+// Debug aid: with SIR_TRAIN_DUMP=<prefix> in the environment the backward writes intermediate tensors to
+// <prefix><name>.bin (raw fp32) after synchronising the stream.  Never set in production.
+static void debug_dump(const char* name, const float* d, size_t n, cudaStream_t st) {
+    static const char* prefix = getenv("SIR_TRAIN_DUMP");
+    if (!prefix) return;
+    std::vector<float> h(n);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), d, n * sizeof(float), cudaMemcpyDeviceToHost);
+    char path[512];
+    snprintf(path, sizeof(path), "%s%s.bin", prefix, name);
+    if (FILE* f = fopen(path, "wb")) {
+        fwrite(h.data(), sizeof(float), n, f);
+        fclose(f);
+    }
+}
+
 template <bool TA>
 static int sgemm(const float* A, int lda, const float* Bm, int ldb, float* Cm, int ldc, int M, int N, int K, float beta,
                  cudaStream_t st) {
@@ -864,6 +906,7 @@ static size_t carve_train(TrainSaved& t, uint8_t* base, int B, int H, int W, int
     const size_t n_a1 = (size_t)B * H2 * W2 * 32, n_a2 = (size_t)B * H4 * W4 * 64, n_g = (size_t)B * T * gin;
     const size_t BT = (size_t)B * T, n_y = BT * 512;
     t.bn_acc = (double*)next(3 * 2 * 256 * 8);     // first: fixed offset, so it stays zeroed when the batch size changes
+    t.amax = (float*)next(8 * 4);                  // [layer 3, layer 2] max |dz|, then their inverse split scales
     t.z1 = (float*)next(n_z1 * 4);
     t.z2 = (float*)next(n_z2 * 4);
     t.z3 = (float*)next(n_z3 * 4);
@@ -928,15 +971,20 @@ static int bn_stage_forward(const float* z, int B, int H, int W, double* acc, fl
 template <int C, int LAYOUT>
 static int bn_stage_backward(const float* z, const float* dpool, int B, int H, int W, double* acc, const float* stats,
                              const float* params, const FlatOffsets& off, int layer, float* dz, __half* dz_hi, __half* dz_lo,
-                             float* grads, cudaStream_t st) {
+                             float* amax, float* grads, cudaStream_t st) {
     const int64_t cells = (int64_t)B * (H / 2) * (W / 2);
     bn_pool_bwd_reduce_kernel<C, LAYOUT><<<blocks_for(cells, 256 / C * 8, 148 * 4), 256, 0, st>>>(
         z, dpool, stats, params + off.bn_g[layer], params + off.bn_b[layer], B, H, W, acc);
     SIR_CHECK_LAUNCH("bn_pool_bwd_reduce_kernel");
     bn_pool_bwd_apply_kernel<C, LAYOUT><<<blocks_for(cells * C), 256, 0, st>>>(
-        z, dpool, stats, params + off.bn_g[layer], params + off.bn_b[layer], B, H, W, acc, dz, dz_hi, dz_lo,
-        grads + off.bn_g[layer], grads + off.bn_b[layer]);
+        z, dpool, stats, params + off.bn_g[layer], params + off.bn_b[layer], B, H, W, acc, dz, amax, grads + off.bn_g[layer],
+        grads + off.bn_b[layer]);
     SIR_CHECK_LAUNCH("bn_pool_bwd_apply_kernel");
+    if (dz_hi) {
+        const int64_t n = (int64_t)B * H * W * C;
+        scaled_split_kernel<<<blocks_for(n), 256, 0, st>>>(dz, n, amax, dz_hi, dz_lo, amax + 2);
+        SIR_CHECK_LAUNCH("scaled_split_kernel");
+    }
     return SIR_OK;
 }
 
@@ -1086,6 +1134,7 @@ extern "C" int sir_model_backward(sir_model* m, const float* d_params, const flo
     const int B = t.B, H = t.H, W = t.W, T = W / 8, C = m->num_classes, BT = B * T;
     int rc;
     SIR_CUDA(cudaMemsetAsync(d_grads, 0, (size_t)o.total * sizeof(float), st));
+    SIR_CUDA(cudaMemsetAsync(t.amax, 0, 8 * sizeof(float), st));
     // head
     {
         const size_t smem = (size_t)(2 * T + 512 + C) * sizeof(float);
@@ -1102,25 +1151,31 @@ extern "C" int sir_model_backward(sir_model* m, const float* d_params, const flo
     SIR_CHECK_LAUNCH("dropout_bwd_kernel");
     SIR_CUDA(cudaMemcpyAsync(t.dy, t.dx, (size_t)BT * 512 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if ((rc = gru_layer_backward(m, 0, d_params, t.ginf, m->gru_in, t.dx, d_grads, st))) return rc;
+    debug_dump("dgin", t.dx, (size_t)BT * m->gru_in, st);
     // conv3 stage: dx is the gradient w.r.t. the GRU input in the reference's feature order
     double* acc = t.bn_acc + 256;
     if ((rc = bn_stage_backward<128, 1>(t.z3, t.dx, B, H / 4, W / 4, acc + 1024, t.stats[2], d_params, o, 2, t.dz, t.dz_hi, t.dz_lo,
-                                        d_grads, st)))
+                                        t.amax, d_grads, st)))
         return rc;
     if ((rc = conv_wgrad<64, 128>(t.dz, t.a2f, B, H / 4, W / 4, t.wg_partial, d_grads + o.conv_w[2], st))) return rc;
-    if ((rc = tc::tc_conv3x3<128, 64>(t.dz_hi, t.dz_lo, m->w3t_hi, m->w3t_lo, nullptr, nullptr, nullptr, t.dact, B, H / 4, W / 4, 0,
-                                      st, "conv3_dgrad")))
+    if ((rc = tc::tc_conv3x3<128, 64>(t.dz_hi, t.dz_lo, m->w3t_hi, m->w3t_lo, t.amax + 2, nullptr, nullptr, t.dact, B, H / 4,
+                                      W / 4, 0, st, "conv3_dgrad")))
         return rc;
+    debug_dump("dz3", t.dz, (size_t)B * (H / 4) * (W / 4) * 128, st);
+    debug_dump("da2", t.dact, (size_t)B * (H / 4) * (W / 4) * 64, st);
     // conv2 stage
     if ((rc = bn_stage_backward<64, 0>(t.z2, t.dact, B, H / 2, W / 2, acc + 512, t.stats[1], d_params, o, 1, t.dz, t.dz_hi, t.dz_lo,
-                                       d_grads, st)))
+                                       t.amax + 1, d_grads, st)))
         return rc;
     if ((rc = conv_wgrad<32, 64>(t.dz, t.a1f, B, H / 2, W / 2, t.wg_partial, d_grads + o.conv_w[1], st))) return rc;
-    if ((rc = tc::tc_conv3x3<64, 32>(t.dz_hi, t.dz_lo, m->w2t_hi, m->w2t_lo, nullptr, nullptr, nullptr, t.dact, B, H / 2, W / 2, 0,
-                                     st, "conv2_dgrad")))
+    if ((rc = tc::tc_conv3x3<64, 32>(t.dz_hi, t.dz_lo, m->w2t_hi, m->w2t_lo, t.amax + 3, nullptr, nullptr, t.dact, B, H / 2,
+                                     W / 2, 0, st, "conv2_dgrad")))
         return rc;
+    debug_dump("dz2", t.dz, (size_t)B * (H / 2) * (W / 2) * 64, st);
+    debug_dump("da1", t.dact, (size_t)B * (H / 2) * (W / 2) * 32, st);
     // conv1 stage (no data gradient: the features need none)
-    if ((rc = bn_stage_backward<32, 0>(t.z1, t.dact, B, H, W, acc, t.stats[0], d_params, o, 0, t.dz, nullptr, nullptr, d_grads, st)))
+    if ((rc = bn_stage_backward<32, 0>(t.z1, t.dact, B, H, W, acc, t.stats[0], d_params, o, 0, t.dz, nullptr, nullptr, nullptr,
+                                       d_grads, st)))
         return rc;
     {
         const int nblk = (int)((int64_t)B * H < kWgradMaxChunks ? (int64_t)B * H : kWgradMaxChunks);

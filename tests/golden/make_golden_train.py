@@ -34,7 +34,7 @@ from oracle import train_port  # noqa: E402
 from oracle.torch_port import ClassifierPort, load_numpy_state  # noqa: E402
 
 from tests.util import (TRAIN_B as B, TRAIN_CLASSES as CLASSES, TRAIN_FRAMES as FRAMES, TRAIN_SEED as SEED,  # noqa: E402
-                        sample_positions, train_inputs as make_inputs)
+                        pool_tie_margin, sample_positions, train_inputs as make_inputs)
 
 torch.set_num_threads(4)
 WEIGHT_SEED, LR, WD = 1234, 1e-3, 1e-4
@@ -64,6 +64,8 @@ def main():
 
     keep = train_port.recover_gru_dropout_keep(SEED, B, FRAMES // 8)
     port = load_numpy_state(ClassifierPort(CLASSES), sd)
+    margin = pool_tie_margin(port, xt)
+    assert margin > 1e-5, f"seed {SEED} has a near-tied max-pool window (gap {margin:.2e}); scan for another seed"
     p_loss, p_logits, p_grads = train_port.loss_and_grads(port, xt, lt, keep)
     assert torch.allclose(p_logits, out.detach(), atol=2e-5, rtol=1e-5), (p_logits - out).abs().max()
     assert abs(p_loss - float(loss)) < 1e-5
@@ -82,7 +84,8 @@ def main():
 
     pos = sample_positions(sd)
     store = {"seed": SEED, "weight_seed": WEIGHT_SEED, "lr": LR, "weight_decay": WD, "x_sha": sha(x), "labels": labels,
-             "keep_bits": np.packbits(keep.numpy().reshape(-1)), "logits": out.detach().numpy(), "loss": np.float32(float(loss))}
+             "keep_bits": np.packbits(keep.numpy().reshape(-1)), "logits": out.detach().numpy(), "loss": np.float32(float(loss)),
+             "pool_tie_margin": np.float64(margin)}
     new_sd = ref.state_dict()
     for k, g in ref_grads.items():
         g = g.numpy().reshape(-1).astype(np.float64)

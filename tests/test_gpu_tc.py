@@ -21,3 +21,17 @@ def test_gemm_nt_split_f16_matches_fp64(M, N, K):
     scale = want.abs().max().item()
     # fp32 GEMM accuracy is ~1e-6 of the scale; a single fp16 pass would be ~1e-3
     assert err < 2e-6 * scale * (K / 64) ** 0.5 + 1e-6, (err, scale)
+
+
+@pytest.mark.parametrize("cin,cout,H,W", [(32, 64, 32, 100), (64, 128, 16, 50), (128, 64, 16, 50), (64, 32, 32, 100),
+                                          (64, 32, 9, 21)])
+def test_tc_conv3x3_matches_conv2d(cin, cout, H, W):
+    """Every instantiation of the implicit-GEMM convolution (forward shapes and data-gradient shapes)."""
+    torch.manual_seed(cin + cout)
+    B = 3
+    x = torch.randn(B, H, W, cin, device="cuda")
+    w = torch.randn(cout, cin, 3, 3, device="cuda") * 0.1
+    got = native.conv3x3_nhwc_split_f16(x, w.permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous())
+    want = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), padding=1).permute(0, 2, 3, 1)
+    err = float((got.double() - want).abs().max() / want.abs().max())
+    assert err < 1e-5, err          # fp32-level: K = 9 * C_in up to 1152 products per output

@@ -22,6 +22,7 @@ def test_oracle_training_step_matches_reference_golden():
     g = golden("train")
     x, labels = train_inputs()
     assert sha(x) == str(g["x_sha"]) and np.array_equal(labels, g["labels"])
+    assert float(g["pool_tie_margin"]) > 1e-5          # fixture chosen without near-tied max-pool windows
     sd = synth.make_weights(int(g["weight_seed"]))
     port = load_numpy_state(ClassifierPort(31), sd)
     keep = torch.from_numpy(golden_keep(g))

@@ -45,7 +45,9 @@ def golden_waves():
 
 # ---- training-step fixtures (shared with tests/golden/make_golden_train.py) -----------------------------------
 TRAIN_B, TRAIN_FRAMES, TRAIN_VALID, TRAIN_CLASSES = 6, 200, 94, 31
-TRAIN_SEED, TRAIN_N_SAMPLES = 20261018, 48
+# seeds picked by scanning for fixtures without near-tied max-pool windows (pool_tie_margin below)
+TRAIN_SEED, TRAIN_N_SAMPLES = 20261077, 48
+TRAIN_SEED_B16 = 179
 
 
 def train_inputs(seed=TRAIN_SEED, batch=TRAIN_B):
@@ -67,3 +69,31 @@ def sample_positions(sd, seed=TRAIN_SEED):
 def golden_keep(g, batch=TRAIN_B, frames=TRAIN_FRAMES):
     n = batch * (frames // 8) * 512
     return np.unpackbits(g["keep_bits"])[:n].reshape(batch, frames // 8, 512).astype(np.uint8)
+
+
+def pool_tie_margin(port, x):
+    """Smallest gap between the two largest candidates of any 2x2 max-pool window that passes its ReLU, over the
+    three conv stages of ``port`` (a ClassifierPort) in train mode on ``x [B,64,T]`` (torch tensor).
+
+    Max-pool routes the whole gradient of a window to its arg-max.  Two implementations whose conv outputs differ
+    by fp32 rounding (~1e-6) pick different arg-maxes where the top two candidates tie to that precision - both
+    are valid sub-gradients, but the gradients differ visibly.  Gradient-parity fixtures are therefore chosen (by
+    seed) so that no window ties, and the tests assert this margin to say so.
+    """
+    import copy
+    import torch
+    import torch.nn.functional as F
+    m = copy.deepcopy(port).train()
+    h, margin = x.unsqueeze(1), float("inf")
+    with torch.no_grad():
+        for i in (1, 2, 3):
+            u = getattr(m, f"bn{i}")(getattr(m, f"conv{i}")(h))
+            B, C, H, W = u.shape
+            win = u[:, :, :H // 2 * 2, :W // 2 * 2].reshape(B, C, H // 2, 2, W // 2, 2).permute(0, 1, 2, 4, 3, 5)
+            top2 = win.reshape(B, C, H // 2, W // 2, 4).topk(2, dim=-1).values
+            on = top2[..., 0] > 0
+            gap = (top2[..., 0] - torch.clamp(top2[..., 1], min=0.0))[on]       # a runner-up below 0 ties with ReLU's 0
+            gap = gap[gap > 0]          # exact ties (the all-zero padding frames) resolve identically everywhere: first wins
+            margin = min(margin, float(gap.min()))
+            h = F.max_pool2d(F.relu(u), 2)
+    return margin
