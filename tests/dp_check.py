@@ -42,11 +42,12 @@ def main():
     n = model.weight_count()
     tr.step(xs, ls, dropout_keep=ks)
     reduced = model._flat_grad[:n].clone()
-    # (a) identical parameters everywhere
+    # (a) identical trainable parameters everywhere (BatchNorm running statistics are per GPU: no SyncBN in the reference)
     mine = model._flat.clone()
     other = mine.clone()
     dist.broadcast(other, src=0)
-    assert torch.equal(mine, other), "parameters diverged between ranks"
+    for o, k in model.param_segments():
+        assert torch.equal(mine[o:o + k], other[o:o + k]), "parameters diverged between ranks"
     # (b) the all-reduce is the sum of the local gradients
     if rank == 0:
         total = torch.zeros(n, device="cuda")
