@@ -385,7 +385,8 @@ __global__ void __cluster_dims__(kGbCluster, 1, 1) __launch_bounds__(kGbThreads,
                          const float* __restrict__ dy,        // [B, T, 512] gradient w.r.t. the layer output
                          float* __restrict__ dgi,             // [B*T, 1536]
                          float* __restrict__ dgh,             // [2][B*T, 768] natural gate order
-                         int B, int T) {
+                         float* __restrict__ dbih_f, float* __restrict__ dbih_r,   // [768] bias gradients (pre-zeroed)
+                         float* __restrict__ dbhh_f, float* __restrict__ dbhh_r, int B, int T) {
     extern __shared__ __align__(16) float gsm[];
     float* s_w = gsm;                                    // [32 units][772]
     float* s_dgh = gsm + 32 * kGbWStride;                // [2][16][768]
@@ -408,6 +409,7 @@ __global__ void __cluster_dims__(kGbCluster, 1, 1) __launch_bounds__(kGbThreads,
     const int bu = tid & 31, bq = tid >> 5;
     const uint32_t s_dgh_addr = (uint32_t)__cvta_generic_to_shared(s_dgh);
     const int64_t BT = (int64_t)B * T;
+    float sum_r[2] = {0.f, 0.f}, sum_z[2] = {0.f, 0.f}, sum_n[2] = {0.f, 0.f}, sum_hn[2] = {0.f, 0.f};
     __syncthreads();
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
@@ -447,6 +449,10 @@ __global__ void __cluster_dims__(kGbCluster, 1, 1) __launch_bounds__(kGbThreads,
                 o_n[e] = dpn;
                 o_hn[e] = dpn * r;
                 s_dh[ab * 33 + 2 * aug + e] = z * dh;
+                sum_r[e] += o_r[e];
+                sum_z[e] += o_z[e];
+                sum_n[e] += o_n[e];
+                sum_hn[e] += o_hn[e];
             }
             if (avalid) {
                 float* dgip = dgi + row * 1536 + dir * 768 + j0 + 2 * aug;
@@ -498,6 +504,36 @@ __global__ void __cluster_dims__(kGbCluster, 1, 1) __launch_bounds__(kGbThreads,
     // keep this CTA's shared memory alive until every peer has finished pushing into it
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    // bias gradients: column sums of dgi / dgh over (utterance, step); reduce the 16 utterances through shared memory
+    float* s_b = s_dgh;                                  // [4 kinds][16 utterances][32 units], free after the last barrier
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        s_b[(0 * kGbNB + ab) * 32 + 2 * aug + e] = sum_r[e];
+        s_b[(1 * kGbNB + ab) * 32 + 2 * aug + e] = sum_z[e];
+        s_b[(2 * kGbNB + ab) * 32 + 2 * aug + e] = sum_n[e];
+        s_b[(3 * kGbNB + ab) * 32 + 2 * aug + e] = sum_hn[e];
+    }
+    __syncthreads();
+    if (tid < 128) {
+        const int kind = tid >> 5, u = tid & 31;
+        float a = 0.f;
+#pragma unroll
+        for (int bb = 0; bb < kGbNB; ++bb) a += s_b[(kind * kGbNB + bb) * 32 + u];
+        float* dbih = dir == 0 ? dbih_f : dbih_r;
+        float* dbhh = dir == 0 ? dbhh_f : dbhh_r;
+        // several utterance slices add into the same element; a single slice (batch <= 16) is deterministic
+        if (kind == 0) {
+            atomicAdd(dbih + j0 + u, a);
+            atomicAdd(dbhh + j0 + u, a);
+        } else if (kind == 1) {
+            atomicAdd(dbih + 256 + j0 + u, a);
+            atomicAdd(dbhh + 256 + j0 + u, a);
+        } else if (kind == 2) {
+            atomicAdd(dbih + 512 + j0 + u, a);
+        } else {
+            atomicAdd(dbhh + 512 + j0 + u, a);
+        }
+    }
 }
 
 // C[M,N] = op(A) B + beta C on the fp32 CUDA cores; B stored [K][N]; TA: A stored [K][M], else [M][K].
@@ -552,20 +588,6 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
             *c = beta != 0.f ? acc[i][j] + beta * *c : acc[i][j];
         }
     }
-}
-
-// out[n] = sum over rows of X[rows][ld] column n (bias gradients); one thread per column, coalesced rows.
-__global__ void colsum_kernel(const float* __restrict__ X, int ld, int rows, int cols, float* __restrict__ out) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= cols) return;
-    float a0 = 0.f, a1 = 0.f;
-    int r = 0;
-    for (; r + 1 < rows; r += 2) {
-        a0 += X[(int64_t)r * ld + n];
-        a1 += X[(int64_t)(r + 1) * ld + n];
-    }
-    if (r < rows) a0 += X[(int64_t)r * ld + n];
-    out[n] = a0 + a1;
 }
 
 __global__ void dropout_bwd_kernel(float* __restrict__ d, const uint8_t* __restrict__ keep, int64_t n) {
@@ -894,6 +916,8 @@ static inline unsigned blocks_for(int64_t n, int per_block = 256, int cap = 148 
     return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+constexpr int kWgradMaxChunks = 48;     // x 9 taps = 432 CTAs, ~3 per SM; keeps the partial buffer and its reduction small
+
 static size_t carve_train(TrainSaved& t, uint8_t* base, int B, int H, int W, int gin) {
     const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, T = W / 8;
     size_t off = 0;
@@ -945,11 +969,10 @@ static size_t carve_train(TrainSaved& t, uint8_t* base, int B, int H, int W, int
     t.dz_hi = (__half*)next(n_z2 * 2);
     t.dz_lo = (__half*)next(n_z2 * 2);
     t.dact = (float*)next(n_a1 * 4);               // data gradients w.r.t. a2 / a1
-    t.wg_partial = (float*)next((size_t)320 * 9 * 128 * 64 * 4);
+    t.wg_partial = (float*)next((size_t)kWgradMaxChunks * 9 * 128 * 64 * 4);
     return off;
 }
 
-constexpr int kWgradMaxChunks = 320;
 
 template <int C, int LAYOUT>
 static int bn_stage_forward(const float* z, int B, int H, int W, double* acc, float* stats, float* params,
@@ -1026,7 +1049,9 @@ static int gru_layer_backward(sir_model* m, int layer, const float* params, cons
         dim3 grid((unsigned)(kGbCluster * ((B + kGbNB - 1) / kGbNB)), 2);
         ProfScope ps(layer == 0 ? "gru_l0_bptt" : "gru_l1_bptt", st);
         gru_layer_bwd_kernel<<<grid, kGbThreads, kGbSmemBytes, st>>>(params + m->off.whh[layer][0], params + m->off.whh[layer][1],
-                                                                     t.gi[layer], t.gh, t.y[layer], t.dy, t.dgi, t.dgh, B, T);
+                                                                     t.gi[layer], t.gh, t.y[layer], t.dy, t.dgi, t.dgh,
+                                                                     grads + m->off.bih[layer][0], grads + m->off.bih[layer][1],
+                                                                     grads + m->off.bhh[layer][0], grads + m->off.bhh[layer][1], B, T);
         SIR_CHECK_LAUNCH("gru_layer_bwd_kernel");
     }
     for (int d = 0; d < 2; ++d) {
@@ -1037,10 +1062,6 @@ static int gru_layer_backward(sir_model* m, int layer, const float* params, cons
         if ((rc = sgemm<true>(dgh_d, 768, t.hprevf + (size_t)d * BT * 256, 256, grads + m->off.whh[layer][d], 256, 768, 256, BT,
                               0.f, st)))
             return rc;
-        colsum_kernel<<<3, 256, 0, st>>>(dgi_d, 1536, BT, 768, grads + m->off.bih[layer][d]);
-        SIR_CHECK_LAUNCH("colsum_kernel");
-        colsum_kernel<<<3, 256, 0, st>>>(dgh_d, 768, BT, 768, grads + m->off.bhh[layer][d]);
-        SIR_CHECK_LAUNCH("colsum_kernel");
         // dx (+)= dgi W_ih
         if (dx && (rc = sgemm<false>(dgi_d, 1536, params + m->off.wih[layer][d], in_sz, dx, in_sz, BT, in_sz, 768,
                                      d == 0 ? 0.f : 1.f, st)))
@@ -1178,7 +1199,7 @@ extern "C" int sir_model_backward(sir_model* m, const float* d_params, const flo
                                        d_grads, st)))
         return rc;
     {
-        const int nblk = (int)((int64_t)B * H < kWgradMaxChunks ? (int64_t)B * H : kWgradMaxChunks);
+        const int nblk = (int)((int64_t)B * H < 592 ? (int64_t)B * H : 592);
         conv1_wgrad_kernel<<<nblk, 256, 0, st>>>(t.dz, t.feat, B, H, W, t.wg_partial);
         SIR_CHECK_LAUNCH("conv1_wgrad_kernel");
         wgrad_reduce_kernel<<<2, 256, 0, st>>>(t.wg_partial, nblk, 1, 32, d_grads + o.conv_w[0]);
