@@ -168,6 +168,15 @@ int sir_adam_step(float* d_params, const float* d_grads, float* d_exp_avg, float
                   int n_segments, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                   float inv_scale, const float* d_found_inf, void* stream);
 
+/* Staged forward for host-resident batches (the public entry that overlaps the H2D copy of sub-batch i+1 with
+ * the conv stack of sub-batch i): sir_model_forward_convs runs conv1..3 (+BN+ReLU+pool) for utterances
+ * [first, first + count) of a batch of batch_total utterances, d_features pointing at utterance `first`;
+ * sir_model_forward_head then runs the GRU layers, attention pooling and fc (models/models.py:60-67) over all
+ * batch_total utterances.  Together they equal sir_model_forward; batch_total <= 336 (one workspace pass). */
+int sir_model_forward_convs(sir_model* m, const float* d_features, int batch_total, int first, int count, int n_frames,
+                            void* stream);
+int sir_model_forward_head(sir_model* m, int batch_total, int n_frames, float* d_logits, void* stream);
+
 /* sir_gemm_nt_split_f16: C[M,N] = A[M,K] W[N,K]^T + bias[N] on the 5th-gen tensor cores (tcgen05, TMEM
  * accumulators, TMA-staged operands) with the 3-pass fp16 hi/lo operand split that keeps fp32-level accuracy.
  * It is the contraction behind nn.GRU's input projection (models/models.py:60) and, in implicit-GEMM form,

@@ -38,6 +38,8 @@ SIGNATURES = {
     "sir_model_load_weights": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "sir_model_weight_count": (c_int64, [c_void_p]),
     "sir_model_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "sir_model_forward_convs": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "sir_model_forward_head": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "sir_model_train_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_uint64, c_uint64, c_float,
                                         c_float, c_void_p, c_void_p]),
     "sir_model_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -234,6 +236,23 @@ class Model:
         B, M, T = feat.shape
         logits = torch.empty((B, self.num_classes), device=feat.device, dtype=torch.float32)
         check(load_library().sir_model_forward(self._h, ptr(feat), B, T, ptr(logits), stream_ptr()), "sir_model_forward")
+        return logits
+
+    MAX_STAGED_BATCH = 336
+
+    def forward_convs(self, feat_chunk: torch.Tensor, batch_total: int, first: int):
+        """conv stack for utterances ``[first, first + len(feat_chunk))`` of a ``batch_total`` batch (staged forward)."""
+        require_cuda(feat_chunk, "features")
+        assert feat_chunk.is_contiguous()
+        n, M, T = feat_chunk.shape
+        check(load_library().sir_model_forward_convs(self._h, ptr(feat_chunk), batch_total, first, n, T, stream_ptr()),
+              "sir_model_forward_convs")
+
+    def forward_head(self, batch_total: int, n_frames: int, logits: torch.Tensor = None) -> torch.Tensor:
+        if logits is None:
+            logits = torch.empty((batch_total, self.num_classes), device="cuda", dtype=torch.float32)
+        check(load_library().sir_model_forward_head(self._h, batch_total, n_frames, ptr(logits), stream_ptr()),
+              "sir_model_forward_head")
         return logits
 
     # -- training step pieces (flat fp32 parameter / gradient buffers owned by the caller) ---------------------

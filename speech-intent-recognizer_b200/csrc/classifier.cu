@@ -458,24 +458,31 @@ static size_t carve(Workspace& w, uint8_t* base, int B, int H, int W, int gin) {
     return off;
 }
 
-int model_forward_chunk(sir_model* m, const Workspace& ws, const float* feat, int B, int W, float* logits,
-                        cudaStream_t st) {
+// conv stack for utterances [first, first + count) of a workspace carved for a larger batch: the host entry
+// that overlaps the H2D copy of the next sub-batch with the conv stack of the previous one uses this directly.
+int model_forward_convs(sir_model* m, const Workspace& ws, const float* feat, int first, int count, int W, cudaStream_t st) {
     const int H = m->n_mels;
     const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2, Tg = W4 / 2;
+    const size_t o1 = (size_t)first * H2 * W2 * 32, o2 = (size_t)first * H4 * W4 * 64, o3 = (size_t)first * Tg * m->gru_in;
     int rc;
     {
-        dim3 grid((unsigned)((H2 * W2 + 127) / 128), (unsigned)B);
+        dim3 grid((unsigned)((H2 * W2 + 127) / 128), (unsigned)count);
         ProfScope ps("conv1_bn_relu_pool", st);
-        conv1_bn_relu_pool_kernel<<<grid, 128, 0, st>>>(feat, m->w1, m->sh1, ws.act1_hi, ws.act1_lo, H, W);
+        conv1_bn_relu_pool_kernel<<<grid, 128, 0, st>>>(feat, m->w1, m->sh1, ws.act1_hi + o1, ws.act1_lo + o1, H, W);
         SIR_CHECK_LAUNCH("conv1_bn_relu_pool_kernel");
     }
-    if ((rc = tc::tc_conv3x3<32, 64>(ws.act1_hi, ws.act1_lo, m->w2_hi, m->w2_lo, m->sh2, ws.act2_hi, ws.act2_lo, nullptr, B,
-                                     H2, W2, 0, st, "conv2_bn_relu_pool")))
+    if ((rc = tc::tc_conv3x3<32, 64>(ws.act1_hi + o1, ws.act1_lo + o1, m->w2_hi, m->w2_lo, m->sh2, ws.act2_hi + o2,
+                                     ws.act2_lo + o2, nullptr, count, H2, W2, 0, st, "conv2_bn_relu_pool")))
         return rc;
     // conv3 writes [B][T/8][H/8][128]: the GRU input, time-major with channels-last features
-    if ((rc = tc::tc_conv3x3<64, 128>(ws.act2_hi, ws.act2_lo, m->w3_hi, m->w3_lo, m->sh3, ws.gin_hi, ws.gin_lo, nullptr, B,
-                                      H4, W4, 1, st, "conv3_bn_relu_pool")))
-        return rc;
+    return tc::tc_conv3x3<64, 128>(ws.act2_hi + o2, ws.act2_lo + o2, m->w3_hi, m->w3_lo, m->sh3, ws.gin_hi + o3, ws.gin_lo + o3,
+                                   nullptr, count, H4, W4, 1, st, "conv3_bn_relu_pool");
+}
+
+// 2-layer bidirectional GRU + attention pooling + fc over the B utterances whose GRU input is in the workspace.
+int model_forward_head(sir_model* m, const Workspace& ws, int B, int W, float* logits, cudaStream_t st) {
+    const int Tg = W / 8;
+    int rc;
     const __half *x_hi = ws.gin_hi, *x_lo = ws.gin_lo;
     int in_sz = m->gru_in;
     float* ys[2] = {ws.y0, ws.y1};
@@ -494,13 +501,19 @@ int model_forward_chunk(sir_model* m, const Workspace& ws, const float* feat, in
         x_lo = ws.y0_lo;
         in_sz = 512;
     }
-    if ((rc = launch_attention_fc(m, ws.y1, logits, B, Tg, st))) return rc;
-    return SIR_OK;
+    return launch_attention_fc(m, ws.y1, logits, B, Tg, st);
+}
+
+int model_forward_chunk(sir_model* m, const Workspace& ws, const float* feat, int B, int W, float* logits,
+                        cudaStream_t st) {
+    int rc = model_forward_convs(m, ws, feat, 0, B, W, st);
+    if (rc != SIR_OK) return rc;
+    return model_forward_head(m, ws, B, W, logits, st);
 }
 
 }  // namespace sir
 
-static int model_prepare(sir_model* m, int batch, int n_frames, Workspace& ws, int& chunk) {
+static int model_prepare(sir_model* m, int batch, int n_frames, Workspace& ws, int& chunk) {   // (re)carves the workspace
     if (!m->loaded) return fail(SIR_ERR_INVALID, "sir_model_forward: weights not loaded");
     if (n_frames < 8) return fail(SIR_ERR_INVALID, "sir_model_forward: n_frames must be >= 8 (got %d)", n_frames);
     chunk = batch < kModelChunk ? batch : kModelChunk;
@@ -528,6 +541,35 @@ extern "C" int sir_model_forward(sir_model* m, const float* d_features, int batc
         if (rc != SIR_OK) return rc;
     }
     return SIR_OK;
+}
+
+extern "C" int sir_model_forward_convs(sir_model* m, const float* d_features, int batch_total, int first, int count,
+                                       int n_frames, void* stream) {
+    if (!m || !d_features) return fail(SIR_ERR_INVALID, "sir_model_forward_convs: NULL argument");
+    if (batch_total < 1 || batch_total > kModelChunk)
+        return fail(SIR_ERR_UNSUPPORTED, "sir_model_forward_convs: batch_total must be in [1, %d] (got %d)", kModelChunk,
+                    batch_total);
+    if (first < 0 || count < 0 || first + count > batch_total)
+        return fail(SIR_ERR_INVALID, "sir_model_forward_convs: [%d, %d) is not inside the batch of %d", first, first + count,
+                    batch_total);
+    if (count == 0) return SIR_OK;
+    Workspace ws;
+    int chunk = 0;
+    int rc = model_prepare(m, batch_total, n_frames, ws, chunk);
+    if (rc != SIR_OK) return rc;
+    return model_forward_convs(m, ws, d_features, first, count, n_frames, (cudaStream_t)stream);
+}
+
+extern "C" int sir_model_forward_head(sir_model* m, int batch_total, int n_frames, float* d_logits, void* stream) {
+    if (!m || !d_logits) return fail(SIR_ERR_INVALID, "sir_model_forward_head: NULL argument");
+    if (batch_total < 1 || batch_total > kModelChunk)
+        return fail(SIR_ERR_UNSUPPORTED, "sir_model_forward_head: batch_total must be in [1, %d] (got %d)", kModelChunk,
+                    batch_total);
+    Workspace ws;
+    int chunk = 0;
+    int rc = model_prepare(m, batch_total, n_frames, ws, chunk);
+    if (rc != SIR_OK) return rc;
+    return model_forward_head(m, ws, batch_total, n_frames, d_logits, (cudaStream_t)stream);
 }
 
 extern "C" int sir_pipeline_forward(sir_frontend* fe, sir_model* m, const float* d_wave, int64_t wave_stride,

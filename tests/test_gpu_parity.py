@@ -182,3 +182,22 @@ def test_full_size_properties(fe, model):
     # gain invariance: log-mel of a*x is a dB shift, removed by the normalisation
     f2 = fe.forward(w[:8] * 0.25, out_frames=200)
     assert rel_to_scale(f2.cpu().numpy(), feats[:8].cpu().numpy()) < FEATURE_REL_TOL
+
+
+def test_host_pipeline_equals_device_path():
+    """IntentPipeline.infer_host (H2D overlapped with frontend + conv stack, staged forward) == the plain path."""
+    pre = importlib.import_module("speech-intent-recognizer_b200.scripts.precompute_features")
+    models = importlib.import_module("speech-intent-recognizer_b200.models.models")
+    pipeline = importlib.import_module("speech-intent-recognizer_b200.pipeline")
+    ex = pre.AudioFeatureExtractor()
+    m = models.CNNAudioGRU(31)
+    sd = synth.make_weights(1234)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    m = m.cuda().eval()
+    for B, subs in ((37, 4), (256, 4), (5, 8), (400, 4)):
+        w = torch.from_numpy(synth.white_noise(B, B, 16000) * np.linspace(0.05, 1, B, dtype=np.float32)[:, None]).pin_memory()
+        want = m(ex.extract_batch(w.cuda(), out_frames=200)).cpu()
+        got = pipeline.IntentPipeline(ex, m, sub_batches=subs).infer_host(w)
+        assert got.is_pinned() and torch.equal(got, want), (B, float((got - want).abs().max()))
+    with pytest.raises(native.NativeError):
+        pipeline.IntentPipeline(ex, m).infer_host(w.cuda())
