@@ -201,3 +201,8 @@ def test_host_pipeline_equals_device_path():
         assert got.is_pinned() and torch.equal(got, want), (B, float((got - want).abs().max()))
     with pytest.raises(native.NativeError):
         pipeline.IntentPipeline(ex, m).infer_host(w.cuda())
+    # streaming: several batches in flight on rotating slots, results in order
+    batches = [torch.from_numpy(synth.white_noise(50 + i, 24, 16000)).pin_memory() for i in range(5)]
+    pipe = pipeline.IntentPipeline(ex, m, sub_batches=3, depth=2)
+    for i, got in enumerate(pipe.infer_stream(batches)):
+        assert torch.equal(got, m(ex.extract_batch(batches[i].cuda(), out_frames=200)).cpu()), i
