@@ -322,6 +322,7 @@ extern "C" int sir_model_create(sir_model** out, int num_classes, int n_mels) {
     m->n_mels = n_mels;
     m->gru_in = 128 * (n_mels / 8);
     m->off = make_offsets(num_classes, n_mels);
+    if (cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || m->num_sms < 1) m->num_sms = 148;
     // carve the repacked-weight buffers (sizes depend on the architecture only)
     const int gin = m->gru_in, C = num_classes;
     size_t nf = 0, nh = 0;
@@ -471,8 +472,8 @@ int model_forward_convs(sir_model* m, const Workspace& ws, const float* feat, in
         conv1_bn_relu_pool_kernel<<<grid, 128, 0, st>>>(feat, m->w1, m->sh1, ws.act1_hi + o1, ws.act1_lo + o1, H, W);
         SIR_CHECK_LAUNCH("conv1_bn_relu_pool_kernel");
     }
-    if ((rc = tc::tc_conv3x3<32, 64>(ws.act1_hi + o1, ws.act1_lo + o1, m->w2_hi, m->w2_lo, m->sh2, ws.act2_hi + o2,
-                                     ws.act2_lo + o2, nullptr, count, H2, W2, 0, st, "conv2_bn_relu_pool")))
+    if ((rc = tc::tc_conv3x3_persistent<32, 64>(ws.act1_hi + o1, ws.act1_lo + o1, m->w2_hi, m->w2_lo, m->sh2, ws.act2_hi + o2,
+                                                ws.act2_lo + o2, count, H2, W2, m->num_sms, st, "conv2_bn_relu_pool")))
         return rc;
     // conv3 writes [B][T/8][H/8][128]: the GRU input, time-major with channels-last features
     return tc::tc_conv3x3<64, 128>(ws.act2_hi + o2, ws.act2_lo + o2, m->w3_hi, m->w3_lo, m->sh3, ws.gin_hi + o3, ws.gin_lo + o3,

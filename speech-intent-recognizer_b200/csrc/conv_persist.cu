@@ -1,0 +1,230 @@
+// Persistent implicit-GEMM 3x3 convolution + BN shift + ReLU + 2x2 max-pool for the layers whose weights fit in
+// shared memory next to the activation ring (conv2: 32 -> 64 channels, 72 KB of fp16 hi/lo weights).
+//
+// Replaces models/models.py:51 (conv2 + bn2 + relu + pool) of the reference in eval mode; same arithmetic as
+// tc_contract_kernel<CONV> in gemm_tc.cu (3-pass fp16 hi/lo split, fp32 accumulation in TMEM), different schedule:
+//
+//   * one CTA per SM walks over output tiles (16 x 8 pixels = 128 UMMA rows) round-robin;
+//   * the nine weight taps are loaded ONCE per CTA and stay resident in shared memory;
+//   * per tile only THREE activation loads are issued, one per horizontal tap offset kw: the TMA box
+//     (C, 16, 10, 1) carries the vertical halo, and the three vertical taps read it through UMMA descriptors
+//     advanced by 16 rows (row = y * 16 + x, so a vertical shift is a 1024-byte offset - swizzle-atom aligned);
+//     L2 -> SM traffic per tile drops from 9 x (A + B) tiles to 3 x 1.25 A tiles (measured on the non-persistent
+//     kernel: 1.6 GB per launch at batch 256, L2-bandwidth bound);
+//   * two TMEM accumulators: the epilogue of tile i (pool by warp shuffles, shift, ReLU, fp16 split, channels-last
+//     store) overlaps the MMAs of tile i+1.
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM lane
+// quadrant = warp % 4).  Every mbarrier wait is bounded (tc_common.cuh) - a protocol bug traps instead of hanging.
+#include "sir_common.cuh"
+#include "tc_common.cuh"
+
+namespace sir {
+namespace tc {
+
+int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint32_t* box);
+
+constexpr int kCpThreads = 192;
+
+template <int CIN, int COUT, int STAGES>
+struct CpLayout {
+    static constexpr int kRowBytes = CIN * 2;                       // one pixel's channels = one swizzle row (64 B)
+    static constexpr int kTapBytes = COUT * kRowBytes;              // one weight tap, one of (hi, lo)
+    static constexpr int kWBytes = 9 * 2 * kTapBytes;               // all taps, hi + lo
+    static constexpr int kABytes = 160 * kRowBytes;                 // 16 x 10 pixel halo box, one of (hi, lo)
+    static constexpr int kStageBytes = 2 * kABytes;
+    static constexpr int kOffA = kWBytes;
+    static constexpr int kOffBar = kOffA + STAGES * kStageBytes;
+    static constexpr int kSmemBytes = kOffBar + (2 * STAGES + 5) * 8 + 16 + 1024;
+    static_assert(kTapBytes % 1024 == 0 && kABytes % 1024 == 0, "operand tiles keep 1024-byte alignment");
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+struct CpParams {
+    int B, H, W, tiles_x, tiles_y, num_tiles;
+    const float* shift;
+    __half* out_hi;
+    __half* out_lo;
+};
+
+template <int CIN, int COUT, int STAGES>
+__global__ void __launch_bounds__(kCpThreads, 1)
+    conv3x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                              const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                              const CpParams p) {
+    using L = CpLayout<CIN, COUT, STAGES>;
+    constexpr int kSwizzle = L::kRowBytes;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+    uint64_t* empty = full + STAGES;
+    uint64_t* w_full = empty + STAGES;
+    uint64_t* acc_full = w_full + 1;       // [2]
+    uint64_t* acc_empty = acc_full + 2;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_a_hi);
+        prefetch_tmap(&tm_a_lo);
+        prefetch_tmap(&tm_w_hi);
+        prefetch_tmap(&tm_w_lo);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(w_full, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 4);           // one arrival per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<2 * COUT>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // resident weights: tap t at smem + t * 2 * kTapBytes (hi), + kTapBytes (lo)
+            mbar_arrive_expect_tx(w_full, L::kWBytes);
+            for (int t = 0; t < 9; ++t) {
+                tma_load_2d(smem + t * 2 * L::kTapBytes, &tm_w_hi, w_full, 0, t * COUT);
+                tma_load_2d(smem + t * 2 * L::kTapBytes + L::kTapBytes, &tm_w_lo, w_full, 0, t * COUT);
+            }
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+                const int y0 = (r / p.tiles_x) * 8, x0 = (r % p.tiles_x) * 16;
+                for (int kw = 0; kw < 3; ++kw, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((it / STAGES) & 1u) ^ 1u);
+                    uint8_t* st = smem + L::kOffA + s * L::kStageBytes;
+                    mbar_arrive_expect_tx(&full[s], L::kStageBytes);
+                    tma_load_4d(st, &tm_a_hi, &full[s], 0, x0 + kw - 1, y0 - 1, img);
+                    tma_load_4d(st + L::kABytes, &tm_a_lo, &full[s], 0, x0 + kw - 1, y0 - 1, img);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // all 32 lanes walk the loop (uniform control flow and operands); one elected lane issues
+        constexpr uint32_t idesc = make_idesc_f16(128, COUT);
+        mbar_wait(w_full, 0);
+        tc_fence_after();
+        const uint32_t sbase = smem_u32(smem);
+        uint32_t it = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t acc = lt & 1u;
+            mbar_wait(&acc_empty[acc], ((lt >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * COUT;
+            for (int kw = 0; kw < 3; ++kw, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&full[s], (it / STAGES) & 1u);
+                tc_fence_after();
+                const uint32_t a_base = sbase + L::kOffA + s * L::kStageBytes;
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const uint32_t a_off = kh * 16 * L::kRowBytes;      // vertical tap = 16 rows further down the halo box
+                        const uint64_t a_hi = make_kmajor_desc<kSwizzle>(a_base + a_off);
+                        const uint64_t a_lo = make_kmajor_desc<kSwizzle>(a_base + L::kABytes + a_off);
+                        const uint32_t w_base = sbase + (kh * 3 + kw) * 2 * L::kTapBytes;
+                        const uint64_t b_hi = make_kmajor_desc<kSwizzle>(w_base);
+                        const uint64_t b_lo = make_kmajor_desc<kSwizzle>(w_base + L::kTapBytes);
+#pragma unroll
+                        for (int k = 0; k < CIN; k += 16) {
+                            umma_f16(d_tmem, desc_advance_k(a_hi, k), desc_advance_k(b_hi, k), idesc, (kw | kh | k) ? 1u : 0u);
+                            umma_f16(d_tmem, desc_advance_k(a_hi, k), desc_advance_k(b_lo, k), idesc, 1u);
+                            umma_f16(d_tmem, desc_advance_k(a_lo, k), desc_advance_k(b_hi, k), idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                    if (kw == 2) umma_commit(&acc_full[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---- epilogue warps: TMEM lane quadrant q; rows of the quadrant = pixel rows 2q, 2q+1 of the tile ----------
+        const int q = warp & 3;
+        const int H2 = p.H / 2, W2 = p.W / 2;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t acc = lt & 1u;
+            const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+            const int y0 = (r / p.tiles_x) * 8, x0 = (r % p.tiles_x) * 16;
+            mbar_wait(&acc_full[acc], (lt >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + acc * COUT + ((uint32_t)(q * 32) << 16);
+            const int y2 = y0 / 2 + q, x2 = x0 / 2 + ((lane & 15) >> 1);
+            const bool inside = y2 < H2 && x2 < W2;
+            const int64_t pix = ((int64_t)img * H2 + y2) * W2 + x2;
+#pragma unroll 1
+            for (int c = 0; c < COUT; c += 32) {
+                float v[32], o[8];
+                tmem_ld_32x32(trow + c, v);
+                const int ch = c + pool2x2_split_channels(v, lane, o);
+                if (inside) shift_relu_split_store8(o, p.shift + ch, p.out_hi + pix * COUT + ch, p.out_lo + pix * COUT + ch);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);             // this warp's quadrant of the accumulator is free
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<2 * COUT>(tmem_base);
+    }
+}
+
+// conv (3x3, s1, p1) + shift + ReLU + 2x2 max-pool, channels-last fp16 hi/lo in and out; weights [9][COUT][CIN].
+template <int CIN, int COUT>
+int tc_conv3x3_persistent(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
+                          __half* out_hi, __half* out_lo, int B, int H, int W, int num_sms, cudaStream_t st, const char* name) {
+    constexpr int STAGES = 6;
+    using L = CpLayout<CIN, COUT, STAGES>;
+    CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+    const uint64_t adims[4] = {(uint64_t)CIN, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint32_t abox[4] = {(uint32_t)CIN, 16, 10, 1};
+    const uint64_t wdims[2] = {(uint64_t)CIN, (uint64_t)(9 * COUT)};
+    const uint32_t wbox[2] = {(uint32_t)CIN, (uint32_t)COUT};
+    int rc;
+    if ((rc = make_tmap(&ta_hi, in_hi, 4, adims, abox)) || (rc = make_tmap(&ta_lo, in_lo, 4, adims, abox)) ||
+        (rc = make_tmap(&tw_hi, w_hi, 2, wdims, wbox)) || (rc = make_tmap(&tw_lo, w_lo, 2, wdims, wbox)))
+        return rc;
+    CpParams p{};
+    p.B = B;
+    p.H = H;
+    p.W = W;
+    p.tiles_x = (W + 15) / 16;
+    p.tiles_y = (H + 7) / 8;
+    p.num_tiles = B * p.tiles_x * p.tiles_y;
+    p.shift = shift;
+    p.out_hi = out_hi;
+    p.out_lo = out_lo;
+    auto kern = conv3x3_persistent_kernel<CIN, COUT, STAGES>;
+    static bool attr = false;
+    if (!attr) {
+        SIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes));
+        attr = true;
+    }
+    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    {
+        ProfScope ps(name, st);
+        kern<<<grid, kCpThreads, L::kSmemBytes, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
+    }
+    SIR_CHECK_LAUNCH(name);
+    return SIR_OK;
+}
+
+template int tc_conv3x3_persistent<32, 64>(const __half*, const __half*, const __half*, const __half*, const float*, __half*,
+                                           __half*, int, int, int, int, cudaStream_t, const char*);
+
+}  // namespace tc
+}  // namespace sir

@@ -192,37 +192,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             // rows of this warp: dy = 2q + (lane >> 4), x = lane & 15  ->  one 2 x 16 pixel patch
             const int H2 = p.H / 2, W2 = p.W / 2;
             const int y2 = y0 / 2 + q, x2 = x0 / 2 + ((lane & 15) >> 1);
-            const bool writer = ((lane & 17) == 0) && y2 < H2 && x2 < W2;
+            const bool inside = y2 < H2 && x2 < W2;
             const int64_t pix = p.out_whc ? ((int64_t)img * W2 + x2) * H2 + y2 : ((int64_t)img * H2 + y2) * W2 + x2;
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N; c += 32) {
-                float v[32];
+                float v[32], o[8];
                 tmem_ld_32x32(trow + c, v);
-                uint32_t hi2[16], lo2[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float a = v[i], b = v[i + 1];
-                    a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
-                    b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, 1));
-                    a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 16));
-                    b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, 16));
-                    a = fmaxf(a + __ldg(p.shift + c + i), 0.f);
-                    b = fmaxf(b + __ldg(p.shift + c + i + 1), 0.f);
-                    __half ah, al, bh, bl;
-                    split_f16(a, ah, al);
-                    split_f16(b, bh, bl);
-                    hi2[i >> 1] = (uint32_t)__half_as_ushort(ah) | ((uint32_t)__half_as_ushort(bh) << 16);
-                    lo2[i >> 1] = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
-                }
-                if (writer) {
-                    uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * BLOCK_N + c);
-                    uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * BLOCK_N + c);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        dh[i] = make_uint4(hi2[4 * i], hi2[4 * i + 1], hi2[4 * i + 2], hi2[4 * i + 3]);
-                        dl[i] = make_uint4(lo2[4 * i], lo2[4 * i + 1], lo2[4 * i + 2], lo2[4 * i + 3]);
-                    }
-                }
+                const int ch = c + pool2x2_split_channels(v, lane, o);
+                if (inside)
+                    shift_relu_split_store8(o, p.shift + ch, p.out_hi + pix * BLOCK_N + ch, p.out_lo + pix * BLOCK_N + ch);
             }
         }
     }

@@ -20,6 +20,22 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- warp-uniform role dispatch ------------------------------------------------------------------------------
+// tcgen05.mma / commit and TMA take warp-uniform operands.  Inside `if (lane == 0)` the compiler cannot prove
+// uniformity and wraps every issue in an R2UR + vote "waterfall" loop (~10 SASS instructions per MMA, measured to
+// bound the issue rate of the single MMA thread).  Making the warp index provably uniform (shuffle from lane 0) and
+// electing the issuing lane with elect.sync right at the issue site keeps descriptors in uniform registers.
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -146,6 +162,51 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
     x = fminf(fmaxf(x, -65504.f), 65504.f);      // fp16 range; activations and weights of this model are O(1..100)
     hi = __float2half_rn(x);
     lo = __float2half_rn(x - __half2float(hi));
+}
+
+// ---- pooled conv epilogue -----------------------------------------------------------------------------------
+// One warp holds a 2 x 16 pixel patch of a conv tile (lane = (dy << 4) | x) and, per lane, 32 consecutive output
+// channels v[0..32) of its pixel.  2x2 max-pool partners are lanes ^1 (x) and ^16 (y).  Instead of reducing all
+// 32 channels in all four lanes, the lanes of a pooling group split the channels while they reduce: after the x
+// step each lane owns 16 channels, after the y step 8 - 24 shuffles per lane instead of 64, and every lane ends
+// with 8 DISTINCT pooled channels: + shift, ReLU, fp16 hi/lo split, one 16-byte store each to hi and lo.
+// Returns the first channel (relative to the chunk) this lane owns.
+__device__ __forceinline__ int pool2x2_split_channels(const float (&v)[32], int lane, float (&out)[8]) {
+    const bool sx = lane & 1, sy = (lane >> 4) & 1;
+    float m[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float keep = sx ? v[i + 16] : v[i];
+        const float send = sx ? v[i] : v[i + 16];
+        m[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float keep = sy ? m[j + 8] : m[j];
+        const float send = sy ? m[j] : m[j + 8];
+        out[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+    }
+    return (sx ? 16 : 0) + (sy ? 8 : 0);
+}
+
+// out[j] + shift[j] -> ReLU -> fp16 (hi, lo) -> dst_hi[0..8), dst_lo[0..8)  (16-byte aligned destinations)
+__device__ __forceinline__ void shift_relu_split_store8(const float (&o)[8], const float* __restrict__ shift8,
+                                                        __half* __restrict__ dst_hi, __half* __restrict__ dst_lo) {
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift8));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(shift8) + 1);
+    const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    uint32_t hi2[4], lo2[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        const float a = fminf(fmaxf(o[j] + sh[j], 0.f), 65504.f), b = fminf(fmaxf(o[j + 1] + sh[j + 1], 0.f), 65504.f);
+        const __half2 h = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+        hi2[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+        lo2[j >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    *reinterpret_cast<uint4*>(dst_hi) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
+    *reinterpret_cast<uint4*>(dst_lo) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
 }
 
 }  // namespace tc
