@@ -46,6 +46,17 @@ FLOPS_PER_UTT = {  # SURVEY.md 8 a11 (2 flops per MAC)
     "gru_l1_recurrence": 19.66e6, "attention_fc": 0.06e6,
 }
 FRONTEND_BYTES_PER_UTT = 4 * SAMPLES + 4 * N_MELS * OUT_FRAMES      # reads the waveform once, writes [64,200] once
+# conv2 / conv3 / the GRU projections run as 3-pass fp16 hi/lo splits: the tensor pipe executes 3x these FLOPs.
+SPLIT_PASSES = {"conv2_bn_relu_pool": 3, "conv3_bn_relu_pool": 3, "gru_l0_input_gemm": 3, "gru_l1_input_gemm": 3,
+                "gru_l0_recurrence": 3, "gru_l1_recurrence": 3}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of THIS workload
+# (256 utterances; profiles/r1_summary.md names the capture of each row).  None: not captured for this build.
+NCU_TRAFFIC_B256 = {
+    "logmel_frontend_kernel": 53.18e6 + 0.58e6, "conv1_bn_relu_pool": 22.68e6 + 59.04e6,
+    "conv2_bn_relu_pool": 104.96e6 + 26.63e6, "conv3_bn_relu_pool": 52.74e6 + 1.94e6,
+    "gru_l0_input_gemm": 32.54e6 + 1.39e6, "gru_l1_input_gemm": 16.29e6 + 0.94e6,
+    "gru_l0_recurrence": 40.94e6 + 0.81e6, "gru_l1_recurrence": 40.93e6 + 0.03e6,
+}
 
 
 def measured_peaks():
@@ -339,22 +350,38 @@ def main():
             if name in FLOPS_PER_UTT:
                 entry["tflops"] = round(FLOPS_PER_UTT[name] * B / (per_step * 1e-3) / 1e12, 3)
             stage_out[name] = entry
-        model_stages = {k: v for k, v in stage_out.items() if k in FLOPS_PER_UTT}
-        dom = max(model_stages, key=lambda k: model_stages[k]["ms_per_step"]) if model_stages else None
-        roofline = None
-        if dom:
-            ach = model_stages[dom]["tflops"]
-            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                        "frac": round(ach / peaks["tflops"], 5), "traffic": None, "peak_source": peaks["source"],
-                        "share_of_step": round(model_stages[dom]["ms_per_step"] /
-                                               sum(v["ms_per_step"] for v in stage_out.values()), 4)}
-        fr = None
-        if "logmel_frontend_kernel" in stage_out:
-            ms = stage_out["logmel_frontend_kernel"]["ms_per_step"]
-            gbs = FRONTEND_BYTES_PER_UTT * B / (ms * 1e-3) / 1e9
-            fr = {"kernel": "logmel_frontend_kernel", "bound": "hbm", "achieved": round(gbs, 2), "peak": peaks["hbm_gbs"],
-                  "unit": "GB/s", "frac": round(gbs / peaks["hbm_gbs"], 5), "traffic": None,
-                  "bytes_per_utt": FRONTEND_BYTES_PER_UTT, "peak_source": peaks["source"]}
+        step_ms = sum(v["ms_per_step"] for v in stage_out.values())
+
+        def stage_roofline(name):
+            """roofline object of one stage: algorithmic FLOPs or bytes / event-timed duration vs the measured peak."""
+            v = stage_out[name]
+            traffic = NCU_TRAFFIC_B256.get(name) if B == BATCH_PER_GPU else None
+            base = {"kernel": name, "ms": v["ms_per_step"], "share_of_step": round(v["ms_per_step"] / step_ms, 4),
+                    "traffic": traffic, "peak_source": peaks["source"]}
+            if name == "logmel_frontend_kernel":
+                gbs = FRONTEND_BYTES_PER_UTT * B / (v["ms_per_step"] * 1e-3) / 1e9
+                return {**base, "bound": "hbm", "achieved": round(gbs, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": round(gbs / peaks["hbm_gbs"], 5), "bytes_per_utt": FRONTEND_BYTES_PER_UTT,
+                        "note": "fp32-issue bound: ~1,400 fp32 instructions per lane per frame (DESIGN.md section 4)"}
+            if name == "conv1_bn_relu_pool":
+                nbytes = (4 * N_MELS * OUT_FRAMES + 4 * 32 * (N_MELS // 2) * (OUT_FRAMES // 2)) * B
+                gbs = nbytes / (v["ms_per_step"] * 1e-3) / 1e9
+                return {**base, "bound": "hbm", "achieved": round(gbs, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": round(gbs / peaks["hbm_gbs"], 5)}
+            ach = v.get("tflops", 0.0)
+            out = {**base, "bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                   "frac": round(ach / peaks["tflops"], 5)}
+            if name in SPLIT_PASSES:
+                out["tensor_pipe_flops_factor"] = SPLIT_PASSES[name]
+                out["note"] = ("fp32-accurate 3-pass fp16 hi/lo split: the tensor pipe executes 3x the algorithmic FLOPs "
+                               f"({round(3 * ach, 1)} TFLOP/s of fp16 MMA work)")
+            if "recurrence" in name:
+                out["note"] = "latency chain of 25 dependent time steps (one launch per layer); " + out.get("note", "")
+            return out
+
+        rooflines = [stage_roofline(k) for k in stage_out]
+        roofline = max(rooflines, key=lambda r: r["ms"]) if rooflines else None
+        fr = next((r for r in rooflines if r["kernel"] == "logmel_frontend_kernel"), None)
         line = {
             "metric": "utterances/sec (features+forward)", "value": value, "unit": "utt/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -370,7 +397,7 @@ def main():
                            f"in flight, {args.sub_batches} sub-batches per batch: H2D overlapped with frontend + conv "
                            f"stack and with the previous batch's GRU/head; max |logit diff| vs the device-resident "
                            f"path {e2e_check:.1e}"},
-            "roofline": roofline, "frontend_roofline": fr, "stages": stage_out,
+            "roofline": roofline, "frontend_roofline": fr, "rooflines": rooflines, "stages": stage_out,
         }
         if not args.no_cpu_baseline:
             arm = CpuArm(native_synth, B)

@@ -87,28 +87,38 @@ __global__ void __launch_bounds__(128) conv1_bn_relu_pool_kernel(const float* __
 // ---------------------------------------------------------------------------------------------------------
 // attention-softmax pooling over time + classifier head; one CTA per utterance.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) attention_fc_kernel(const float* __restrict__ y,      // [B, T, 512]
+__global__ void __launch_bounds__(256) attention_fc_kernel(const float* __restrict__ y,      // [B, T, 512]
                                                            const float* __restrict__ att_w,  // [512]
                                                            const float* __restrict__ att_b_ptr,
                                                            const float* __restrict__ fc_w,  // [C][512]
                                                            const float* __restrict__ fc_b, float* __restrict__ logits,
                                                            int T, int C) {
-    extern __shared__ float sm[];
-    float* score = sm;            // [T]
-    float* ctx = sm + T;          // [512]
-    __shared__ float s_red[2];
+    extern __shared__ __align__(16) float sm[];
+    float* ctx = sm;              // [512]
+    float* score = sm + 512;      // [T] scores, then softmax weights
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float att_b = __ldg(att_b_ptr);
-    const float* __restrict__ yb = y + (int64_t)b * T * 512;
-    for (int t = warp; t < T; t += 4) {
+    const float4* __restrict__ yb4 = reinterpret_cast<const float4*>(y + (int64_t)b * T * 512);
+    const float4* __restrict__ aw4 = reinterpret_cast<const float4*>(att_w);
+    float4 aw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) aw[j] = __ldg(aw4 + lane + 32 * j);
+    for (int t = warp; t < T; t += 8) {
         float s = 0.f;
-        for (int k = lane; k < 512; k += 32) s = fmaf(yb[(int64_t)t * 512 + k], __ldg(att_w + k), s);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 v = yb4[t * 128 + lane + 32 * j];
+            s = fmaf(v.x, aw[j].x, s);
+            s = fmaf(v.y, aw[j].y, s);
+            s = fmaf(v.z, aw[j].z, s);
+            s = fmaf(v.w, aw[j].w, s);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) score[t] = s + att_b;
     }
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 0) {                                        // softmax over time (models/models.py:63)
         float mx = -INFINITY;
         for (int t = lane; t < T; t += 32) mx = fmaxf(mx, score[t]);
 #pragma unroll
@@ -117,22 +127,34 @@ __global__ void __launch_bounds__(128) attention_fc_kernel(const float* __restri
         for (int t = lane; t < T; t += 32) sum += expf(score[t] - mx);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) {
-            s_red[0] = mx;
-            s_red[1] = 1.f / sum;
+        const float inv = 1.f / sum;
+        for (int t = lane; t < T; t += 32) score[t] = expf(score[t] - mx) * inv;
+    }
+    __syncthreads();
+    {                                                       // context = sum_t w_t y_t: 2 features per thread
+        const float2* __restrict__ yb2 = reinterpret_cast<const float2*>(yb4);
+        float2 c = make_float2(0.f, 0.f);
+        for (int t = 0; t < T; ++t) {
+            const float2 v = yb2[t * 256 + tid];
+            const float w = score[t];
+            c.x = fmaf(v.x, w, c.x);
+            c.y = fmaf(v.y, w, c.y);
         }
+        reinterpret_cast<float2*>(ctx)[tid] = c;
     }
     __syncthreads();
-    const float mx = s_red[0], inv = s_red[1];
-    for (int k = tid; k < 512; k += 128) {
-        float c = 0.f;
-        for (int t = 0; t < T; ++t) c = fmaf(yb[(int64_t)t * 512 + k], expf(score[t] - mx) * inv, c);
-        ctx[k] = c;
-    }
-    __syncthreads();
-    for (int c = warp; c < C; c += 4) {
+    const float4* __restrict__ ctx4 = reinterpret_cast<const float4*>(ctx);
+    for (int c = warp; c < C; c += 8) {
+        const float4* __restrict__ w4 = reinterpret_cast<const float4*>(fc_w + (int64_t)c * 512);
         float s = 0.f;
-        for (int k = lane; k < 512; k += 32) s = fmaf(ctx[k], __ldg(fc_w + (int64_t)c * 512 + k), s);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 v = ctx4[lane + 32 * j], w = __ldg(w4 + lane + 32 * j);
+            s = fmaf(v.x, w.x, s);
+            s = fmaf(v.y, w.y, s);
+            s = fmaf(v.z, w.z, s);
+            s = fmaf(v.w, w.w, s);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) logits[(int64_t)b * C + c] = s + __ldg(fc_b + c);
@@ -298,7 +320,7 @@ int model_repack(sir_model* m, const float* d_flat, bool fold_bn, float bn_eps, 
 int launch_attention_fc(const sir_model* m, const float* y, float* logits, int B, int T, cudaStream_t st) {
     const size_t smem = (size_t)(T + 512) * sizeof(float);
     ProfScope ps("attention_fc", st);
-    attention_fc_kernel<<<(unsigned)B, 128, smem, st>>>(y, m->att_w, m->att_b, m->fc_w, m->fc_b, logits, T, m->num_classes);
+    attention_fc_kernel<<<(unsigned)B, 256, smem, st>>>(y, m->att_w, m->att_b, m->fc_w, m->fc_b, logits, T, m->num_classes);
     SIR_CHECK_LAUNCH("attention_fc_kernel");
     return SIR_OK;
 }
@@ -476,8 +498,8 @@ int model_forward_convs(sir_model* m, const Workspace& ws, const float* feat, in
                                                 ws.act2_lo + o2, count, H2, W2, m->num_sms, st, "conv2_bn_relu_pool")))
         return rc;
     // conv3 writes [B][T/8][H/8][128]: the GRU input, time-major with channels-last features
-    return tc::tc_conv3x3<64, 128>(ws.act2_hi + o2, ws.act2_lo + o2, m->w3_hi, m->w3_lo, m->sh3, ws.gin_hi + o3, ws.gin_lo + o3,
-                                   nullptr, count, H4, W4, 1, st, "conv3_bn_relu_pool");
+    return tc::tc_conv3x3_stream<64, 128>(ws.act2_hi + o2, ws.act2_lo + o2, m->w3_hi, m->w3_lo, m->sh3, ws.gin_hi + o3,
+                                          ws.gin_lo + o3, count, H4, W4, 1, m->num_sms, st, "conv3_bn_relu_pool");
 }
 
 // 2-layer bidirectional GRU + attention pooling + fc over the B utterances whose GRU input is in the workspace.

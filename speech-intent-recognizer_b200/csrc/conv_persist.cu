@@ -223,6 +223,218 @@ int tc_conv3x3_persistent(const __half* in_hi, const __half* in_lo, const __half
     return SIR_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Streamed-weight variant for conv3 (64 -> 128 channels: 288 KB of fp16 hi/lo weights do not fit in shared memory).
+// Same persistent schedule, but the tile is 8 x 16 pixels (W = 50 -> 7 tiles of 8 instead of 4 of 16: 12 % fewer
+// tiles; a vertical tap is still a swizzle-atom aligned shift, 8 rows x 128 B = 1024 B), activations come through a
+// 2-deep ring of per-kw halo boxes (C, 8, 18, 1) and the weight taps through a 4-deep ring (one tap = 32 KB hi+lo).
+// The epilogue can write the GRU-input order [B][W/2][H/2][C] (models/models.py:55-57 folded into the store).
+// ---------------------------------------------------------------------------------------------------------------
+template <int CIN, int COUT>
+struct CsLayout {
+    static constexpr int kASt = 2, kBSt = 4;
+    static constexpr int kRowBytes = CIN * 2;                       // 128 B
+    static constexpr int kTapBytes = COUT * kRowBytes;              // one weight tap, one of (hi, lo): 16 KB
+    static constexpr int kABytes = 144 * kRowBytes;                 // 8 x 18 pixel halo box, one of (hi, lo): 18 KB
+    static constexpr int kOffB = kASt * 2 * kABytes;
+    static constexpr int kOffBar = kOffB + kBSt * 2 * kTapBytes;
+    static constexpr int kSmemBytes = kOffBar + (2 * kASt + 2 * kBSt + 4) * 8 + 16 + 1024;
+    static_assert(kRowBytes == 128, "built for 64 input channels (128-byte swizzle rows)");
+    static_assert(kTapBytes % 1024 == 0 && kABytes % 1024 == 0, "operand tiles keep 1024-byte alignment");
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+struct CsParams {
+    int B, H, W, tiles_x, tiles_y, num_tiles, out_whc;
+    const float* shift;
+    __half* out_hi;
+    __half* out_lo;
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kCpThreads, 1)
+    conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                          const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                          const CsParams p) {
+    using L = CsLayout<CIN, COUT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+    uint64_t* a_empty = a_full + L::kASt;
+    uint64_t* b_full = a_empty + L::kASt;
+    uint64_t* b_empty = b_full + L::kBSt;
+    uint64_t* acc_full = b_empty + L::kBSt;   // [2]
+    uint64_t* acc_empty = acc_full + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_a_hi);
+        prefetch_tmap(&tm_a_lo);
+        prefetch_tmap(&tm_w_hi);
+        prefetch_tmap(&tm_w_lo);
+        for (int s = 0; s < L::kASt; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < L::kBSt; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<2 * COUT>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t ia = 0, ib = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+                const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
+                for (int kw = 0; kw < 3; ++kw, ++ia) {
+                    const int sa = ia % L::kASt;
+                    mbar_wait(&a_empty[sa], ((ia / L::kASt) & 1u) ^ 1u);
+                    uint8_t* sta = smem + sa * 2 * L::kABytes;
+                    mbar_arrive_expect_tx(&a_full[sa], 2 * L::kABytes);
+                    tma_load_4d(sta, &tm_a_hi, &a_full[sa], 0, x0 + kw - 1, y0 - 1, img);
+                    tma_load_4d(sta + L::kABytes, &tm_a_lo, &a_full[sa], 0, x0 + kw - 1, y0 - 1, img);
+                    for (int kh = 0; kh < 3; ++kh, ++ib) {
+                        const int sb = ib % L::kBSt;
+                        mbar_wait(&b_empty[sb], ((ib / L::kBSt) & 1u) ^ 1u);
+                        uint8_t* stb = smem + L::kOffB + sb * 2 * L::kTapBytes;
+                        mbar_arrive_expect_tx(&b_full[sb], 2 * L::kTapBytes);
+                        tma_load_2d(stb, &tm_w_hi, &b_full[sb], 0, (kh * 3 + kw) * COUT);
+                        tma_load_2d(stb + L::kTapBytes, &tm_w_lo, &b_full[sb], 0, (kh * 3 + kw) * COUT);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc_f16(128, COUT);
+        const uint32_t sbase = smem_u32(smem);
+        uint32_t ia = 0, ib = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t acc = lt & 1u;
+            mbar_wait(&acc_empty[acc], ((lt >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * COUT;
+            for (int kw = 0; kw < 3; ++kw, ++ia) {
+                const int sa = ia % L::kASt;
+                mbar_wait(&a_full[sa], (ia / L::kASt) & 1u);
+                tc_fence_after();
+                const uint32_t a_base = sbase + sa * 2 * L::kABytes;
+                for (int kh = 0; kh < 3; ++kh, ++ib) {
+                    const int sb = ib % L::kBSt;
+                    mbar_wait(&b_full[sb], (ib / L::kBSt) & 1u);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t a_off = kh * 8 * L::kRowBytes;      // vertical tap = 8 rows (one 1024-byte atom) further down
+                        const uint64_t a_hi = make_kmajor_desc<128>(a_base + a_off);
+                        const uint64_t a_lo = make_kmajor_desc<128>(a_base + L::kABytes + a_off);
+                        const uint32_t w_base = sbase + L::kOffB + sb * 2 * L::kTapBytes;
+                        const uint64_t b_hi = make_kmajor_desc<128>(w_base);
+                        const uint64_t b_lo = make_kmajor_desc<128>(w_base + L::kTapBytes);
+#pragma unroll
+                        for (int k = 0; k < CIN; k += 16) {
+                            umma_f16(d_tmem, desc_advance_k(a_hi, k), desc_advance_k(b_hi, k), idesc, (kw | kh | k) ? 1u : 0u);
+                            umma_f16(d_tmem, desc_advance_k(a_hi, k), desc_advance_k(b_lo, k), idesc, 1u);
+                            umma_f16(d_tmem, desc_advance_k(a_lo, k), desc_advance_k(b_hi, k), idesc, 1u);
+                        }
+                        umma_commit(&b_empty[sb]);
+                        if (kh == 2) umma_commit(&a_empty[sa]);
+                        if (kh == 2 && kw == 2) umma_commit(&acc_full[acc]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // epilogue: quadrant q holds tile rows y = 4q .. 4q+3 (lane = dy * 8 + x); pooling partners are lanes ^1 and ^8
+        const int q = warp & 3;
+        const int H2 = p.H / 2, W2 = p.W / 2;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t acc = lt & 1u;
+            const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+            const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
+            mbar_wait(&acc_full[acc], (lt >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + acc * COUT + ((uint32_t)(q * 32) << 16);
+            const int y2 = y0 / 2 + 2 * q + (lane >> 4), x2 = x0 / 2 + ((lane & 7) >> 1);
+            const bool inside = y2 < H2 && x2 < W2;
+            const int64_t pix = p.out_whc ? ((int64_t)img * W2 + x2) * H2 + y2 : ((int64_t)img * H2 + y2) * W2 + x2;
+#pragma unroll 1
+            for (int c = 0; c < COUT; c += 32) {
+                float v[32], o[8];
+                tmem_ld_32x32(trow + c, v);
+                const int ch = c + pool2x2_split_channels<8>(v, lane, o);
+                if (inside) shift_relu_split_store8(o, p.shift + ch, p.out_hi + pix * COUT + ch, p.out_lo + pix * COUT + ch);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<2 * COUT>(tmem_base);
+    }
+}
+
+template <int CIN, int COUT>
+int tc_conv3x3_stream(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
+                      __half* out_hi, __half* out_lo, int B, int H, int W, int out_whc, int num_sms, cudaStream_t st,
+                      const char* name) {
+    using L = CsLayout<CIN, COUT>;
+    CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+    const uint64_t adims[4] = {(uint64_t)CIN, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint32_t abox[4] = {(uint32_t)CIN, 8, 18, 1};
+    const uint64_t wdims[2] = {(uint64_t)CIN, (uint64_t)(9 * COUT)};
+    const uint32_t wbox[2] = {(uint32_t)CIN, (uint32_t)COUT};
+    int rc;
+    if ((rc = make_tmap(&ta_hi, in_hi, 4, adims, abox)) || (rc = make_tmap(&ta_lo, in_lo, 4, adims, abox)) ||
+        (rc = make_tmap(&tw_hi, w_hi, 2, wdims, wbox)) || (rc = make_tmap(&tw_lo, w_lo, 2, wdims, wbox)))
+        return rc;
+    CsParams p{};
+    p.B = B;
+    p.H = H;
+    p.W = W;
+    p.tiles_x = (W + 7) / 8;
+    p.tiles_y = (H + 15) / 16;
+    p.num_tiles = B * p.tiles_x * p.tiles_y;
+    p.out_whc = out_whc;
+    p.shift = shift;
+    p.out_hi = out_hi;
+    p.out_lo = out_lo;
+    auto kern = conv3x3_stream_kernel<CIN, COUT>;
+    static bool attr = false;
+    if (!attr) {
+        SIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes));
+        attr = true;
+    }
+    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    {
+        ProfScope ps(name, st);
+        kern<<<grid, kCpThreads, L::kSmemBytes, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
+    }
+    SIR_CHECK_LAUNCH(name);
+    return SIR_OK;
+}
+
+template int tc_conv3x3_stream<64, 128>(const __half*, const __half*, const __half*, const __half*, const float*, __half*,
+                                        __half*, int, int, int, int, int, cudaStream_t, const char*);
+
 template int tc_conv3x3_persistent<32, 64>(const __half*, const __half*, const __half*, const __half*, const float*, __half*,
                                            __half*, int, int, int, int, cudaStream_t, const char*);
 

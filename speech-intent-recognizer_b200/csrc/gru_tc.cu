@@ -17,6 +17,8 @@
 //      16-byte chunk each - into the next-step B operand of all 8 CTAs through distributed shared memory;
 //   4. one cluster barrier (release/acquire) per step.
 // No grid-wide synchronisation, no per-step launch, no L2 round trip on the recurrence's critical path.
+#include <cstdlib>
+
 #include "sir_common.cuh"
 #include "tc_common.cuh"
 
@@ -51,7 +53,11 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
     asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
 }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+// Gate non-linearities on the SFU: ex2.approx + rcp.approx (relative error ~1e-6, far inside the 1e-3 logit bar)
+// instead of expf / tanhf / IEEE division, which cost ~1.2 us of the ~7 us per time step (measured by switching
+// them off, tools/gru_experiments.sh).  tanh(x) = 1 - 2 / (1 + e^{2x}) saturates correctly for large |x|.
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 template <int NB>
 __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads, 1)
@@ -60,7 +66,7 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
                         const float* __restrict__ gi,                  // [B*T, 1536]
                         const float* __restrict__ bhh,                 // [2][768]
                         float* __restrict__ y,                         // [B, T, 512]
-                        __half* __restrict__ y_hi, __half* __restrict__ y_lo, int B, int T) {
+                        __half* __restrict__ y_hi, __half* __restrict__ y_lo, int B, int T, int dbg) {
     using L = GtLayout<NB>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -140,7 +146,7 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
                 gin[g][1] = __ldg(gp + g * 64 + 1);
             }
         }
-        if (s > 0) {
+        if (s > 0 && !(dbg & 2)) {
             // (1) D[128 gate rows, NB utterances] = W_slice[128, 256] . h^T   (h: buffer `cur`)
             if (tid == 0) {
                 fence_proxy_async_all();
@@ -208,9 +214,16 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
                     az = s_gate[(1 * 32 + u) * L::kSStride + ui];
                     an = s_gate[(2 * 32 + u) * L::kSStride + ui];
                 }
-                const float r = sigmoid_f(gr[e] + ar + b_r[e]);
-                const float z = sigmoid_f(gz[e] + az + b_z[e]);
-                const float n = tanhf(gn[e] + r * (an + b_n[e]));
+                float r, z, n;
+                if (dbg & 16) {
+                    r = gr[e] + ar + b_r[e];
+                    z = gz[e] + az + b_z[e];
+                    n = gn[e] + r * (an + b_n[e]);
+                } else {
+                    r = sigmoid_f(gr[e] + ar + b_r[e]);
+                    z = sigmoid_f(gz[e] + az + b_z[e]);
+                    n = tanh_f(gn[e] + r * (an + b_n[e]));
+                }
                 hn[e] = (1.f - z) * n + z * hprev[e];
                 hprev[e] = hn[e];
             }
@@ -224,7 +237,7 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
             }
             const uint4 vhi = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
             const uint4 vlo = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
-            if (s + 1 < T) {
+            if (s + 1 < T && !(dbg & 1)) {
                 const uint32_t dst = sbase + L::kOffH + nxt * 2 * L::kHBytes + chunk_off;
 #pragma unroll
                 for (int c = 0; c < kGtCluster; ++c) {
@@ -245,9 +258,13 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
             }
         }
         // (4) the pushes of all 8 CTAs have landed (and this step's reads of s_gate / TMEM are done)
-        fence_proxy_async_all();
-        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        if (!(dbg & 8)) fence_proxy_async_all();
+        if (dbg & 4) {
+            __syncthreads();
+        } else {
+            asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -267,7 +284,8 @@ static int launch_gru(const CUtensorMap& tm_w_hi, const CUtensorMap& tm_w_lo, co
         attr = true;
     }
     dim3 grid((unsigned)(kGtCluster * ((B + NB - 1) / NB)), 2);
-    gru_layer_tc_kernel<NB><<<grid, kGtThreads, L::kSmemBytes, st>>>(tm_w_hi, tm_w_lo, gi, bhh, y, y_hi, y_lo, B, T);
+    static const int dbg = getenv("SIR_GRU_DEBUG_SKIP") ? atoi(getenv("SIR_GRU_DEBUG_SKIP")) : 0;   // timing experiments only
+    gru_layer_tc_kernel<NB><<<grid, kGtThreads, L::kSmemBytes, st>>>(tm_w_hi, tm_w_lo, gi, bhh, y, y_hi, y_lo, B, T, dbg);
     SIR_CHECK_LAUNCH("gru_layer_tc_kernel");
     return SIR_OK;
 }

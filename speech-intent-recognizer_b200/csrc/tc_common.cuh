@@ -165,14 +165,15 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
 }
 
 // ---- pooled conv epilogue -----------------------------------------------------------------------------------
-// One warp holds a 2 x 16 pixel patch of a conv tile (lane = (dy << 4) | x) and, per lane, 32 consecutive output
-// channels v[0..32) of its pixel.  2x2 max-pool partners are lanes ^1 (x) and ^16 (y).  Instead of reducing all
+// One warp holds a 2 x 16 (or 4 x 8) pixel patch of a conv tile (lane = dy * width + x) and, per lane, 32 consecutive
+// output channels v[0..32) of its pixel.  2x2 max-pool partners are lanes ^1 (x) and ^16 (or ^8) (y).  Instead of reducing all
 // 32 channels in all four lanes, the lanes of a pooling group split the channels while they reduce: after the x
 // step each lane owns 16 channels, after the y step 8 - 24 shuffles per lane instead of 64, and every lane ends
 // with 8 DISTINCT pooled channels: + shift, ReLU, fp16 hi/lo split, one 16-byte store each to hi and lo.
 // Returns the first channel (relative to the chunk) this lane owns.
+template <int YBIT = 16>     // lane bit that separates the two pixel rows of a pooling window (tile width 16 or 8)
 __device__ __forceinline__ int pool2x2_split_channels(const float (&v)[32], int lane, float (&out)[8]) {
-    const bool sx = lane & 1, sy = (lane >> 4) & 1;
+    const bool sx = lane & 1, sy = (lane & YBIT) != 0;
     float m[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -184,7 +185,7 @@ __device__ __forceinline__ int pool2x2_split_channels(const float (&v)[32], int 
     for (int j = 0; j < 8; ++j) {
         const float keep = sy ? m[j + 8] : m[j];
         const float send = sy ? m[j] : m[j + 8];
-        out[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+        out[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, YBIT));
     }
     return (sx ? 16 : 0) + (sy ? 8 : 0);
 }
