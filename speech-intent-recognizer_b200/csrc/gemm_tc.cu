@@ -283,10 +283,202 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
     return SIR_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent GEMM for the GRU input projections C[M, N] = X[M, K] W[N, K]^T + bias (M = B*T rows, N = 1536,
+// K = 1024 / 512), computed TRANSPOSED: the weight rows are the UMMA M dimension (128 per tile), the activation rows
+// the UMMA N dimension in tiles of 176.  Why 176: with 6400 activation rows the usual 128 x 128 / 128 x 256 tilings
+// give 600 / 300 tiles = 4.05 / 2.03 waves on 148 SMs (measured: a third of the launch runs 4 % of the SMs), while
+// 12 x ceil(6400 / 176) = 444 tiles = exactly 3 waves.  One CTA per SM walks its tiles; two TMEM accumulators let the
+// epilogue of tile i (bias add, transposed fp32 store: 32 lanes = 32 consecutive output columns) overlap the MMAs of
+// tile i+1; barrier setup, TMEM allocation and pipeline fill are paid once per CTA.
+// ---------------------------------------------------------------------------------------------------------------
+struct GpLayout {
+    static constexpr int kBK = 32, kStages = 5, kBN = 176;         // K-blocks of 32 = 64-byte swizzle rows
+    static constexpr int kABytes = 128 * kBK * 2;                  // weight tile, one of (hi, lo): 8 KB
+    static constexpr int kBBytes = kBN * kBK * 2;                  // activation tile: 11 KB
+    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // 38 KB
+    static constexpr int kOffBar = kStages * kStageBytes;
+    static constexpr int kSmemBytes = kOffBar + (2 * kStages + 4) * 8 + 16 + 1024;
+    static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "operand tiles keep 1024-byte alignment");
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+struct GpParams {
+    int M, N, num_kblocks, tiles_w, tiles_x, num_tiles;   // tiles_w: weight-row tiles (N / 128), tiles_x: activation-row tiles
+    const float* bias;
+    float* C;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+    gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                           const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+                           const GpParams p) {
+    using L = GpLayout;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+    uint64_t* empty = full + L::kStages;
+    uint64_t* acc_full = empty + L::kStages;   // [2]
+    uint64_t* acc_empty = acc_full + 2;        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_w_hi);
+        prefetch_tmap(&tm_w_lo);
+        prefetch_tmap(&tm_x_hi);
+        prefetch_tmap(&tm_x_lo);
+        for (int s = 0; s < L::kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t kAccStride = 256;       // second accumulator at column 256
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int w0 = (tile % p.tiles_w) * 128, x0 = (tile / p.tiles_w) * L::kBN;
+                for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
+                    const int s = it % L::kStages;
+                    mbar_wait(&empty[s], ((it / L::kStages) & 1u) ^ 1u);
+                    uint8_t* st = smem + s * L::kStageBytes;
+                    mbar_arrive_expect_tx(&full[s], L::kStageBytes);
+                    tma_load_2d(st, &tm_w_hi, &full[s], kb * L::kBK, w0);
+                    tma_load_2d(st + L::kABytes, &tm_w_lo, &full[s], kb * L::kBK, w0);
+                    tma_load_2d(st + 2 * L::kABytes, &tm_x_hi, &full[s], kb * L::kBK, x0);
+                    tma_load_2d(st + 2 * L::kABytes + L::kBBytes, &tm_x_lo, &full[s], kb * L::kBK, x0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc_f16(128, L::kBN);
+        const uint32_t sbase = smem_u32(smem);
+        uint32_t it = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t acc = lt & 1u;
+            mbar_wait(&acc_empty[acc], ((lt >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * kAccStride;
+            for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
+                const int s = it % L::kStages;
+                mbar_wait(&full[s], (it / L::kStages) & 1u);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t base = sbase + s * L::kStageBytes;
+                    const uint64_t a_hi = make_kmajor_desc<2 * L::kBK>(base);
+                    const uint64_t a_lo = make_kmajor_desc<2 * L::kBK>(base + L::kABytes);
+                    const uint64_t b_hi = make_kmajor_desc<2 * L::kBK>(base + 2 * L::kABytes);
+                    const uint64_t b_lo = make_kmajor_desc<2 * L::kBK>(base + 2 * L::kABytes + L::kBBytes);
+#pragma unroll
+                    for (int k = 0; k < L::kBK; k += 16) {
+                        umma_f16(d_tmem, desc_advance_k(a_hi, k), desc_advance_k(b_hi, k), idesc, (kb | k) ? 1u : 0u);
+                        umma_f16(d_tmem, desc_advance_k(a_hi, k), desc_advance_k(b_lo, k), idesc, 1u);
+                        umma_f16(d_tmem, desc_advance_k(a_lo, k), desc_advance_k(b_hi, k), idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);
+                    if (kb == p.num_kblocks - 1) umma_commit(&acc_full[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // TMEM lane = weight row (output column n), TMEM column = activation row (output row m)
+        const int q = warp & 3;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t acc = lt & 1u;
+            const int w0 = (tile % p.tiles_w) * 128, x0 = (tile / p.tiles_w) * L::kBN;
+            mbar_wait(&acc_full[acc], (lt >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
+            const int n = w0 + q * 32 + lane;
+            const float bias = __ldg(p.bias + n);
+            float* __restrict__ dst = p.C + n;
+#pragma unroll 1
+            for (int c = 0; c < L::kBN; c += 16) {
+                uint32_t r[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(trow + c)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int m = x0 + c + i;
+                    if (m < p.M) dst[(int64_t)m * p.N] = __uint_as_float(r[i]) + bias;     // 32 lanes -> 128 contiguous bytes
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+static int tc_gemm_nt_persistent(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo, const float* bias,
+                                 float* C, int M, int N, int K, cudaStream_t st, const char* name) {
+    using L = GpLayout;
+    CUtensorMap tw_hi, tw_lo, tx_hi, tx_lo;
+    const uint64_t xdims[2] = {(uint64_t)K, (uint64_t)M}, wdims[2] = {(uint64_t)K, (uint64_t)N};
+    const uint32_t wbox[2] = {L::kBK, 128}, xbox[2] = {L::kBK, L::kBN};
+    int rc;
+    if ((rc = make_tmap(&tw_hi, w_hi, 2, wdims, wbox)) || (rc = make_tmap(&tw_lo, w_lo, 2, wdims, wbox)) ||
+        (rc = make_tmap(&tx_hi, a_hi, 2, xdims, xbox)) || (rc = make_tmap(&tx_lo, a_lo, 2, xdims, xbox)))
+        return rc;
+    GpParams p{};
+    p.M = M;
+    p.N = N;
+    p.num_kblocks = K / L::kBK;
+    p.tiles_w = N / 128;
+    p.tiles_x = (M + L::kBN - 1) / L::kBN;
+    p.num_tiles = p.tiles_w * p.tiles_x;
+    p.bias = bias;
+    p.C = C;
+    static bool attr = false;
+    static int num_sms = 148;
+    if (!attr) {
+        SIR_CUDA(cudaFuncSetAttribute(gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes));
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms < 1) num_sms = 148;
+        attr = true;
+    }
+    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    {
+        ProfScope ps(name, st);
+        gemm_persistent_kernel<<<grid, kTcThreads, L::kSmemBytes, st>>>(tw_hi, tw_lo, tx_hi, tx_lo, p);
+    }
+    SIR_CHECK_LAUNCH(name);
+    return SIR_OK;
+}
+
 // C[M,N] = A[M,K] W[N,K]^T + bias ; operands as fp16 hi/lo pairs.  N % 128 == 0, K % 64 == 0.
 int tc_gemm_nt(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo, const float* bias,
                float* C, int M, int N, int K, cudaStream_t st, const char* name) {
     if (N % 128 || K % 64) return fail(SIR_ERR_INVALID, "tc_gemm_nt: N %% 128 and K %% 64 required (N %d, K %d)", N, K);
+    if ((int64_t)((M + 175) / 176) * (N / 128) >= 32)   // enough tiles to be worth a persistent launch
+        return tc_gemm_nt_persistent(a_hi, a_lo, w_hi, w_lo, bias, C, M, N, K, st, name);
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     const uint64_t adims[2] = {(uint64_t)K, (uint64_t)M}, bdims[2] = {(uint64_t)K, (uint64_t)N};
     const uint32_t abox[2] = {64, 128}, bbox[2] = {64, 128};

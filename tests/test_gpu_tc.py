@@ -8,7 +8,8 @@ pytestmark = pytest.mark.gpu
 native = importlib.import_module("speech-intent-recognizer_b200._native")
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 192), (6400, 1536, 1024), (275, 256, 512), (1, 128, 64)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 192), (6400, 1536, 1024), (275, 256, 512), (1, 128, 64),
+                                   (4100, 512, 128), (6400, 768, 256)])     # the last three take the persistent 128x256 kernel
 def test_gemm_nt_split_f16_matches_fp64(M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + K)
     a = torch.randn(M, K, device="cuda", generator=g) * 3.0
