@@ -84,6 +84,14 @@ int sir_frontend_forward(sir_frontend* fe, const float* d_wave, int64_t wave_str
                          int n_samples, int batch, int max_samples, int mode, int out_frames, float* d_out,
                          const int32_t* d_masks, int32_t* d_status, void* stream);
 
+/* sir_frontend_forward_pcm16: the same, ingesting 16-bit PCM rows (the payload of the WAV files the reference reads):
+ * samples are scaled by 1/32768 on load - bit-identical to torchaudio.load's normalisation
+ * (scripts/precompute_features.py:47, scripts/dataset.py:126) followed by sir_frontend_forward, with half the
+ * HBM / PCIe bytes per utterance.  wave_stride and n_samples count samples. */
+int sir_frontend_forward_pcm16(sir_frontend* fe, const int16_t* d_pcm, int64_t wave_stride, const int32_t* d_lengths,
+                               int n_samples, int batch, int max_samples, int mode, int out_frames, float* d_out,
+                               const int32_t* d_masks, int32_t* d_status, void* stream);
+
 /* sir_amplitude_to_db  <->  AudioFeatureExtractor.amplitude_to_db  scripts/precompute_features.py:36,67
  * 10*log10(max(x, 1e-10)) elementwise over n values (in place allowed). */
 int sir_amplitude_to_db(const float* d_in, float* d_out, int64_t n, void* stream);

@@ -29,6 +29,8 @@ SIGNATURES = {
     "sir_frontend_destroy": (None, [c_void_p]),
     "sir_frontend_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sir_frontend_forward_pcm16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                           c_void_p, c_void_p, c_void_p, c_void_p]),
     "sir_amplitude_to_db": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "sir_specaugment_sample": (c_int, [c_uint64, c_uint64, c_int, c_int, c_int, c_void_p, c_float, c_int, c_int,
                                        c_void_p, c_void_p]),
@@ -134,8 +136,9 @@ class Frontend:
 
     def forward(self, wave, lengths=None, max_samples=0, mode=OUT_LOGMEL_NORM, out_frames=None, masks=None,
                 status=None, out=None):
-        """wave [B, L] fp32 CUDA (rows may be strided) -> [B, n_mels, out_frames] fp32 CUDA."""
-        require_cuda(wave, "wave")
+        """wave [B, L] fp32 (or int16 PCM, scaled by 1/32768) CUDA, rows may be strided -> [B, n_mels, out_frames] fp32."""
+        pcm16 = wave.dtype == torch.int16
+        require_cuda(wave, "wave", torch.int16 if pcm16 else torch.float32)
         if wave.dim() != 2 or wave.stride(1) != 1:
             raise NativeError("wave must be [batch, samples] with contiguous rows")
         B, L = wave.shape
@@ -155,9 +158,9 @@ class Frontend:
         if status is not None:
             require_cuda(status, "status", torch.int32)
         stride = wave.stride(0) if B > 1 else max(L, 1)
-        check(load_library().sir_frontend_forward(self._h, ptr(wave), stride, ptr(lengths), L, B, int(max_samples or 0),
-                                                  mode, out_frames, ptr(out), ptr(masks), ptr(status), stream_ptr()),
-              "sir_frontend_forward")
+        entry = load_library().sir_frontend_forward_pcm16 if pcm16 else load_library().sir_frontend_forward
+        check(entry(self._h, ptr(wave), stride, ptr(lengths), L, B, int(max_samples or 0), mode, out_frames, ptr(out),
+                    ptr(masks), ptr(status), stream_ptr()), "sir_frontend_forward")
         return out
 
 

@@ -85,7 +85,7 @@ static_assert(kOffScratch % 4 == 0 && kOffTile % 4 == 0, "16-byte alignment of v
 static_assert(SIR_FE_MIN_CTAS * (kFeSmemBytes + 1024) <= 232448, "resident CTAs per SM");
 
 struct FrontendParams {
-    const float* wave;
+    const void* wave;          // fp32 or int16 samples (template parameter of the kernel)
     int64_t wave_stride;
     const int32_t* lengths;
     int n_samples;
@@ -103,12 +103,27 @@ struct FrontendParams {
 // Interior frames read their 1024 samples straight from global memory: lane l takes the 8-byte words
 // l + 16 j, so a half-warp covers 128 contiguous bytes per request, and the 50 % overlap with the neighbouring
 // frame (the other half of the same warp) is served by L1/L2 - HBM still sees every sample once.
-struct GlobalFrame {
+template <typename T>
+struct GlobalFrame;
+template <>
+struct GlobalFrame<float> {
     const float2* base;
+    __device__ __forceinline__ explicit GlobalFrame(const float* p) : base(reinterpret_cast<const float2*>(p)) {}
     __device__ __forceinline__ F2 operator()(int n) const {
         const float2 v = __ldg(base + n);
         return F2{v.x, v.y};
     }
+    static constexpr uintptr_t kAlignMask = 7u;
+};
+template <>
+struct GlobalFrame<short> {                       // PCM16: one 4-byte word per sample pair
+    const short2* base;
+    __device__ __forceinline__ explicit GlobalFrame(const short* p) : base(reinterpret_cast<const short2*>(p)) {}
+    __device__ __forceinline__ F2 operator()(int n) const {
+        const short2 v = __ldg(base + n);
+        return F2{sample_to_float(v.x), sample_to_float(v.y)};
+    }
+    static constexpr uintptr_t kAlignMask = 3u;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -117,6 +132,7 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+template <typename SampleT>
 __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_kernel(const FrontendParams p) {
     extern __shared__ __align__(16) float smem[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -149,8 +165,8 @@ __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_k
     const bool valid = L > kNfft / 2;                       // reflect padding needs L > 512
     const int T = valid ? 1 + L / kHop : 0;
     const int n_groups = (T + kGroupFrames - 1) / kGroupFrames;
-    const float* __restrict__ row = p.wave + (int64_t)b * p.wave_stride;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 7u) == 0);
+    const SampleT* __restrict__ row = static_cast<const SampleT*>(p.wave) + (int64_t)b * p.wave_stride;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & GlobalFrame<SampleT>::kAlignMask) == 0);
     float* __restrict__ out = p.out + (int64_t)b * p.n_mels * p.out_frames;
     const bool out_vec = (p.out_frames % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
     if (p.status && crank == 0 && tid == 0) p.status[b] = valid ? 0 : 1;
@@ -173,10 +189,10 @@ __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_k
             // frame t covers original samples [512 t - 512, 512 t + 512)
             const int first = t * kHop - kNfft / 2;
             if (vec_ok && first >= 0 && first + kNfft <= L) {
-                const GlobalFrame ld{reinterpret_cast<const float2*>(row + first)};
+                const GlobalFrame<SampleT> ld(row + first);
                 frame_phase_a(q, ld, st.window, st.tw512, scr, scr + 16 * kRowPad);
             } else {
-                const ReflectFrame ld{row, first, L};
+                const ReflectFrame<SampleT> ld{row, first, L};
                 frame_phase_a(q, ld, st.window, st.tw512, scr, scr + 16 * kRowPad);
             }
         }
@@ -482,7 +498,9 @@ extern "C" int sir_frontend_create(sir_frontend** out, int sample_rate, int n_me
     fe->dev = FrontendTables{(const float*)(base + o_win), (const float*)(base + o_512), (const float*)(base + o_1024),
                              (const int*)(base + o_ms),    (const int*)(base + o_mc),    (const int*)(base + o_mo),
                              (const float*)(base + o_mw)};
-    e = cudaFuncSetAttribute(logmel_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFeSmemBytes);
+    e = cudaFuncSetAttribute(logmel_frontend_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFeSmemBytes);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(logmel_frontend_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFeSmemBytes);
     if (e != cudaSuccess) {
         fe->tables.release();
         delete fe;
@@ -498,10 +516,9 @@ extern "C" void sir_frontend_destroy(sir_frontend* fe) {
     delete fe;
 }
 
-extern "C" int sir_frontend_forward(sir_frontend* fe, const float* d_wave, int64_t wave_stride,
-                                    const int32_t* d_lengths, int n_samples, int batch, int max_samples, int mode,
-                                    int out_frames, float* d_out, const int32_t* d_masks, int32_t* d_status,
-                                    void* stream) {
+static int frontend_launch(sir_frontend* fe, const void* d_wave, bool pcm16, int64_t wave_stride, const int32_t* d_lengths,
+                           int n_samples, int batch, int max_samples, int mode, int out_frames, float* d_out,
+                           const int32_t* d_masks, int32_t* d_status, void* stream) {
     if (!fe || !d_wave || !d_out) return fail(SIR_ERR_INVALID, "sir_frontend_forward: NULL handle or buffer");
     if (batch < 0 || n_samples < 0 || out_frames < 1 || wave_stride < n_samples)
         return fail(SIR_ERR_INVALID, "sir_frontend_forward: bad sizes (batch %d, n_samples %d, out_frames %d)", batch,
@@ -543,10 +560,29 @@ extern "C" int sir_frontend_forward(sir_frontend* fe, const float* d_wave, int64
     cfg.numAttrs = 1;
     {
         ProfScope ps("logmel_frontend_kernel", cfg.stream);
-        SIR_CUDA(cudaLaunchKernelEx(&cfg, logmel_frontend_kernel, p));
+        if (pcm16)
+            SIR_CUDA(cudaLaunchKernelEx(&cfg, logmel_frontend_kernel<short>, p));
+        else
+            SIR_CUDA(cudaLaunchKernelEx(&cfg, logmel_frontend_kernel<float>, p));
     }
     SIR_CHECK_LAUNCH("logmel_frontend_kernel");
     return SIR_OK;
+}
+
+extern "C" int sir_frontend_forward(sir_frontend* fe, const float* d_wave, int64_t wave_stride,
+                                    const int32_t* d_lengths, int n_samples, int batch, int max_samples, int mode,
+                                    int out_frames, float* d_out, const int32_t* d_masks, int32_t* d_status,
+                                    void* stream) {
+    return frontend_launch(fe, d_wave, false, wave_stride, d_lengths, n_samples, batch, max_samples, mode, out_frames, d_out,
+                           d_masks, d_status, stream);
+}
+
+extern "C" int sir_frontend_forward_pcm16(sir_frontend* fe, const int16_t* d_pcm, int64_t wave_stride,
+                                          const int32_t* d_lengths, int n_samples, int batch, int max_samples, int mode,
+                                          int out_frames, float* d_out, const int32_t* d_masks, int32_t* d_status,
+                                          void* stream) {
+    return frontend_launch(fe, d_pcm, true, wave_stride, d_lengths, n_samples, batch, max_samples, mode, out_frames, d_out,
+                           d_masks, d_status, stream);
 }
 
 extern "C" int sir_amplitude_to_db(const float* d_in, float* d_out, int64_t n, void* stream) {

@@ -80,12 +80,18 @@ struct ContiguousFrame {
 
 // Loader that resolves torch.stft's reflect padding: sample i of the utterance for i in [first, first+1024),
 // mirrored at 0 and at L-1 (TA:functional/functional.py:123-134, pad_mode="reflect").
+// Sample types the frontend ingests: fp32 in [-1, 1], or 16-bit PCM scaled by 1/32768 exactly like torchaudio.load's
+// normalisation of a PCM16 file (scripts/precompute_features.py:47) - the conversion is exact in fp32.
+SIR_HD float sample_to_float(float v) { return v; }
+SIR_HD float sample_to_float(short v) { return (float)v * (1.0f / 32768.0f); }
+
+template <typename T = float>
 struct ReflectFrame {
-    const float* row;
+    const T* row;
     int first, L;
     SIR_HD float at(int i) const {
         const int r = i < 0 ? -i : (i >= L ? 2 * (L - 1) - i : i);
-        return (r >= 0 && r < L) ? row[r] : 0.f;
+        return (r >= 0 && r < L) ? sample_to_float(row[r]) : 0.f;
     }
     SIR_HD F2 operator()(int n) const { return F2{at(first + 2 * n), at(first + 2 * n + 1)}; }
 };

@@ -42,17 +42,19 @@ class IntentPipeline:
         self._slots = [_Slot() for _ in range(max(1, int(depth)))]
         self._next = 0
 
-    def _prepare(self, slot, B, L, num_classes, device):
-        if slot.key != (B, L):
-            slot.key = (B, L)
-            slot.d_wave = torch.empty((B, L), device=device, dtype=torch.float32)
+    def _prepare(self, slot, B, L, num_classes, device, dtype):
+        if slot.key != (B, L, dtype):
+            slot.key = (B, L, dtype)
+            slot.d_wave = torch.empty((B, L), device=device, dtype=dtype)
             slot.feats = torch.empty((B, self.extractor.n_mels, self.out_frames), device=device, dtype=torch.float32)
             slot.logits = torch.empty((B, num_classes), device=device, dtype=torch.float32)
             slot.host_logits = torch.empty((B, num_classes), dtype=torch.float32).pin_memory()
 
     @torch.no_grad()
     def submit(self, waves: torch.Tensor, lengths: torch.Tensor = None):
-        """Enqueue one batch (``waves [B, L]`` fp32 in - ideally pinned - host memory); returns a ticket for ``collect``.
+        """Enqueue one batch (``waves [B, L]``, fp32 or int16 PCM, in - ideally pinned - host memory); returns a ticket
+        for ``collect``.  PCM16 input is scaled by 1/32768 on the device (what torchaudio.load does on the host) and
+        halves the PCIe bytes per utterance.
 
         Nothing here waits for the GPU unless all ``depth`` slots are still in flight.
         """
@@ -69,7 +71,9 @@ class IntentPipeline:
             self.collect(slot)                                       # all slots in flight: drain the oldest
         B, L = waves.shape
         dev = torch.device("cuda", torch.cuda.current_device())
-        self._prepare(slot, B, L, model.num_classes, dev)
+        if waves.dtype not in (torch.float32, torch.int16):
+            raise _native.NativeError(f"waves must be float32 or int16 PCM, got {waves.dtype}")
+        self._prepare(slot, B, L, model.num_classes, dev, waves.dtype)
         compute, copy = torch.cuda.current_stream(), self._copy_stream
         copy.wait_event(slot.done)                                   # the slot's previous readers of d_wave are done
         staged = B <= _native.Model.MAX_STAGED_BATCH

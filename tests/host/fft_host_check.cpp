@@ -30,7 +30,7 @@ int main(int argc, char** argv) {
             ContiguousFrame ld{reinterpret_cast<const F2*>(frame.data())};
             for (int l = 0; l < 16; ++l) frame_phase_a(l, ld, t.window, t.tw512, scr_re, scr_im);
         } else {
-            ReflectFrame ld{frame.data(), 0, 1024};
+            ReflectFrame<float> ld{frame.data(), 0, 1024};
             for (int l = 0; l < 16; ++l) frame_phase_a(l, ld, t.window, t.tw512, scr_re, scr_im);
         }
         std::vector<PhaseBRegs> rb(16);

@@ -206,3 +206,32 @@ def test_host_pipeline_equals_device_path():
     pipe = pipeline.IntentPipeline(ex, m, sub_batches=3, depth=2)
     for i, got in enumerate(pipe.infer_stream(batches)):
         assert torch.equal(got, m(ex.extract_batch(batches[i].cuda(), out_frames=200)).cpu()), i
+
+
+def test_pcm16_ingest_is_bit_identical_to_float_path(fe, model):
+    """16-bit PCM rows scaled by 1/32768 on load == torchaudio.load's normalisation followed by the fp32 path."""
+    g, waves, lengths, _ = golden_waves()
+    pcm = np.round(waves * 32767.0).astype(np.int16)
+    as_float = (pcm.astype(np.float32) / 32768.0).astype(np.float32)          # what the reference's loader hands on
+    lens = dev(np.asarray(lengths, np.int32))
+    a = fe.forward(dev(pcm), lengths=lens, max_samples=80000, out_frames=200)
+    b = fe.forward(dev(as_float), lengths=lens, max_samples=80000, out_frames=200)
+    assert torch.equal(a, b)
+    want = np.stack([logmel_np.dataset_item(as_float[i, :n]) for i, n in enumerate(lengths)])
+    assert rel_to_scale(a.cpu().numpy(), want) < FEATURE_REL_TOL
+    odd = torch.zeros(2, 30001, dtype=torch.int16, device="cuda")              # odd stride -> unaligned rows (scalar loads)
+    odd[:, :30000] = dev(pcm[:2, :30000].copy())
+    got_odd = fe.forward(odd[:, :30000]).cpu().numpy()          # the scalar-load path contracts FMAs differently: ulp-level
+    assert rel_to_scale(got_odd, fe.forward(dev(as_float[:2, :30000].copy())).cpu().numpy()) < 1e-5
+    pre = importlib.import_module("speech-intent-recognizer_b200.scripts.precompute_features")
+    models = importlib.import_module("speech-intent-recognizer_b200.models.models")
+    pipeline = importlib.import_module("speech-intent-recognizer_b200.pipeline")
+    ex = pre.AudioFeatureExtractor()
+    m = models.CNNAudioGRU(31)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_weights(1234).items()}, strict=False)
+    m = m.cuda().eval()
+    pipe = pipeline.IntentPipeline(ex, m)
+    host_pcm = torch.from_numpy(pcm[:, :48000].copy()).pin_memory()
+    got = pipe.infer_host(host_pcm).clone()
+    ref = pipe.infer_host(torch.from_numpy(as_float[:, :48000].copy()).pin_memory())
+    assert torch.equal(got, ref)
