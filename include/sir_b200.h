@@ -135,6 +135,16 @@ int64_t sir_model_weight_count(const sir_model* m);
 int sir_model_forward(sir_model* m, const float* d_features, int batch, int n_frames, float* d_logits,
                       void* stream);
 
+/* sir_predict  <->  the evaluation head right after the logits:
+ *                   scripts/test_model.py:121-156 (softmax, argmax, confidence, get_top_predictions k = 3) and
+ *                   scripts/evaluate.py:79-98 (argmax, accuracy_score / confusion_matrix inputs)
+ *   d_pred [batch] int32 = argmax (first maximum); d_conf [batch] = softmax probability of d_pred;
+ *   d_topk_idx / d_topk_prob [batch, k] = argsort(probs)[::-1][:k] (ties: higher index first, as numpy does), k <= 8;
+ *   with d_labels: d_correct[0] += #(pred == label), d_confusion[label * C + pred] += 1 (int64 counters, accumulated
+ *   across calls; the caller zeroes them).  Any output pointer may be NULL. */
+int sir_predict(const float* d_logits, int batch, int num_classes, int k, const int64_t* d_labels, int32_t* d_pred,
+                float* d_conf, int32_t* d_topk_idx, float* d_topk_prob, int64_t* d_confusion, int64_t* d_correct, void* stream);
+
 /* ---- training step --------------------------------------------------------------------------------------
  * The device work of scripts/train.py:80-116 (model.train() forward, CrossEntropyLoss, backward, Adam, GradScaler
  * unscale / inf-skip).  Parameters, gradients and Adam moments are FLAT fp32 device buffers owned by the caller,

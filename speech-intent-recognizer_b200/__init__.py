@@ -20,6 +20,7 @@ _EXPORTS = {
     "FSCIntentDataset": "scripts.dataset", "apply_spec_augmentation": "scripts.augment",
     "collate_fn": "scripts.train", "train_epoch": "scripts.train", "validate": "scripts.train",
     "DataParallelTrainer": "scripts.train", "CNNAudioGRU": "models.models", "IntentPipeline": "pipeline",
+    "predict": "scripts.test_model", "predict_batch": "scripts.test_model", "evaluate_loader": "scripts.evaluate",
 }
 
 

@@ -42,6 +42,8 @@ SIGNATURES = {
     "sir_model_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "sir_model_forward_convs": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sir_model_forward_head": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "sir_predict": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_void_p]),
     "sir_model_train_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_uint64, c_uint64, c_float,
                                         c_float, c_void_p, c_void_p]),
     "sir_model_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -340,3 +342,24 @@ def conv3x3_nhwc_split_f16(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     check(load_library().sir_conv3x3_nhwc_split_f16(ptr(x), ptr(w), ptr(out), B, H, W, cin, cout, stream_ptr()),
           "sir_conv3x3_nhwc_split_f16")
     return out
+
+
+def predict(logits: torch.Tensor, k: int = 3, labels: torch.Tensor = None, confusion: torch.Tensor = None,
+            correct: torch.Tensor = None):
+    """softmax / argmax / confidence / top-k of ``logits [B, C]`` (+ accuracy and confusion counts when ``labels`` is
+    given) in one launch -> ``(pred int32 [B], conf [B], topk_idx int32 [B,k], topk_prob [B,k])``."""
+    require_cuda(logits, "logits")
+    logits = logits.contiguous()
+    B, C = logits.shape
+    pred = torch.empty(B, device=logits.device, dtype=torch.int32)
+    conf = torch.empty(B, device=logits.device, dtype=torch.float32)
+    tk_i = torch.empty((B, k), device=logits.device, dtype=torch.int32) if k else None
+    tk_p = torch.empty((B, k), device=logits.device, dtype=torch.float32) if k else None
+    if labels is not None:
+        require_cuda(labels, "labels", torch.int64)
+    for t, n in ((confusion, "confusion"), (correct, "correct")):
+        if t is not None:
+            require_cuda(t, n, torch.int64)
+    check(load_library().sir_predict(ptr(logits), B, C, k, ptr(labels), ptr(pred), ptr(conf), ptr(tk_i), ptr(tk_p),
+                                     ptr(confusion), ptr(correct), stream_ptr()), "sir_predict")
+    return pred, conf, tk_i, tk_p

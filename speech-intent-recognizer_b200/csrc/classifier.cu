@@ -606,3 +606,104 @@ extern "C" int sir_pipeline_forward(sir_frontend* fe, sir_model* m, const float*
     if (rc != SIR_OK) return rc;
     return sir_model_forward(m, d_features, batch, out_frames, d_logits, stream);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Evaluation head: softmax, arg-max, confidence, top-k and (optionally) accuracy / confusion counts on the
+// device - the step right after the logits in scripts/test_model.py:121-156 (predict, get_top_predictions) and
+// scripts/evaluate.py:79-98 (arg-max, accuracy_score, confusion_matrix).  One warp per utterance.
+//   pred      = argmax(logits)           (first maximum, torch.argmax)
+//   conf      = softmax(logits)[pred]
+//   top-k     = argsort(probs)[::-1][:k] (numpy: among equal probabilities the HIGHER index comes first)
+// ---------------------------------------------------------------------------------------------------------
+namespace sir {
+
+constexpr int kMaxTopK = 8;
+
+__global__ void __launch_bounds__(128) predict_kernel(const float* __restrict__ logits, int B, int C, int k,
+                                                      const int64_t* __restrict__ labels, int32_t* __restrict__ pred,
+                                                      float* __restrict__ conf, int32_t* __restrict__ topk_idx,
+                                                      float* __restrict__ topk_prob, unsigned long long* __restrict__ confusion,
+                                                      unsigned long long* __restrict__ correct) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const float* row = logits + (int64_t)b * C;
+    float mx = -INFINITY;
+    int arg = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {
+        const float v = row[c];
+        if (v > mx) {
+            mx = v;
+            arg = c;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ov > mx || (ov == mx && oa < arg)) {
+            mx = ov;
+            arg = oa;
+        }
+    }
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += expf(row[c] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    if (lane == 0) {
+        if (pred) pred[b] = arg;
+        if (conf) conf[b] = expf(row[arg] - mx) * inv;
+        if (labels) {
+            const int y = (int)labels[b];
+            if (correct && y == arg) atomicAdd(correct, 1ull);
+            if (confusion && y >= 0 && y < C) atomicAdd(confusion + (int64_t)y * C + arg, 1ull);
+        }
+    }
+    if (k > 0 && topk_idx) {
+        int chosen[kMaxTopK];
+        for (int j = 0; j < k; ++j) {
+            float best = -1.f;
+            int bi = -1;
+            for (int c = lane; c < C; c += 32) {
+                bool taken = false;
+                for (int t = 0; t < j; ++t) taken |= chosen[t] == c;
+                if (taken) continue;
+                const float pv = expf(row[c] - mx) * inv;
+                if (pv > best || (pv == best && c > bi)) {
+                    best = pv;
+                    bi = c;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi > bi)) {
+                    best = ov;
+                    bi = oi;
+                }
+            }
+            chosen[j] = bi;
+            if (lane == 0) {
+                topk_idx[(int64_t)b * k + j] = bi;
+                if (topk_prob) topk_prob[(int64_t)b * k + j] = best;
+            }
+        }
+    }
+}
+
+}  // namespace sir
+
+extern "C" int sir_predict(const float* d_logits, int batch, int num_classes, int k, const int64_t* d_labels, int32_t* d_pred,
+                           float* d_conf, int32_t* d_topk_idx, float* d_topk_prob, int64_t* d_confusion, int64_t* d_correct,
+                           void* stream) {
+    if (!d_logits || batch < 0 || num_classes < 1) return fail(SIR_ERR_INVALID, "sir_predict: bad arguments");
+    if (k < 0 || k > kMaxTopK || k > num_classes) return fail(SIR_ERR_INVALID, "sir_predict: k must be in [0, min(%d, C)]", kMaxTopK);
+    if (batch == 0) return SIR_OK;
+    predict_kernel<<<(batch + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_logits, batch, num_classes, k, d_labels, d_pred, d_conf,
+                                                                     d_topk_idx, d_topk_prob, (unsigned long long*)d_confusion,
+                                                                     (unsigned long long*)d_correct);
+    SIR_CHECK_LAUNCH("predict_kernel");
+    return SIR_OK;
+}

@@ -235,3 +235,42 @@ def test_pcm16_ingest_is_bit_identical_to_float_path(fe, model):
     got = pipe.infer_host(host_pcm).clone()
     ref = pipe.infer_host(torch.from_numpy(as_float[:, :48000].copy()).pin_memory())
     assert torch.equal(got, ref)
+
+
+def test_evaluation_head_matches_reference_semantics(model):
+    """softmax / argmax / confidence / top-3 / accuracy / confusion counts (scripts/test_model.py:121-156, evaluate.py:79-98)."""
+    from oracle import eval_np
+    rng = np.random.default_rng(11)
+    logits = (rng.standard_normal((300, 31)) * 4).astype(np.float32)
+    logits[5] = 0.0                                   # all-equal row: argmax -> 0, top-k -> highest indices first
+    logits[6, :] = -200.0
+    logits[6, 7] = 30.0                               # saturated softmax: the zero-probability tail ties
+    logits[7, 3] = logits[7, 9] = 12.5                # tied maximum
+    labels = rng.integers(0, 31, 300).astype(np.int64)
+    conf_m = torch.zeros((31, 31), dtype=torch.int64, device="cuda")
+    correct = torch.zeros(1, dtype=torch.int64, device="cuda")
+    pred, conf, ti, tp = native.predict(dev(logits), k=3, labels=dev(labels), confusion=conf_m, correct=correct)
+    w_pred, w_conf, w_idx, w_prob = eval_np.predict(logits, 3)
+    assert np.array_equal(pred.cpu().numpy(), w_pred)
+    assert np.array_equal(ti.cpu().numpy(), w_idx)
+    assert np.max(np.abs(conf.cpu().numpy() - w_conf)) < 1e-6 and np.max(np.abs(tp.cpu().numpy() - w_prob)) < 1e-6
+    acc, cm = eval_np.accuracy_and_confusion(w_pred, labels, 31)
+    assert np.array_equal(conf_m.cpu().numpy(), cm) and int(correct) == int(round(acc * 300))
+    # the mirrors of the callers
+    tm = importlib.import_module("speech-intent-recognizer_b200.scripts.test_model")
+    ev = importlib.import_module("speech-intent-recognizer_b200.scripts.evaluate")
+    models = importlib.import_module("speech-intent-recognizer_b200.models.models")
+    m = models.CNNAudioGRU(31)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_weights(1234).items()}, strict=False)
+    m = m.cuda().eval()
+    g = golden("classifier")
+    label_map = {f"intent_{i}": i for i in range(31)}
+    res = tm.predict_batch(m, dev(g["x"]), label_map)
+    want_pred, want_conf, want_idx, _ = eval_np.predict(g["logits"], 3)
+    assert [r["predicted_label"] for r in res] == [f"intent_{i}" for i in want_pred]
+    assert max(abs(r["confidence"] - c) for r, c in zip(res, want_conf)) < 1e-3
+    assert [r["top_predictions"][0]["label"] for r in res] == [f"intent_{i}" for i in want_idx[:, 0]]
+    y = torch.from_numpy(want_pred.astype(np.int64))
+    y[0] = (y[0] + 1) % 31
+    acc, cm = ev.evaluate_loader(m, [(torch.from_numpy(g["x"]), y), (None, None)], 31)
+    assert abs(acc - (len(y) - 1) / len(y)) < 1e-9 and int(cm.sum()) == len(y) and int(cm.trace()) == len(y) - 1
