@@ -33,9 +33,11 @@ extern "C" {
 #define SIR_OUT_MEL_POWER 0    /* MelSpectrogram only                    (mel_transform attribute)          */
 #define SIR_OUT_MEL_DB 1       /* + AmplitudeToDB                        (amplitude_to_db(mel_transform(w))) */
 #define SIR_OUT_LOGMEL_NORM 2  /* + per-utterance (x-mean)/(std+1e-5)    (extract_features)                  */
+#define SIR_OUT_MFCC 3         /* dB with top_db floor + ortho DCT-II     (sir_frontend_mfcc only)           */
 
 typedef struct sir_frontend sir_frontend;
 typedef struct sir_model sir_model;
+typedef struct sir_resampler sir_resampler;
 
 const char* sir_last_error(void);
 int sir_version(void);
@@ -83,6 +85,31 @@ void sir_frontend_destroy(sir_frontend* fe);
 int sir_frontend_forward(sir_frontend* fe, const float* d_wave, int64_t wave_stride, const int32_t* d_lengths,
                          int n_samples, int batch, int max_samples, int mode, int out_frames, float* d_out,
                          const int32_t* d_masks, int32_t* d_status, void* stream);
+
+/* sir_frontend_mfcc / sir_preemphasis: the MFCC / pre-emphasis variant the north star names.  The reference itself
+ * computes log-mel only; the semantics follow the library it builds on:
+ * torchaudio.transforms.MFCC(sample_rate, n_mfcc, melkwargs={n_fft, hop_length, n_mels})
+ *   = MelSpectrogram -> AmplitudeToDB("power", top_db) with the floor at the per-utterance maximum - top_db ->
+ *     ortho DCT-II (create_dct)   TA:transforms/_transforms.py:634-718, TA:functional/functional.py:356-406,636-665
+ * fused into the same kernel: dB values are staged, the maximum is merged across the cluster, every frame is clamped
+ * and projected.  d_out [batch, n_mfcc, out_frames], zero beyond the utterance's frames; top_db <= 0 disables the floor.
+ * sir_preemphasis: y[n] = x[n] - coeff x[n-1] per row (torchaudio.functional.preemphasis), out of place. */
+int sir_frontend_mfcc(sir_frontend* fe, const float* d_wave, int64_t wave_stride, const int32_t* d_lengths, int n_samples,
+                      int batch, int max_samples, int n_mfcc, float top_db, int out_frames, float* d_out, int32_t* d_status,
+                      void* stream);
+int sir_preemphasis(const float* d_in, float* d_out, int64_t stride, int n_samples, int batch, float coeff, void* stream);
+
+/* sir_resampler_*  <->  torchaudio.transforms.Resample(orig_freq, new_freq) as the reference applies it before the
+ *                       frontend to files that are not 16 kHz   scripts/precompute_features.py:54-56,
+ *                       scripts/dataset.py:133-135, scripts/test_model.py:69-72
+ * sinc_interp_hann polyphase FIR (lowpass_filter_width 6, rolloff 0.99 are torchaudio's defaults), taps built in
+ * double precision.  Row b of d_out receives ceil(new * L_b / orig) samples (written to d_out_lengths[b] if given)
+ * followed by zeros up to n_out. */
+int sir_resampler_create(sir_resampler** out, int orig_freq, int new_freq, int lowpass_filter_width, double rolloff);
+void sir_resampler_destroy(sir_resampler* r);
+int64_t sir_resampler_output_length(const sir_resampler* r, int64_t n_in);
+int sir_resampler_forward(sir_resampler* r, const float* d_in, int64_t in_stride, const int32_t* d_in_lengths, int n_in,
+                          int batch, float* d_out, int64_t out_stride, int n_out, int32_t* d_out_lengths, void* stream);
 
 /* sir_frontend_forward_pcm16: the same, ingesting 16-bit PCM rows (the payload of the WAV files the reference reads):
  * samples are scaled by 1/32768 on load - bit-identical to torchaudio.load's normalisation

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 import torch
 
@@ -29,6 +29,14 @@ SIGNATURES = {
     "sir_frontend_destroy": (None, [c_void_p]),
     "sir_frontend_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sir_frontend_mfcc": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p,
+                                  c_void_p, c_void_p]),
+    "sir_preemphasis": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_void_p]),
+    "sir_resampler_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_double]),
+    "sir_resampler_destroy": (None, [c_void_p]),
+    "sir_resampler_output_length": (c_int64, [c_void_p, c_int64]),
+    "sir_resampler_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_void_p,
+                                      c_void_p]),
     "sir_frontend_forward_pcm16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                            c_void_p, c_void_p, c_void_p, c_void_p]),
     "sir_amplitude_to_db": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
@@ -164,6 +172,38 @@ class Frontend:
         check(entry(self._h, ptr(wave), stride, ptr(lengths), L, B, int(max_samples or 0), mode, out_frames, ptr(out),
                     ptr(masks), ptr(status), stream_ptr()), "sir_frontend_forward")
         return out
+
+
+def _frontend_mfcc(self, wave, n_mfcc=40, top_db=80.0, lengths=None, max_samples=0, out_frames=None, status=None):
+    """``wave [B, L]`` fp32 CUDA -> MFCC ``[B, n_mfcc, out_frames]`` with torchaudio.transforms.MFCC semantics."""
+    require_cuda(wave, "wave")
+    if wave.dim() != 2 or wave.stride(1) != 1:
+        raise NativeError("wave must be [batch, samples] with contiguous rows")
+    B, L = wave.shape
+    if lengths is not None:
+        require_cuda(lengths, "lengths", torch.int32)
+    if out_frames is None:
+        eff = min(L, max_samples) if max_samples and max_samples > 0 else L
+        out_frames = 1 + eff // self.hop
+    out = torch.empty((B, n_mfcc, out_frames), device=wave.device, dtype=torch.float32)
+    stride = wave.stride(0) if B > 1 else max(L, 1)
+    check(load_library().sir_frontend_mfcc(self._h, ptr(wave), stride, ptr(lengths), L, B, int(max_samples or 0), n_mfcc,
+                                           float(top_db or 0.0), out_frames, ptr(out), ptr(status), stream_ptr()),
+          "sir_frontend_mfcc")
+    return out
+
+
+Frontend.mfcc = _frontend_mfcc
+
+
+def preemphasis(wave: torch.Tensor, coeff: float = 0.97) -> torch.Tensor:
+    """``y[n] = x[n] - coeff * x[n-1]`` along the last axis of ``wave [B, L]`` (torchaudio.functional.preemphasis)."""
+    require_cuda(wave, "wave")
+    wave = wave.contiguous()
+    B, L = wave.shape
+    out = torch.empty_like(wave)
+    check(load_library().sir_preemphasis(ptr(wave), ptr(out), L, L, B, float(coeff), stream_ptr()), "sir_preemphasis")
+    return out
 
 
 def amplitude_to_db(x: torch.Tensor) -> torch.Tensor:
@@ -363,3 +403,43 @@ def predict(logits: torch.Tensor, k: int = 3, labels: torch.Tensor = None, confu
     check(load_library().sir_predict(ptr(logits), B, C, k, ptr(labels), ptr(pred), ptr(conf), ptr(tk_i), ptr(tk_p),
                                      ptr(confusion), ptr(correct), stream_ptr()), "sir_predict")
     return pred, conf, tk_i, tk_p
+
+
+class Resampler:
+    """``torchaudio.transforms.Resample(orig_freq, new_freq)`` on the GPU (sinc-Hann polyphase FIR)."""
+
+    def __init__(self, orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+        lib = load_library()
+        if not torch.cuda.is_available():
+            raise NativeError("no CUDA device: the resampler has no CPU path")
+        h = c_void_p()
+        check(lib.sir_resampler_create(ctypes.byref(h), int(orig_freq), int(new_freq), int(lowpass_filter_width),
+                                       float(rolloff)), "sir_resampler_create")
+        self._h = h
+        self.orig_freq, self.new_freq = orig_freq, new_freq
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and _lib is not None:
+            _lib.sir_resampler_destroy(h)
+
+    def output_length(self, n_in: int) -> int:
+        return int(load_library().sir_resampler_output_length(self._h, int(n_in)))
+
+    def __call__(self, wave: torch.Tensor, lengths: torch.Tensor = None, return_lengths: bool = False):
+        """``wave [..., L]`` fp32 CUDA (+ per-row ``lengths``) -> ``[..., ceil(new * L / orig)]``."""
+        require_cuda(wave, "wave")
+        lead = wave.shape[:-1]
+        w = wave.reshape(-1, wave.shape[-1]).contiguous()
+        B, L = w.shape
+        n_out = self.output_length(L)
+        out = torch.empty((B, n_out), device=w.device, dtype=torch.float32)
+        out_len = torch.empty(B, device=w.device, dtype=torch.int32) if return_lengths else None
+        if lengths is not None:
+            require_cuda(lengths, "lengths", torch.int32)
+        check(load_library().sir_resampler_forward(self._h, ptr(w), L, ptr(lengths), L, B, ptr(out), n_out, n_out, ptr(out_len),
+                                                   stream_ptr()), "sir_resampler_forward")
+        out = out.reshape(*lead, n_out)
+        return (out, out_len) if return_lengths else out
+
+    forward = __call__

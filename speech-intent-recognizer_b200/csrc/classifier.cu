@@ -613,7 +613,8 @@ extern "C" int sir_pipeline_forward(sir_frontend* fe, sir_model* m, const float*
 // scripts/evaluate.py:79-98 (arg-max, accuracy_score, confusion_matrix).  One warp per utterance.
 //   pred      = argmax(logits)           (first maximum, torch.argmax)
 //   conf      = softmax(logits)[pred]
-//   top-k     = argsort(probs)[::-1][:k] (numpy: among equal probabilities the HIGHER index comes first)
+//   top-k     = argsort(probs)[::-1][:k]; among exactly equal probabilities the HIGHER index comes first (what a
+//               stable argsort reversed gives; numpy's default introsort leaves that order unspecified)
 // ---------------------------------------------------------------------------------------------------------
 namespace sir {
 

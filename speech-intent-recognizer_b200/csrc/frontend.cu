@@ -22,6 +22,7 @@
 // frame the kernel sits at the fp32-issue ridge; see DESIGN.md for the arithmetic.
 #include <cooperative_groups.h>
 
+#include <cmath>
 #include <vector>
 
 #include "frontend_tables.h"
@@ -98,6 +99,13 @@ struct FrontendParams {
     int32_t* status;
     FrontendTables tables;
     int mel_weight_count;
+    // SIR_OUT_MFCC: dB values are staged in db_stage [batch][n_mels][stage_frames]; after the per-utterance maximum is
+    // known each frame is clamped at max - top_db and projected with dct [n_mels][n_mfcc] (ortho DCT-II)
+    float* db_stage;
+    int stage_frames;
+    const float* dct;
+    int n_mfcc;
+    float top_db;
 };
 
 // Interior frames read their 1024 samples straight from global memory: lane l takes the 8-byte words
@@ -167,8 +175,12 @@ __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_k
     const int n_groups = (T + kGroupFrames - 1) / kGroupFrames;
     const SampleT* __restrict__ row = static_cast<const SampleT*>(p.wave) + (int64_t)b * p.wave_stride;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & GlobalFrame<SampleT>::kAlignMask) == 0);
-    float* __restrict__ out = p.out + (int64_t)b * p.n_mels * p.out_frames;
-    const bool out_vec = (p.out_frames % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+    const bool mfcc = p.mode == SIR_OUT_MFCC;
+    // where the group loop writes its (un-normalised) values: the output itself, or the dB staging buffer for MFCC
+    const int row_stride = mfcc ? p.stage_frames : p.out_frames;
+    float* __restrict__ out = mfcc ? p.db_stage + (int64_t)b * p.n_mels * p.stage_frames
+                                   : p.out + (int64_t)b * p.n_mels * p.out_frames;
+    const bool out_vec = (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
     if (p.status && crank == 0 && tid == 0) p.status[b] = valid ? 0 : 1;
 
     float* tile = smem + kOffTile;
@@ -177,7 +189,7 @@ __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_k
     const int slot = 2 * warp + half;
     float* scr = smem + kOffScratch + slot * kFrameScratch;
 
-    float shift = 0.f, s1 = 0.f, s2 = 0.f;
+    float shift = 0.f, s1 = 0.f, s2 = 0.f, vmax = -INFINITY;
     bool have_shift = false;
     __syncthreads();                                        // tables visible
 
@@ -229,12 +241,13 @@ __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_k
             have_shift = true;
         }
         const int nslots = min(kGroupFrames, T - t0);
-        if (out_vec && nslots == kGroupFrames && t0 + kGroupFrames <= p.out_frames) {
+        if (out_vec && nslots == kGroupFrames && t0 + kGroupFrames <= row_stride) {
             for (int idx = tid; idx < p.n_mels * 2; idx += kFeThreads) {
                 const int m = idx >> 1, h4 = (idx & 1) * 4;
                 const float* tp = tile + m * kTileStride + h4;
                 const float4 v = make_float4(tp[0], tp[1], tp[2], tp[3]);
-                *reinterpret_cast<float4*>(out + (int64_t)m * p.out_frames + t0 + h4) = v;
+                *reinterpret_cast<float4*>(out + (int64_t)m * row_stride + t0 + h4) = v;
+                vmax = fmaxf(vmax, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
                 const float d0 = v.x - shift, d1 = v.y - shift, d2 = v.z - shift, d3 = v.w - shift;
                 s1 += (d0 + d1) + (d2 + d3);
                 s2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
@@ -244,7 +257,8 @@ __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_k
                 const int m = idx >> 3, s = idx & 7;
                 if (s < nslots) {
                     const float v = tile[m * kTileStride + s];
-                    if (t0 + s < p.out_frames) out[(int64_t)m * p.out_frames + t0 + s] = v;
+                    if (t0 + s < row_stride) out[(int64_t)m * row_stride + t0 + s] = v;
+                    vmax = fmaxf(vmax, v);
                     const float d = v - shift;
                     s1 += d;
                     s2 += d * d;
@@ -254,12 +268,54 @@ __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_k
         __syncthreads();                                    // tile consumed before the next group overwrites it
     }
 
-    if (p.mode != SIR_OUT_LOGMEL_NORM || !valid) {
+    if ((p.mode != SIR_OUT_LOGMEL_NORM && !mfcc) || !valid) {
         // zero padding (and whole rows of invalid utterances); rows are split over the cluster
         const int first = valid ? min(T, p.out_frames) : 0;
-        for (int m = crank; m < p.n_mels; m += csize)
-            for (int t = first + tid; t < p.out_frames; t += kFeThreads) out[(int64_t)m * p.out_frames + t] = 0.f;
+        const int rows = mfcc ? p.n_mfcc : p.n_mels;
+        float* __restrict__ o = p.out + (int64_t)b * rows * p.out_frames;
+        for (int m = crank; m < rows; m += csize)
+            for (int t = first + tid; t < p.out_frames; t += kFeThreads) o[(int64_t)m * p.out_frames + t] = 0.f;
         return;                                             // uniform over the whole cluster
+    }
+    if (mfcc) {
+        // ---- MFCC: per-utterance max over the cluster -> clamp at max - top_db -> DCT of every frame ------------
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 16));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 8));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 4));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 2));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 1));
+        __syncthreads();
+        if (lane == 0) red[warp] = vmax;
+        __syncthreads();
+        if (tid == 0) {
+            float mx = red[0];
+            for (int w = 1; w < kFeWarps; ++w) mx = fmaxf(mx, red[w]);
+            red[16] = mx;
+        }
+        float* s_dct = smem + kOffScratch;                  // the frame scratch is free now: [n_mels][n_mfcc]
+        for (int i = tid; i < p.n_mels * p.n_mfcc; i += kFeThreads) s_dct[i] = p.dct[i];
+        cluster.sync();
+        float mx = -INFINITY;
+        for (int r = 0; r < csize; ++r) mx = fmaxf(mx, *cluster.map_shared_rank(red + 16, r));
+        const float floor_db = p.top_db > 0.f ? mx - p.top_db : -INFINITY;
+        float* __restrict__ o = p.out + (int64_t)b * p.n_mfcc * p.out_frames;
+        for (int g = crank; g < n_groups; g += csize) {
+            const int t0 = g * kGroupFrames;
+            const int nslots = min(min(kGroupFrames, T - t0), p.out_frames - t0);
+            for (int idx = tid; idx < p.n_mfcc * kGroupFrames; idx += kFeThreads) {
+                const int c = idx >> 3, sl = idx & 7;
+                if (sl < nslots) {
+                    float acc = 0.f;
+                    for (int m = 0; m < p.n_mels; ++m)
+                        acc = fmaf(fmaxf(__ldcg(out + (int64_t)m * row_stride + t0 + sl), floor_db), s_dct[m * p.n_mfcc + c], acc);
+                    o[(int64_t)c * p.out_frames + t0 + sl] = acc;
+                }
+            }
+        }
+        for (int c = crank; c < p.n_mfcc; c += csize)
+            for (int t = T + tid; t < p.out_frames; t += kFeThreads) o[(int64_t)c * p.out_frames + t] = 0.f;
+        cluster.sync();                                     // keep every CTA's shared memory alive for its peers
+        return;
     }
 
     // ---- per-utterance statistics: CTA partial (n, mean, M2) -> cluster merge over DSMEM ----------------
@@ -405,6 +461,9 @@ struct sir_frontend {
     int mel_weight_count = 0;
     DeviceBuffer tables;
     FrontendTables dev{};
+    DeviceBuffer db_stage;       // MFCC: staged dB values
+    DeviceBuffer dct;            // MFCC: [n_mels][n_mfcc] ortho DCT-II
+    int dct_n_mfcc = 0;
 };
 
 extern "C" const char* sir_last_error(void) { return g_error; }
@@ -513,17 +572,19 @@ extern "C" int sir_frontend_create(sir_frontend** out, int sample_rate, int n_me
 extern "C" void sir_frontend_destroy(sir_frontend* fe) {
     if (!fe) return;
     fe->tables.release();
+    fe->db_stage.release();
+    fe->dct.release();
     delete fe;
 }
 
 static int frontend_launch(sir_frontend* fe, const void* d_wave, bool pcm16, int64_t wave_stride, const int32_t* d_lengths,
                            int n_samples, int batch, int max_samples, int mode, int out_frames, float* d_out,
-                           const int32_t* d_masks, int32_t* d_status, void* stream) {
+                           const int32_t* d_masks, int32_t* d_status, void* stream, int n_mfcc = 0, float top_db = 0.f) {
     if (!fe || !d_wave || !d_out) return fail(SIR_ERR_INVALID, "sir_frontend_forward: NULL handle or buffer");
     if (batch < 0 || n_samples < 0 || out_frames < 1 || wave_stride < n_samples)
         return fail(SIR_ERR_INVALID, "sir_frontend_forward: bad sizes (batch %d, n_samples %d, out_frames %d)", batch,
                     n_samples, out_frames);
-    if (mode < SIR_OUT_MEL_POWER || mode > SIR_OUT_LOGMEL_NORM) return fail(SIR_ERR_INVALID, "bad mode %d", mode);
+    if (mode < SIR_OUT_MEL_POWER || mode > SIR_OUT_MFCC) return fail(SIR_ERR_INVALID, "bad mode %d", mode);
     if (d_masks && mode != SIR_OUT_LOGMEL_NORM)
         return fail(SIR_ERR_INVALID, "mask bands are applied to normalised features only");
     if (batch == 0) return SIR_OK;
@@ -541,6 +602,33 @@ static int frontend_launch(sir_frontend* fe, const void* d_wave, bool pcm16, int
     p.status = d_status;
     p.tables = fe->dev;
     p.mel_weight_count = fe->mel_weight_count;
+    if (mode == SIR_OUT_MFCC) {
+        if (n_mfcc < 1 || n_mfcc > fe->n_mels || fe->n_mels * n_mfcc > kGroupFrames * kFrameScratch)
+            return fail(SIR_ERR_INVALID, "sir_frontend_mfcc: n_mfcc must be in [1, n_mels] (got %d)", n_mfcc);
+        if (fe->dct_n_mfcc != n_mfcc) {                      // create_dct(n_mfcc, n_mels, "ortho"), TA:functional.py:636-665
+            const double pi = 3.14159265358979323846;
+            std::vector<float> h((size_t)fe->n_mels * n_mfcc);
+            for (int m = 0; m < fe->n_mels; ++m)
+                for (int c = 0; c < n_mfcc; ++c) {
+                    double v = std::cos(pi / fe->n_mels * (m + 0.5) * c) * std::sqrt(2.0 / fe->n_mels);
+                    if (c == 0) v *= 1.0 / std::sqrt(2.0);
+                    h[(size_t)m * n_mfcc + c] = (float)v;
+                }
+            int rc = fe->dct.reserve(h.size() * sizeof(float));
+            if (rc != SIR_OK) return rc;
+            SIR_CUDA(cudaMemcpyAsync(fe->dct.ptr, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+            SIR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));      // h goes out of scope
+            fe->dct_n_mfcc = n_mfcc;
+        }
+        const int eff0 = max_samples > 0 && max_samples < n_samples ? max_samples : n_samples;
+        p.stage_frames = ((1 + eff0 / kHop) + 3) & ~3;
+        int rc = fe->db_stage.reserve((size_t)batch * fe->n_mels * p.stage_frames * sizeof(float));
+        if (rc != SIR_OK) return rc;
+        p.db_stage = (float*)fe->db_stage.ptr;
+        p.dct = (const float*)fe->dct.ptr;
+        p.n_mfcc = n_mfcc;
+        p.top_db = top_db;
+    }
     // cluster size: enough CTAs for ~2 waves of 3 CTAs/SM, never more CTAs than 8-frame groups
     int eff = max_samples > 0 && max_samples < n_samples ? max_samples : n_samples;
     const int groups = (1 + eff / kHop + kGroupFrames - 1) / kGroupFrames;
@@ -575,6 +663,35 @@ extern "C" int sir_frontend_forward(sir_frontend* fe, const float* d_wave, int64
                                     void* stream) {
     return frontend_launch(fe, d_wave, false, wave_stride, d_lengths, n_samples, batch, max_samples, mode, out_frames, d_out,
                            d_masks, d_status, stream);
+}
+
+extern "C" int sir_frontend_mfcc(sir_frontend* fe, const float* d_wave, int64_t wave_stride, const int32_t* d_lengths,
+                                 int n_samples, int batch, int max_samples, int n_mfcc, float top_db, int out_frames,
+                                 float* d_out, int32_t* d_status, void* stream) {
+    return frontend_launch(fe, d_wave, false, wave_stride, d_lengths, n_samples, batch, max_samples, SIR_OUT_MFCC, out_frames,
+                           d_out, nullptr, d_status, stream, n_mfcc, top_db);
+}
+
+// y[n] = x[n] - coeff * x[n-1], y[0] = x[0] per row (torchaudio.functional.preemphasis, TA:functional.py:2426)
+namespace sir {
+__global__ void preemphasis_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t stride, int n, float coeff) {
+    const float* row = in + (int64_t)blockIdx.y * stride;
+    float* orow = out + (int64_t)blockIdx.y * stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        orow[i] = i > 0 ? row[i] - coeff * row[i - 1] : row[i];
+}
+}  // namespace sir
+
+extern "C" int sir_preemphasis(const float* d_in, float* d_out, int64_t stride, int n_samples, int batch, float coeff,
+                               void* stream) {
+    if (!d_in || !d_out || d_in == d_out || n_samples < 0 || batch < 0 || stride < n_samples)
+        return fail(SIR_ERR_INVALID, "sir_preemphasis: bad arguments (in-place is not supported)");
+    if (batch == 0 || n_samples == 0) return SIR_OK;
+    if (batch > 65535) return fail(SIR_ERR_UNSUPPORTED, "sir_preemphasis: batch > 65535");
+    dim3 grid((unsigned)((n_samples + 1023) / 1024 < 64 ? (n_samples + 1023) / 1024 : 64), (unsigned)batch);
+    preemphasis_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, stride, n_samples, coeff);
+    SIR_CHECK_LAUNCH("preemphasis_kernel");
+    return SIR_OK;
 }
 
 extern "C" int sir_frontend_forward_pcm16(sir_frontend* fe, const int16_t* d_pcm, int64_t wave_stride,
@@ -619,5 +736,123 @@ extern "C" int sir_features_finalize(const float* d_in, int batch, int n_mels, i
     features_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, n_mels, in_frames, d_frames, d_masks,
                                                                      out_frames, d_out);
     SIR_CHECK_LAUNCH("features_finalize_kernel");
+    return SIR_OK;
+}
+
+// ---- polyphase sinc resampler ---------------------------------------------------------------------------------
+// torchaudio.transforms.Resample(orig, new) (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99) - the step the
+// reference applies before the frontend when a file is not 16 kHz (scripts/precompute_features.py:54-56,
+// scripts/test_model.py:69-72; the TTS clips are 24 kHz).  out[m * new + p] = sum_k kernel[p][k] x_pad[m * orig + k],
+// x_pad = x padded by (width, width + orig) zeros; one thread per output sample, the kernel table in shared memory.
+namespace sir {
+__global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__ in, int64_t in_stride, const int32_t* __restrict__ in_len,
+                                                       int n_in, const float* __restrict__ taps, int n_taps, int width, int orig,
+                                                       int nw, int staged, float* __restrict__ out, int64_t out_stride,
+                                                       int n_out_cap, int32_t* __restrict__ out_len) {
+    extern __shared__ float s_taps_buf[];
+    if (staged) {                                          // small tap tables live in shared memory, big ones in L2
+        for (int i = threadIdx.x; i < nw * n_taps; i += blockDim.x) s_taps_buf[i] = taps[i];
+        __syncthreads();
+    }
+    const float* __restrict__ s_taps = staged ? s_taps_buf : taps;
+    const int b = blockIdx.y;
+    const int L = in_len ? min(in_len[b], n_in) : n_in;
+    const int n_out = (int)(((int64_t)nw * L + orig - 1) / orig);              // ceil(new * L / orig)
+    if (out_len && blockIdx.x == 0 && threadIdx.x == 0) out_len[b] = n_out;
+    const float* __restrict__ row = in + (int64_t)b * in_stride;
+    float* __restrict__ orow = out + (int64_t)b * out_stride;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_out_cap; o += gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        if (o < n_out) {
+            const int m = o / nw, p = o - m * nw;
+            const int base = m * orig - width;
+            const float* __restrict__ k = s_taps + p * n_taps;
+            for (int j = 0; j < n_taps; ++j) {
+                const int i = base + j;
+                if (i >= 0 && i < L) acc = fmaf(k[j], __ldg(row + i), acc);
+            }
+        }
+        orow[o] = acc;
+    }
+}
+}  // namespace sir
+
+struct sir_resampler {
+    int orig = 1, nw = 1, width = 0, n_taps = 0;
+    DeviceBuffer taps;
+};
+
+extern "C" int sir_resampler_create(sir_resampler** out, int orig_freq, int new_freq, int lowpass_filter_width, double rolloff) {
+    if (!out) return fail(SIR_ERR_INVALID, "sir_resampler_create: out is NULL");
+    *out = nullptr;
+    if (orig_freq < 1 || new_freq < 1 || lowpass_filter_width < 1 || !(rolloff > 0.0 && rolloff <= 1.0))
+        return fail(SIR_ERR_INVALID, "sir_resampler_create: bad arguments");
+    int a = orig_freq, b2 = new_freq;
+    while (b2) {
+        const int t = a % b2;
+        a = b2;
+        b2 = t;
+    }
+    const int orig = orig_freq / a, nw = new_freq / a;
+    const double pi = 3.14159265358979323846;
+    const double base_freq = (orig < nw ? orig : nw) * rolloff;
+    const int width = (int)std::ceil(lowpass_filter_width * orig / base_freq);
+    const int n_taps = 2 * width + orig;
+    if ((size_t)nw * n_taps > ((size_t)1 << 26))
+        return fail(SIR_ERR_UNSUPPORTED, "sir_resampler_create: %d x %d taps", nw, n_taps);
+    std::vector<float> h((size_t)nw * n_taps);
+    for (int p = 0; p < nw; ++p)
+        for (int j = 0; j < n_taps; ++j) {
+            double t = ((double)(-p) / nw + (double)(j - width) / orig) * base_freq;
+            t = t < -lowpass_filter_width ? -lowpass_filter_width : (t > lowpass_filter_width ? lowpass_filter_width : t);
+            const double c = std::cos(t * pi / lowpass_filter_width / 2);
+            const double window = c * c;
+            const double tp = t * pi;
+            const double sinc = tp == 0.0 ? 1.0 : std::sin(tp) / tp;
+            h[(size_t)p * n_taps + j] = (float)(sinc * window * (base_freq / orig));
+        }
+    sir_resampler* r = new sir_resampler();
+    r->orig = orig;
+    r->nw = nw;
+    r->width = width;
+    r->n_taps = n_taps;
+    int rc = r->taps.reserve(h.size() * sizeof(float));
+    if (rc == SIR_OK && cudaMemcpy(r->taps.ptr, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+        rc = fail(SIR_ERR_CUDA, "sir_resampler_create: tap upload failed");
+    if (rc != SIR_OK) {
+        r->taps.release();
+        delete r;
+        return rc;
+    }
+    if ((size_t)nw * n_taps * sizeof(float) > 48 * 1024 && (size_t)nw * n_taps * sizeof(float) <= 160 * 1024)
+        cudaFuncSetAttribute(sir::resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)nw * n_taps * sizeof(float)));
+    *out = r;
+    return SIR_OK;
+}
+
+extern "C" void sir_resampler_destroy(sir_resampler* r) {
+    if (!r) return;
+    r->taps.release();
+    delete r;
+}
+
+extern "C" int64_t sir_resampler_output_length(const sir_resampler* r, int64_t n_in) {
+    return r ? (n_in * r->nw + r->orig - 1) / r->orig : 0;
+}
+
+extern "C" int sir_resampler_forward(sir_resampler* r, const float* d_in, int64_t in_stride, const int32_t* d_in_lengths, int n_in,
+                                     int batch, float* d_out, int64_t out_stride, int n_out, int32_t* d_out_lengths, void* stream) {
+    if (!r || !d_in || !d_out || batch < 0 || n_in < 0 || n_out < 0 || in_stride < n_in || out_stride < n_out)
+        return fail(SIR_ERR_INVALID, "sir_resampler_forward: bad arguments");
+    if (batch == 0 || n_out == 0) return SIR_OK;
+    if (batch > 65535) return fail(SIR_ERR_UNSUPPORTED, "sir_resampler_forward: batch > 65535");
+    size_t smem = (size_t)r->nw * r->n_taps * sizeof(float);
+    const bool staged = smem <= 160 * 1024;                 // small rational ratios (24 k -> 16 k: 2 x 23 taps) live in smem
+    if (!staged) smem = 0;                                  // e.g. 22.05 k -> 16 k: 320 x 459 taps stay in global / L2
+    dim3 grid((unsigned)((n_out + 255) / 256 < 148 ? (n_out + 255) / 256 : 148), (unsigned)batch);
+    sir::resample_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d_in, in_stride, d_in_lengths, n_in, (const float*)r->taps.ptr,
+                                                                    r->n_taps, r->width, r->orig, r->nw, staged ? 1 : 0, d_out, out_stride,
+                                                                    n_out, d_out_lengths);
+    SIR_CHECK_LAUNCH("resample_kernel");
     return SIR_OK;
 }

@@ -72,6 +72,7 @@ class AudioFeatureExtractor:
         self._fe = _native.Frontend(sample_rate, n_mels, n_fft, hop_length)
         self.mel_transform = _MelTransform(self._fe)
         self.amplitude_to_db = _AmplitudeToDB()
+        self._resamplers = {}
 
     # -- batched entry (new) ------------------------------------------------------------------------------
     def extract_batch(self, waveforms: torch.Tensor, lengths: torch.Tensor = None, max_duration=5.0,
@@ -93,9 +94,11 @@ class AudioFeatureExtractor:
         waveform, sr = load_audio(audio_path)
         if waveform.shape[0] > 1:
             waveform = torch.mean(waveform, dim=0, keepdim=True)
-        if sr != self.sample_rate:
-            import torchaudio
-            waveform = torchaudio.functional.resample(waveform.cuda(), sr, self.sample_rate)
+        if sr != self.sample_rate:                               # reference: torchaudio.transforms.Resample (:54-56)
+            key = (int(sr), int(self.sample_rate))
+            if key not in self._resamplers:
+                self._resamplers[key] = _native.Resampler(*key)
+            waveform = self._resamplers[key](waveform.to(device="cuda", dtype=torch.float32))
         return waveform
 
     def extract_features(self, audio_path, max_duration=5.0):

@@ -127,3 +127,21 @@ def test_weights_are_discriminative():
     top = np.sort(y, axis=1)
     assert len(counts) >= 12 and max(counts.values()) <= 20
     assert np.median(top[:, -1] - top[:, -2]) > 0.2
+
+
+def test_mfcc_preemphasis_resample_restatements_match_torchaudio():
+    """The section-8(f) rows have no counterpart inside the reference tree; their oracle is pinned by a live differential
+    test against the torchaudio the reference builds on (MFCC, preemphasis, Resample)."""
+    import torch
+    import torchaudio
+    w = synth.speech_like(3, 2, 30000)
+    for n_mels, n_mfcc in ((64, 40), (80, 13)):
+        m = torchaudio.transforms.MFCC(sample_rate=16000, n_mfcc=n_mfcc, melkwargs=dict(n_fft=1024, hop_length=512, n_mels=n_mels))
+        want = m(torch.from_numpy(w[0:1]))[0].numpy()
+        assert rel_to_scale(logmel_np.mfcc(w[0], n_mfcc=n_mfcc, n_mels=n_mels), want) < 1e-5
+    assert np.array_equal(logmel_np.preemphasis(w), torchaudio.functional.preemphasis(torch.from_numpy(w), 0.97).numpy())
+    x = synth.speech_like(4, 1, 36001)[0]
+    for orig in (24000, 22050, 8000):
+        want = torchaudio.transforms.Resample(orig, 16000)(torch.from_numpy(x)).numpy()
+        got = logmel_np.resample(x, orig, 16000)
+        assert got.shape == want.shape and np.max(np.abs(got - want)) < 1e-5, orig
