@@ -184,7 +184,7 @@ class CpuArm:
         return steps, feat_s, fwd_s
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """--impl reference: the reference's own CPU implementation of the path, all host threads, rank 0 only.
     One step = the full configs[1] batch (256 utterances x 3 s)."""
     if rank != 0:
@@ -215,10 +215,25 @@ def run_reference(args, rank, world):
                          "host_cpus": os.cpu_count() or 1, "torch": torch.__version__},
         "e2e": {"value": value, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    out.emit(line)
+
+
+class JsonStdout:
+    """The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version banner on
+    init), so file descriptor 1 is pointed at stderr for the whole run and the result line goes to the saved fd."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.fd = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, obj):
+        sys.stdout.flush()
+        os.write(self.fd, (json.dumps(obj) + "\n").encode())
 
 
 def main():
+    out = JsonStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -228,6 +243,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sub-batches", type=int, default=1, help="sub-batches of the host-buffer pipeline (e2e)")
     ap.add_argument("--depth", type=int, default=2, help="batches in flight in the host-buffer pipeline (e2e)")
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams consecutive steps alternate over (value)")
+    ap.add_argument("--numa-bind", type=int, default=1, help="bind each rank to its GPU's CPU cores before allocating pinned buffers")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work spent on the cpu_baseline sample")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -236,7 +253,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import torch.distributed as dist
@@ -250,6 +267,9 @@ def main():
     pre = importlib.import_module("speech-intent-recognizer_b200.scripts.precompute_features")
     models = importlib.import_module("speech-intent-recognizer_b200.models.models")
 
+    pipe_mod = importlib.import_module("speech-intent-recognizer_b200.pipeline")
+    all_cpus = os.sched_getaffinity(0)
+    bound_cpus = pipe_mod.bind_host_to_gpu(local) if args.numa_bind else None
     B = args.batch
     extractor = pre.AudioFeatureExtractor()                      # the reference-facing objects (public API)
     sd = native_synth.make_weights(1234)
@@ -268,6 +288,24 @@ def main():
     dev_waves = [(host.cuda() * (1.0 - 0.1 * i)).contiguous() for i in range(n_rot)]
     feats = torch.empty((B, N_MELS, OUT_FRAMES), device="cuda")
     stream = torch.cuda.current_stream()
+    # consecutive steps (independent batches) alternate over `--streams` CUDA streams, each with its own feature
+    # buffer and - inside the model handle - its own workspace: the latency-bound GRU recurrence of step i overlaps
+    # the frontend and conv stack of step i+1.  Every step still runs every kernel; all of them finish inside the
+    # timed region (the timing stream waits for every worker stream before the closing event).
+    workers = [torch.cuda.Stream() for _ in range(max(1, args.streams))]
+    feats_w = [torch.empty((B, N_MELS, OUT_FRAMES), device="cuda") for _ in workers]
+
+    def run_steps(n):
+        for w in workers:
+            w.wait_stream(stream)
+        res = None
+        for i in range(n):
+            k = i % len(workers)
+            with torch.cuda.stream(workers[k]):
+                res = step_device(dev_waves[i % n_rot], feats_w[k])
+        for w in workers:
+            stream.wait_stream(w)
+        return res
 
     def barrier():
         if world > 1:
@@ -276,6 +314,7 @@ def main():
 
     for i in range(args.warmup):
         logits = step_device(dev_waves[i % n_rot], feats)
+    run_steps(max(args.warmup, 2 * len(workers)))
     barrier()
 
     # ---- value: K steps, inputs resident in HBM ------------------------------------------------------------
@@ -286,8 +325,7 @@ def main():
     barrier()
     sampler.mark()
     e0.record(stream)
-    for i in range(args.steps):
-        logits = step_device(dev_waves[i % n_rot], feats)
+    logits = run_steps(args.steps)
     e1.record(stream)
     barrier()
     sampler.mark()
@@ -297,7 +335,6 @@ def main():
     # ---- e2e: host buffers, H2D + pipeline + D2H each step, public API -------------------------------------
     # IntentPipeline.infer_host: pinned host waveforms in, pinned host logits out; the H2D copy of sub-batch i+1
     # overlaps the frontend + conv stack of sub-batch i; it synchronises before returning (the caller reads logits).
-    pipe_mod = importlib.import_module("speech-intent-recognizer_b200.pipeline")
     pipe = pipe_mod.IntentPipeline(extractor, model, sub_batches=args.sub_batches, out_frames=OUT_FRAMES, max_duration=5.0,
                                    depth=args.depth)
 
@@ -399,6 +436,11 @@ def main():
             "config": {"workload": "configs[1]: 256 utt x 3 s @16 kHz per GPU, config.yaml model "
                                    "(64 mel, 200 frames, 31 classes), seeded random-init weights",
                        "batch_per_gpu": B, "samples": SAMPLES, "parallelism": f"batch-sharded x{world}, no collective",
+                       "concurrency": f"consecutive steps alternate over {len(workers)} CUDA streams (value) / {args.depth} "
+                                      "pipeline slots with their own streams (e2e); `stages` are timed serially on one "
+                                      "stream, so their sum exceeds ms_per_step",
+                       "host_binding": (f"rank pinned to the {len(bound_cpus)} CPU cores NVML lists for its GPU before "
+                                        "allocating pinned buffers" if bound_cpus else "none"),
                        "l2_policy": f"{n_rot} rotating input batches ({n_rot * B * SAMPLES * 4 / 1e6:.0f} MB > 126 MB L2)"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": total_utts / e2e_s, "unit": "utt/s", "h2d_bytes_per_step": B * SAMPLES * 4,
@@ -413,6 +455,7 @@ def main():
             "roofline": roofline, "frontend_roofline": fr, "rooflines": rooflines, "stages": stage_out,
         }
         if not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)                     # the CPU arm gets every host core again
             arm = CpuArm(native_synth, B)
             arm.step()
             n_steps, fs, ws = arm.run_for(args.cpu_seconds)
@@ -422,7 +465,7 @@ def main():
                                               f"work): per-utterance torchaudio feature loop {fs / n_steps:.3f} s + "
                                               f"CNNAudioGRU fp32 batched forward {ws / n_steps:.3f} s per pass",
                                     "host_cpus": os.cpu_count() or 1}
-        print(json.dumps(line), flush=True)
+        out.emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

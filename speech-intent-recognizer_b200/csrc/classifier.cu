@@ -426,7 +426,7 @@ extern "C" void sir_model_destroy(sir_model* m) {
     m->flat.release();
     m->packed.release();
     m->halves.release();
-    m->work.release();
+    for (auto& w : m->work) w.release();
     m->train_ws.release();
     delete m;
 }
@@ -536,15 +536,24 @@ int model_forward_chunk(sir_model* m, const Workspace& ws, const float* feat, in
 
 }  // namespace sir
 
-static int model_prepare(sir_model* m, int batch, int n_frames, Workspace& ws, int& chunk) {   // (re)carves the workspace
+static int model_prepare(sir_model* m, int batch, int n_frames, Workspace& ws, int& chunk, void* stream) {   // (re)carves the workspace
     if (!m->loaded) return fail(SIR_ERR_INVALID, "sir_model_forward: weights not loaded");
     if (n_frames < 8) return fail(SIR_ERR_INVALID, "sir_model_forward: n_frames must be >= 8 (got %d)", n_frames);
     chunk = batch < kModelChunk ? batch : kModelChunk;
     Workspace probe;
     const size_t need = carve(probe, nullptr, chunk, m->n_mels, n_frames, m->gru_in);
-    int rc = m->work.reserve(need);
+    int slot = 0;
+    while (slot < m->work_used && m->work_stream[slot] != stream) ++slot;
+    if (slot == m->work_used) {
+        if (slot == sir_model::kMaxStreams)
+            return fail(SIR_ERR_UNSUPPORTED, "sir_model_forward: one handle serves at most %d streams; create another handle",
+                        sir_model::kMaxStreams);
+        m->work_stream[slot] = stream;
+        ++m->work_used;
+    }
+    int rc = m->work[slot].reserve(need);
     if (rc != SIR_OK) return rc;
-    carve(ws, (uint8_t*)m->work.ptr, chunk, m->n_mels, n_frames, m->gru_in);
+    carve(ws, (uint8_t*)m->work[slot].ptr, chunk, m->n_mels, n_frames, m->gru_in);
     return SIR_OK;
 }
 
@@ -555,7 +564,7 @@ extern "C" int sir_model_forward(sir_model* m, const float* d_features, int batc
     if (batch == 0) return SIR_OK;
     Workspace ws;
     int chunk = 0;
-    int rc = model_prepare(m, batch, n_frames, ws, chunk);
+    int rc = model_prepare(m, batch, n_frames, ws, chunk, stream);
     if (rc != SIR_OK) return rc;
     for (int b0 = 0; b0 < batch; b0 += chunk) {
         const int nb = batch - b0 < chunk ? batch - b0 : chunk;
@@ -578,7 +587,7 @@ extern "C" int sir_model_forward_convs(sir_model* m, const float* d_features, in
     if (count == 0) return SIR_OK;
     Workspace ws;
     int chunk = 0;
-    int rc = model_prepare(m, batch_total, n_frames, ws, chunk);
+    int rc = model_prepare(m, batch_total, n_frames, ws, chunk, stream);
     if (rc != SIR_OK) return rc;
     return model_forward_convs(m, ws, d_features, first, count, n_frames, (cudaStream_t)stream);
 }
@@ -590,7 +599,7 @@ extern "C" int sir_model_forward_head(sir_model* m, int batch_total, int n_frame
                     batch_total);
     Workspace ws;
     int chunk = 0;
-    int rc = model_prepare(m, batch_total, n_frames, ws, chunk);
+    int rc = model_prepare(m, batch_total, n_frames, ws, chunk, stream);
     if (rc != SIR_OK) return rc;
     return model_forward_head(m, ws, batch_total, n_frames, d_logits, (cudaStream_t)stream);
 }

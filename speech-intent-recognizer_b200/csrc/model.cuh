@@ -87,7 +87,13 @@ struct sir_model {
     sir::DeviceBuffer flat;      // the model's own copy of the flat parameters (eval path)
     sir::DeviceBuffer packed;    // repacked fp32 parameters
     sir::DeviceBuffer halves;    // fp16 (hi, lo) operands of the tensor-core contractions
-    sir::DeviceBuffer work;      // eval activations
+    // eval activations: one workspace per stream the handle is called on, so that batches enqueued on different
+    // streams (IntentPipeline slots, bench.py's alternating steps) run concurrently on the GPU - the latency-bound
+    // GRU recurrence of one batch then overlaps the frontend / conv stack of the next
+    static constexpr int kMaxStreams = 8;
+    sir::DeviceBuffer work[kMaxStreams];
+    void* work_stream[kMaxStreams] = {};
+    int work_used = 0;
     sir::DeviceBuffer train_ws;  // training activations + backward scratch
     // fp32 pointers into `packed`
     float *w1 = nullptr, *sh1 = nullptr, *sh2 = nullptr, *sh3 = nullptr;
