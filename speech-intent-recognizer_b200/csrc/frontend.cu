@@ -5,23 +5,21 @@
 // reference and the torchaudio calls behind them with ONE kernel launch for a batch.
 //
 // Mapping
-//   * one thread-block CLUSTER per utterance (1, 2, 4 or 8 CTAs, picked so the grid covers the 148 SMs a
-//     few times over even for small batches); the cluster's CTAs take 8-frame groups round-robin;
+//   * work item = (utterance, group of 8 frames); a persistent grid (3 CTAs per SM) draws items from a ticket
+//     counter, so every SM is busy until the last item whatever the batch size;
 //   * each HALF-WARP owns one frame and reads its 1024 samples straight from global memory (128 contiguous
 //     bytes per half-warp request; the 50 % overlap with the neighbouring frame, held by the other half of
 //     the same warp, is served by L1/L2, so HBM sees every sample once); only the first and last frame of an
 //     utterance take the scalar path that resolves torch.stft's reflect padding;
 //   * per frame: 512-point complex FFT as 32-point x 16-point register FFTs with one
 //     shared-memory transposition (logmel_frame.cuh), real-FFT post-pass, power, sparse mel taps, log10;
-//   * un-normalised values go to the output through an 8-frame shared tile (32-byte row segments), the
-//     per-utterance mean / unbiased std are combined across the cluster through distributed shared memory
-//     (shifted sums + Chan's merge), then each CTA re-reads its own L2-resident values, normalises, applies
-//     the mask bands and writes the zero padding.  HBM sees each sample once and each feature once.
+//   * un-normalised values go to the output through an 8-frame shared tile (32-byte row segments) and the item's
+//     partial statistics (shifted sums) to a small global array; the CTA whose item completes the utterance (atomic
+//     count) merges the partials in group order (Chan's formula, fp64), re-reads the utterance's L2-resident values,
+//     normalises, applies the mask bands and writes the zero padding.  HBM sees each sample once and each feature once.
 //
 // Roofline: HBM-bound by intent (4 L + 4 n_mels T bytes per utterance), but at ~19 k fp32 instructions per
 // frame the kernel sits at the fp32-issue ridge; see DESIGN.md for the arithmetic.
-#include <cooperative_groups.h>
-
 #include <cmath>
 #include <vector>
 
@@ -29,8 +27,6 @@
 #include "logmel_frame.cuh"
 #include "philox.cuh"
 #include "sir_common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace sir {
 
@@ -106,6 +102,14 @@ struct FrontendParams {
     const float* dct;
     int n_mfcc;
     float top_db;
+    // work items: utterance i / groups_max, 8-frame group i % groups_max; per-item partial statistics and the
+    // per-utterance count of finished items (zero between launches)
+    int batch;
+    int groups_max;
+    struct ItemPartial* partials;
+    int* counters;
+    unsigned long long* work_counter;   // ticket counter (never reset) and the first ticket of this launch
+    unsigned long long work_base;
 };
 
 // Interior frames read their 1024 samples straight from global memory: lane l takes the 8-byte words
@@ -140,16 +144,30 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// One (utterance, 8-frame group) work item's contribution to the utterance statistics, written to global memory by
+// the CTA that processed the item and merged in group order by the CTA that finishes the utterance.
+struct alignas(32) ItemPartial {
+    double s1, s2;             // sums of (v - shift) and (v - shift)^2 over the item's values
+    float shift, vmax;
+    int n, pad;                // number of values
+};
+
+// Persistent grid (SIR_FE_MIN_CTAS CTAs per SM) over work items: item i is the 8-frame group i % groups_max of
+// utterance i / groups_max.  CTAs DRAW items from a global ticket counter (the next ticket is fetched while the
+// current item computes), so the SMs finish within one item of each other whatever the batch size and whatever an
+// item costs (a cluster per utterance left 42 % of the machine idle at 256 utterances: 512 CTAs of 6 groups on 444
+// slots; a static round-robin let the CTAs that lag - reflect-padded first/last groups, finisher work - collect
+// every later finisher job too).  The CTA whose item completes an utterance - an atomic counter per utterance,
+// reset by that CTA for the next launch - merges the item partials in GROUP order (deterministic whichever CTA it
+// is), re-reads the utterance's still-L2-resident values, normalises, masks and pads them.
+// Tickets: the counter is never reset; every CTA draws (its items + 1) tickets, so a launch consumes exactly
+// total_items + gridDim.x of them and the host passes the first ticket of the launch (work_base).
 template <typename SampleT>
 __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_kernel(const FrontendParams p) {
     extern __shared__ __align__(16) float smem[];
-    cg::cluster_group cluster = cg::this_cluster();
-    const int csize = (int)cluster.num_blocks();
-    const int crank = (int)cluster.block_rank();
-    const int b = blockIdx.x / csize;
     const int tid = threadIdx.x;
 
-    // ---- constants into shared memory ------------------------------------------------------------------
+    // ---- constants into shared memory (once per CTA) -----------------------------------------------------
     for (int i = tid; i < 1024; i += kFeThreads) {
         smem[kOffWindow + i] = p.tables.window[i];
         smem[kOffTw512 + i] = p.tables.tw512[i];
@@ -167,33 +185,39 @@ __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_k
     const FrontendTables st{smem + kOffWindow, smem + kOffTw512, smem + kOffTw1024, s_mel_start,
                             s_mel_count,       s_mel_offset,     smem + kOffMelWeight};
 
-    // ---- this utterance --------------------------------------------------------------------------------
-    int L = p.lengths ? min(p.lengths[b], p.n_samples) : p.n_samples;
-    if (p.max_samples > 0) L = min(L, p.max_samples);
-    const bool valid = L > kNfft / 2;                       // reflect padding needs L > 512
-    const int T = valid ? 1 + L / kHop : 0;
-    const int n_groups = (T + kGroupFrames - 1) / kGroupFrames;
-    const SampleT* __restrict__ row = static_cast<const SampleT*>(p.wave) + (int64_t)b * p.wave_stride;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & GlobalFrame<SampleT>::kAlignMask) == 0);
-    const bool mfcc = p.mode == SIR_OUT_MFCC;
-    // where the group loop writes its (un-normalised) values: the output itself, or the dB staging buffer for MFCC
-    const int row_stride = mfcc ? p.stage_frames : p.out_frames;
-    float* __restrict__ out = mfcc ? p.db_stage + (int64_t)b * p.n_mels * p.stage_frames
-                                   : p.out + (int64_t)b * p.n_mels * p.out_frames;
-    const bool out_vec = (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
-    if (p.status && crank == 0 && tid == 0) p.status[b] = valid ? 0 : 1;
-
     float* tile = smem + kOffTile;
     float* red = smem + kOffReduce;
+    int* s_flag = reinterpret_cast<int*>(red + 32);
     const int lane = tid & 31, warp = tid >> 5, half = lane >> 4, q = lane & 15;
     const int slot = 2 * warp + half;
     float* scr = smem + kOffScratch + slot * kFrameScratch;
+    const bool mfcc = p.mode == SIR_OUT_MFCC;
+    const bool needs_finish = mfcc || p.mode == SIR_OUT_LOGMEL_NORM;
+    const int out_rows = mfcc ? p.n_mfcc : p.n_mels;
+    const int row_stride = mfcc ? p.stage_frames : p.out_frames;
+    const int64_t total_items = (int64_t)p.batch * p.groups_max;
+    long long* s_item = reinterpret_cast<long long*>(red + 40);
 
-    float shift = 0.f, s1 = 0.f, s2 = 0.f, vmax = -INFINITY;
-    bool have_shift = false;
-    __syncthreads();                                        // tables visible
+    auto process_item = [&](const int64_t item) {
+        const int b = (int)(item / p.groups_max), g = (int)(item - (int64_t)b * p.groups_max);
+        int L = p.lengths ? min(p.lengths[b], p.n_samples) : p.n_samples;
+        if (p.max_samples > 0) L = min(L, p.max_samples);
+        const bool valid = L > kNfft / 2;                   // reflect padding needs L > 512
+        const int T = valid ? 1 + L / kHop : 0;
+        const int n_groups = valid ? (T + kGroupFrames - 1) / kGroupFrames : 1;   // an invalid utterance: one zero-fill item
+        if (g >= n_groups) return;                          // uniform over the CTA
+        float* __restrict__ final_out = p.out + (int64_t)b * out_rows * p.out_frames;
+        if (g == 0 && tid == 0 && p.status) p.status[b] = valid ? 0 : 1;
+        if (!valid) {
+            for (int i = tid; i < out_rows * p.out_frames; i += kFeThreads) final_out[i] = 0.f;
+            return;
+        }
+        const SampleT* __restrict__ row = static_cast<const SampleT*>(p.wave) + (int64_t)b * p.wave_stride;
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & GlobalFrame<SampleT>::kAlignMask) == 0);
+        // where the item writes its (un-normalised) values: the output itself, or the dB staging buffer for MFCC
+        float* __restrict__ out = mfcc ? p.db_stage + (int64_t)b * p.n_mels * p.stage_frames : final_out;
+        const bool out_vec = (row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
 
-    for (int g = crank; g < n_groups; g += csize) {
         const int t0 = g * kGroupFrames;
         const int t = t0 + slot;
         const bool active = t < T;
@@ -235,11 +259,9 @@ __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_k
         }
         __syncthreads();                                    // tile complete
 
-        // tile -> global (8 consecutive frames of one mel row = one 32-byte segment) + statistics
-        if (!have_shift) {
-            shift = tile[0];
-            have_shift = true;
-        }
+        // tile -> global (8 consecutive frames of one mel row = one 32-byte segment) + the item's statistics
+        const float shift = tile[0];                        // fp32 sums of deviations from a nearby value stay short
+        float s1 = 0.f, s2 = 0.f, vmax = -INFINITY;
         const int nslots = min(kGroupFrames, T - t0);
         if (out_vec && nslots == kGroupFrames && t0 + kGroupFrames <= row_stride) {
             for (int idx = tid; idx < p.n_mels * 2; idx += kFeThreads) {
@@ -265,102 +287,98 @@ __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_k
                 }
             }
         }
-        __syncthreads();                                    // tile consumed before the next group overwrites it
-    }
-
-    if ((p.mode != SIR_OUT_LOGMEL_NORM && !mfcc) || !valid) {
-        // zero padding (and whole rows of invalid utterances); rows are split over the cluster
-        const int first = valid ? min(T, p.out_frames) : 0;
-        const int rows = mfcc ? p.n_mfcc : p.n_mels;
-        float* __restrict__ o = p.out + (int64_t)b * rows * p.out_frames;
-        for (int m = crank; m < rows; m += csize)
-            for (int t = first + tid; t < p.out_frames; t += kFeThreads) o[(int64_t)m * p.out_frames + t] = 0.f;
-        return;                                             // uniform over the whole cluster
-    }
-    if (mfcc) {
-        // ---- MFCC: per-utterance max over the cluster -> clamp at max - top_db -> DCT of every frame ------------
-        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 16));
-        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 8));
-        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 4));
-        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 2));
-        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 1));
-        __syncthreads();
-        if (lane == 0) red[warp] = vmax;
-        __syncthreads();
-        if (tid == 0) {
-            float mx = red[0];
-            for (int w = 1; w < kFeWarps; ++w) mx = fmaxf(mx, red[w]);
-            red[16] = mx;
+        if (!needs_finish) {
+            if (g == 0)                                     // zero padding behind the last frame, all rows
+                for (int m = 0; m < p.n_mels; ++m)
+                    for (int tt = T + tid; tt < p.out_frames; tt += kFeThreads) out[(int64_t)m * p.out_frames + tt] = 0.f;
+            return;                                         // (the item loop ends every item with a barrier)
         }
-        float* s_dct = smem + kOffScratch;                  // the frame scratch is free now: [n_mels][n_mfcc]
-        for (int i = tid; i < p.n_mels * p.n_mfcc; i += kFeThreads) s_dct[i] = p.dct[i];
-        cluster.sync();
-        float mx = -INFINITY;
-        for (int r = 0; r < csize; ++r) mx = fmaxf(mx, *cluster.map_shared_rank(red + 16, r));
-        const float floor_db = p.top_db > 0.f ? mx - p.top_db : -INFINITY;
-        float* __restrict__ o = p.out + (int64_t)b * p.n_mfcc * p.out_frames;
-        for (int g = crank; g < n_groups; g += csize) {
-            const int t0 = g * kGroupFrames;
-            const int nslots = min(min(kGroupFrames, T - t0), p.out_frames - t0);
-            for (int idx = tid; idx < p.n_mfcc * kGroupFrames; idx += kFeThreads) {
-                const int c = idx >> 3, sl = idx & 7;
-                if (sl < nslots) {
-                    float acc = 0.f;
-                    for (int m = 0; m < p.n_mels; ++m)
-                        acc = fmaf(fmaxf(__ldcg(out + (int64_t)m * row_stride + t0 + sl), floor_db), s_dct[m * p.n_mfcc + c], acc);
-                    o[(int64_t)c * p.out_frames + t0 + sl] = acc;
+
+        // ---- the item's partial (n, mean, M2, max) -> global; count the item; the last one finishes the utterance ----
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        if (lane == 0) {
+            red[warp] = s1;
+            red[8 + warp] = s2;
+            red[16 + warp] = vmax;
+        }
+        __syncthreads();                                    // every thread's feature stores happen before thread 0's fence
+        if (tid == 0) {
+            ItemPartial part;
+            part.s1 = ((double)red[0] + (double)red[1]) + ((double)red[2] + (double)red[3]);
+            part.s2 = ((double)red[8] + (double)red[9]) + ((double)red[10] + (double)red[11]);
+            part.shift = shift;
+            part.vmax = fmaxf(fmaxf(red[16], red[17]), fmaxf(red[18], red[19]));
+            part.n = nslots * p.n_mels;
+            part.pad = 0;
+            p.partials[item] = part;
+            __threadfence();                                // release: the CTA's stores (bar.sync above) and the partial
+            const bool last = atomicAdd(p.counters + b, 1) == n_groups - 1;
+            if (last) __threadfence();                      // acquire: the other items' stores; also drops this SM's L1 lines
+            *s_flag = last;
+        }
+        __syncthreads();
+        if (!*s_flag) return;                               // uniform over the CTA
+
+        // ---- finisher: every item of utterance b is in global memory ------------------------------------------
+        if (warp == 0) {
+            if (lane == 0) p.counters[b] = 0;               // ready for the next launch
+            const ItemPartial* parts = p.partials + (int64_t)b * p.groups_max;
+            double n = 0, mean = 0, m2 = 0;
+            float mx = -INFINITY;
+            for (int base = 0; base < n_groups; base += 32) {
+                // lane i turns item base + i into (n, mean, M2); then all lanes merge the items in GROUP order
+                // (deterministic whichever CTA finishes) with one fp64 division per item
+                double ni = 0, mi = 0, m2i = 0;
+                if (base + lane < n_groups) {
+                    const double2 a = __ldcg(reinterpret_cast<const double2*>(parts + base + lane));       // (s1, s2)
+                    const float2 c = __ldcg(reinterpret_cast<const float2*>(parts + base + lane) + 2);     // (shift, vmax)
+                    const int cnt = __ldcg(reinterpret_cast<const int*>(parts + base + lane) + 6);
+                    ni = (double)cnt;
+                    const double r = a.x / ni;
+                    mi = (double)c.x + r;
+                    m2i = fmax(a.y - a.x * r, 0.0);
+                    mx = fmaxf(mx, c.y);
+                }
+                const int cnt_items = min(32, n_groups - base);
+                for (int gg = 0; gg < cnt_items; ++gg) {
+                    const double nb = __shfl_sync(0xffffffffu, ni, gg), mb = __shfl_sync(0xffffffffu, mi, gg),
+                                 m2b = __shfl_sync(0xffffffffu, m2i, gg);
+                    const double nt = n + nb, delta = mb - mean, qd = delta * nb / nt;
+                    mean += qd;
+                    m2 += m2b + delta * qd * n;
+                    n = nt;
                 }
             }
-        }
-        for (int c = crank; c < p.n_mfcc; c += csize)
-            for (int t = T + tid; t < p.out_frames; t += kFeThreads) o[(int64_t)c * p.out_frames + t] = 0.f;
-        cluster.sync();                                     // keep every CTA's shared memory alive for its peers
-        return;
-    }
-
-    // ---- per-utterance statistics: CTA partial (n, mean, M2) -> cluster merge over DSMEM ----------------
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    __syncthreads();
-    if (lane == 0) {
-        red[warp] = s1;
-        red[8 + warp] = s2;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int my_frames = 0;
-        for (int g = crank; g < n_groups; g += csize) my_frames += min(kGroupFrames, T - g * kGroupFrames);
-        const double n = (double)my_frames * (double)p.n_mels;
-        double S1 = 0, S2 = 0;
-        for (int w = 0; w < kFeWarps; ++w) {
-            S1 += (double)red[w];
-            S2 += (double)red[8 + w];
-        }
-        double mean = 0, m2 = 0;
-        if (n > 0) {
-            mean = (double)shift + S1 / n;
-            m2 = fmax(S2 - S1 * S1 / n, 0.0);
-        }
-        double* part = reinterpret_cast<double*>(red + 16);
-        part[0] = n;
-        part[1] = mean;
-        part[2] = m2;
-    }
-    cluster.sync();
-    {
-        double n = 0, mean = 0, m2 = 0;                     // every thread merges in rank order: deterministic
-        for (int r = 0; r < csize; ++r) {
-            const double* part = reinterpret_cast<const double*>(cluster.map_shared_rank(red + 16, r));
-            const double nb = part[0], mb = part[1], m2b = part[2];
-            if (nb > 0) {
-                const double nt = n + nb, delta = mb - mean;
-                mean += delta * nb / nt;
-                m2 += m2b + delta * delta * n * nb / nt;
-                n = nt;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) {
+                red[33] = (float)mean;
+                red[34] = (float)(1.0 / (sqrt(m2 / (n - 1.0)) + 1e-5));
+                red[35] = mx;
             }
         }
-        const float fmean = (float)mean;
-        const float inv = (float)(1.0 / (sqrt(m2 / (n - 1.0)) + 1e-5));
+        if (mfcc) {
+            float* s_dct = smem + kOffScratch;              // the frame scratch is free: [n_mels][n_mfcc]
+            for (int i = tid; i < p.n_mels * p.n_mfcc; i += kFeThreads) s_dct[i] = p.dct[i];
+            __syncthreads();
+            const float floor_db = p.top_db > 0.f ? red[35] - p.top_db : -INFINITY;
+            const int Tn = min(T, p.out_frames);
+            for (int idx = tid; idx < p.n_mfcc * Tn; idx += kFeThreads) {
+                const int c = idx / Tn, tt = idx - c * Tn;
+                float acc = 0.f;
+                for (int m = 0; m < p.n_mels; ++m)
+                    acc = fmaf(fmaxf(__ldcg(out + (int64_t)m * row_stride + tt), floor_db), s_dct[m * p.n_mfcc + c], acc);
+                final_out[(int64_t)c * p.out_frames + tt] = acc;
+            }
+            for (int c = 0; c < p.n_mfcc; ++c)
+                for (int tt = T + tid; tt < p.out_frames; tt += kFeThreads) final_out[(int64_t)c * p.out_frames + tt] = 0.f;
+            return;                                         // (the item loop's barrier protects s_dct / the scratch)
+        }
+        __syncthreads();
+        const float fmean = red[33], inv = red[34];
         int mt0 = 0, mt1 = 0, mf0 = 0, mf1 = 0;
         if (p.masks) {
             mt0 = p.masks[4 * b + 0];
@@ -368,25 +386,80 @@ __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_k
             mf0 = p.masks[4 * b + 2];
             mf1 = p.masks[4 * b + 3];
         }
-        // normalise this CTA's own frames (still L2-resident; ld.cg so no stale L1 line is read)
-        for (int g = crank; g < n_groups; g += csize) {
-            const int t0 = g * kGroupFrames;
-            const int nslots = min(min(kGroupFrames, T - t0), p.out_frames - t0);
-            for (int idx = tid; idx < p.n_mels * kGroupFrames; idx += kFeThreads) {
-                const int m = idx >> 3, s = idx & 7;
-                if (s < nslots) {
-                    float* addr = out + (int64_t)m * p.out_frames + t0 + s;
-                    float v = (__ldcg(addr) - fmean) * inv;
-                    const int t = t0 + s;
-                    if ((t >= mt0 && t < mt1) || (m >= mf0 && m < mf1)) v = 0.f;
-                    *addr = v;
+        // normalise + mask + pad the whole utterance.  Its values are still L2-resident; plain loads are safe: thread 0's
+        // fence after the counting atomic is the acquire and dropped this SM's L1 lines.  Loads of a batch are issued
+        // before its first store (a load -> store chain per element would pay one L2 round trip per iteration: the
+        // stores alias the loads as far as the compiler knows); (row, column) advance by kFeThreads elements per step
+        // without a division per element.
+        constexpr int kU = 8;
+        const int cols = out_vec ? p.out_frames >> 2 : p.out_frames;          // float4 chunks or floats per row
+        const int dq = kFeThreads / cols, dr = kFeThreads % cols;
+        int m_ld = tid / cols, c_ld = tid % cols;
+        while (m_ld < p.n_mels) {
+            int mm[kU], cc[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                mm[u] = m_ld;
+                cc[u] = c_ld;
+                m_ld += dq;
+                c_ld += dr;
+                if (c_ld >= cols) {
+                    c_ld -= cols;
+                    ++m_ld;
+                }
+            }
+            if (out_vec) {
+                float4 x[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (mm[u] < p.n_mels && 4 * cc[u] < T)
+                        x[u] = *reinterpret_cast<const float4*>(out + (int64_t)mm[u] * p.out_frames + 4 * cc[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    if (mm[u] < p.n_mels) {
+                        const int m = mm[u], tt = 4 * cc[u];
+                        const bool fm = m >= mf0 && m < mf1;
+                        float4 v;
+                        v.x = (tt >= T || fm || (tt >= mt0 && tt < mt1)) ? 0.f : (x[u].x - fmean) * inv;
+                        v.y = (tt + 1 >= T || fm || (tt + 1 >= mt0 && tt + 1 < mt1)) ? 0.f : (x[u].y - fmean) * inv;
+                        v.z = (tt + 2 >= T || fm || (tt + 2 >= mt0 && tt + 2 < mt1)) ? 0.f : (x[u].z - fmean) * inv;
+                        v.w = (tt + 3 >= T || fm || (tt + 3 >= mt0 && tt + 3 < mt1)) ? 0.f : (x[u].w - fmean) * inv;
+                        *reinterpret_cast<float4*>(out + (int64_t)m * p.out_frames + tt) = v;
+                    }
+                }
+            } else {
+                float x[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    x[u] = 0.f;
+                    if (mm[u] < p.n_mels && cc[u] < T) x[u] = out[(int64_t)mm[u] * p.out_frames + cc[u]];
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    if (mm[u] < p.n_mels) {
+                        const int m = mm[u], tt = cc[u];
+                        const bool masked = (tt >= mt0 && tt < mt1) || (m >= mf0 && m < mf1);
+                        out[(int64_t)m * p.out_frames + tt] = (tt >= T || masked) ? 0.f : (x[u] - fmean) * inv;
+                    }
                 }
             }
         }
-        for (int m = crank; m < p.n_mels; m += csize)
-            for (int t = T + tid; t < p.out_frames; t += kFeThreads) out[(int64_t)m * p.out_frames + t] = 0.f;
+    };
+
+    // ---- item loop: draw a ticket, fetch the next one while this item computes ---------------------------------
+    long long fetched = 0;
+    if (tid == 0) fetched = (long long)(atomicAdd(p.work_counter, 1ULL) - p.work_base);
+    for (;;) {
+        if (tid == 0) *s_item = fetched;
+        __syncthreads();                                    // also: tables visible (first pass), previous item fully done
+        const long long item = *s_item;
+        if (item >= total_items) break;
+        if (tid == 0) fetched = (long long)(atomicAdd(p.work_counter, 1ULL) - p.work_base);
+        process_item(item);
+        __syncthreads();                                    // tile / red[] / scratch / s_item consumed
     }
-    cluster.sync();                                         // keep every CTA's shared memory alive for its peers
 }
 
 // ---- small companions ----------------------------------------------------------------------------------
@@ -454,6 +527,16 @@ __global__ void features_finalize_kernel(const float* __restrict__ in, int n_mel
 // ---- C ABI ------------------------------------------------------------------------------------------------
 using namespace sir;
 
+// Per-stream scratch of a frontend handle (launches on different streams may overlap on the GPU).
+struct FrontendWorkspace {
+    void* stream = nullptr;
+    DeviceBuffer partials;       // [batch][groups_max] ItemPartial
+    DeviceBuffer counters;       // [batch] finished items per utterance; the finishing CTA resets its entry
+    DeviceBuffer db_stage;       // MFCC: staged dB values
+    DeviceBuffer tickets;        // one 64-bit ticket counter
+    unsigned long long next_ticket = 0;
+};
+
 struct sir_frontend {
     int device = 0;
     int sample_rate = 16000, n_mels = 64;
@@ -461,7 +544,9 @@ struct sir_frontend {
     int mel_weight_count = 0;
     DeviceBuffer tables;
     FrontendTables dev{};
-    DeviceBuffer db_stage;       // MFCC: staged dB values
+    static constexpr int kMaxStreams = 8;
+    FrontendWorkspace work[kMaxStreams];
+    int work_used = 0;
     DeviceBuffer dct;            // MFCC: [n_mels][n_mfcc] ortho DCT-II
     int dct_n_mfcc = 0;
 };
@@ -572,7 +657,12 @@ extern "C" int sir_frontend_create(sir_frontend** out, int sample_rate, int n_me
 extern "C" void sir_frontend_destroy(sir_frontend* fe) {
     if (!fe) return;
     fe->tables.release();
-    fe->db_stage.release();
+    for (auto& w : fe->work) {
+        w.partials.release();
+        w.counters.release();
+        w.db_stage.release();
+        w.tickets.release();
+    }
     fe->dct.release();
     delete fe;
 }
@@ -588,6 +678,16 @@ static int frontend_launch(sir_frontend* fe, const void* d_wave, bool pcm16, int
     if (d_masks && mode != SIR_OUT_LOGMEL_NORM)
         return fail(SIR_ERR_INVALID, "mask bands are applied to normalised features only");
     if (batch == 0) return SIR_OK;
+    int slot = 0;
+    while (slot < fe->work_used && fe->work[slot].stream != stream) ++slot;
+    if (slot == fe->work_used) {
+        if (slot == sir_frontend::kMaxStreams)
+            return fail(SIR_ERR_UNSUPPORTED, "sir_frontend_forward: one handle serves at most %d streams; create another handle",
+                        sir_frontend::kMaxStreams);
+        fe->work[slot].stream = stream;
+        ++fe->work_used;
+    }
+    FrontendWorkspace& ws = fe->work[slot];
     FrontendParams p{};
     p.wave = d_wave;
     p.wave_stride = wave_stride;
@@ -622,30 +722,47 @@ static int frontend_launch(sir_frontend* fe, const void* d_wave, bool pcm16, int
         }
         const int eff0 = max_samples > 0 && max_samples < n_samples ? max_samples : n_samples;
         p.stage_frames = ((1 + eff0 / kHop) + 3) & ~3;
-        int rc = fe->db_stage.reserve((size_t)batch * fe->n_mels * p.stage_frames * sizeof(float));
+        int rc = ws.db_stage.reserve((size_t)batch * fe->n_mels * p.stage_frames * sizeof(float));
         if (rc != SIR_OK) return rc;
-        p.db_stage = (float*)fe->db_stage.ptr;
+        p.db_stage = (float*)ws.db_stage.ptr;
         p.dct = (const float*)fe->dct.ptr;
         p.n_mfcc = n_mfcc;
         p.top_db = top_db;
     }
-    // cluster size: enough CTAs for ~2 waves of 3 CTAs/SM, never more CTAs than 8-frame groups
+    // work items: (utterance, 8-frame group); a persistent grid of SIR_FE_MIN_CTAS CTAs per SM takes them round-robin
     int eff = max_samples > 0 && max_samples < n_samples ? max_samples : n_samples;
-    const int groups = (1 + eff / kHop + kGroupFrames - 1) / kGroupFrames;
-    int csize = 1;
-    while (csize < 8 && (int64_t)batch * csize < (int64_t)fe->num_sms * 6 && csize * 2 <= groups) csize *= 2;
+    const int groups = eff > kNfft / 2 ? (1 + eff / kHop + kGroupFrames - 1) / kGroupFrames : 1;
+    const int64_t items = (int64_t)batch * groups;
+    p.batch = batch;
+    p.groups_max = groups;
+    if (mode == SIR_OUT_LOGMEL_NORM || mode == SIR_OUT_MFCC) {
+        int rc = ws.partials.reserve((size_t)items * sizeof(ItemPartial));
+        if (rc != SIR_OK) return rc;
+        if ((size_t)batch * sizeof(int) > ws.counters.bytes) {
+            if ((rc = ws.counters.reserve((size_t)batch * sizeof(int))) != SIR_OK) return rc;
+            SIR_CUDA(cudaMemsetAsync(ws.counters.ptr, 0, ws.counters.bytes, (cudaStream_t)stream));
+        }
+        p.partials = (ItemPartial*)ws.partials.ptr;
+        p.counters = (int*)ws.counters.ptr;
+    }
+    const int64_t slots = (int64_t)fe->num_sms * SIR_FE_MIN_CTAS;
+    const int64_t grid = items < slots ? items : slots;
+    if (!ws.tickets.ptr) {
+        int rc = ws.tickets.reserve(sizeof(unsigned long long));
+        if (rc != SIR_OK) return rc;
+        SIR_CUDA(cudaMemsetAsync(ws.tickets.ptr, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+        ws.next_ticket = 0;
+    }
+    p.work_counter = (unsigned long long*)ws.tickets.ptr;
+    p.work_base = ws.next_ticket;
+    ws.next_ticket += (unsigned long long)(items + grid);   // every CTA draws its items + 1 tickets
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(batch * csize));
+    cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kFeThreads);
     cfg.dynamicSmemBytes = kFeSmemBytes;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)csize;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.attrs = nullptr;
+    cfg.numAttrs = 0;
     {
         ProfScope ps("logmel_frontend_kernel", cfg.stream);
         if (pcm16)

@@ -90,8 +90,12 @@ struct ReflectFrame {
     const T* row;
     int first, L;
     SIR_HD float at(int i) const {
+        // branch-free: the index is clamped and the load is unconditional, so the 128 loads of a frame are all in
+        // flight together (a guarded load per sample serialised them: one L2 round trip each)
         const int r = i < 0 ? -i : (i >= L ? 2 * (L - 1) - i : i);
-        return (r >= 0 && r < L) ? sample_to_float(row[r]) : 0.f;
+        const int rc = r < 0 ? 0 : (r >= L ? L - 1 : r);
+        const float v = sample_to_float(row[rc]);
+        return r == rc ? v : 0.f;
     }
     SIR_HD F2 operator()(int n) const { return F2{at(first + 2 * n), at(first + 2 * n + 1)}; }
 };
