@@ -242,8 +242,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="utterances per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sub-batches", type=int, default=1, help="sub-batches of the host-buffer pipeline (e2e)")
-    ap.add_argument("--depth", type=int, default=2, help="batches in flight in the host-buffer pipeline (e2e)")
-    ap.add_argument("--streams", type=int, default=2, help="CUDA streams consecutive steps alternate over (value)")
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight in the host-buffer pipeline (e2e)")
+    ap.add_argument("--streams", type=int, default=3, help="CUDA streams consecutive steps alternate over (value)")
     ap.add_argument("--numa-bind", type=int, default=1, help="bind each rank to its GPU's CPU cores before allocating pinned buffers")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work spent on the cpu_baseline sample")
     args = ap.parse_args()

@@ -18,6 +18,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cstdlib>
+
 #include "model.cuh"
 
 namespace sir {
@@ -427,6 +429,7 @@ extern "C" void sir_model_destroy(sir_model* m) {
     m->packed.release();
     m->halves.release();
     for (auto& w : m->work) w.release();
+    for (auto& w : m->ticket_buf) w.release();
     m->train_ws.release();
     delete m;
 }
@@ -455,6 +458,7 @@ constexpr int kModelChunk = 336;   // utterances per pass through the workspace:
 struct Workspace {
     __half *act1_hi, *act1_lo, *act2_hi, *act2_lo, *gin_hi, *gin_lo, *y0_hi, *y0_lo;
     float *gi, *y0, *y1;
+    tc::TicketSource* tickets = nullptr;    // the stream's tile-ticket counter (dynamic tile order of the persistent kernels)
 };
 
 static size_t carve(Workspace& w, uint8_t* base, int B, int H, int W, int gin) {
@@ -495,11 +499,11 @@ int model_forward_convs(sir_model* m, const Workspace& ws, const float* feat, in
         SIR_CHECK_LAUNCH("conv1_bn_relu_pool_kernel");
     }
     if ((rc = tc::tc_conv3x3_persistent<32, 64>(ws.act1_hi + o1, ws.act1_lo + o1, m->w2_hi, m->w2_lo, m->sh2, ws.act2_hi + o2,
-                                                ws.act2_lo + o2, count, H2, W2, m->num_sms, st, "conv2_bn_relu_pool")))
+                                                ws.act2_lo + o2, count, H2, W2, m->num_sms, st, "conv2_bn_relu_pool", ws.tickets)))
         return rc;
     // conv3 writes [B][T/8][H/8][128]: the GRU input, time-major with channels-last features
     return tc::tc_conv3x3_stream<64, 128>(ws.act2_hi + o2, ws.act2_lo + o2, m->w3_hi, m->w3_lo, m->sh3, ws.gin_hi + o3,
-                                          ws.gin_lo + o3, count, H4, W4, 1, m->num_sms, st, "conv3_bn_relu_pool");
+                                          ws.gin_lo + o3, count, H4, W4, 1, m->num_sms, st, "conv3_bn_relu_pool", ws.tickets);
 }
 
 // 2-layer bidirectional GRU + attention pooling + fc over the B utterances whose GRU input is in the workspace.
@@ -512,7 +516,7 @@ int model_forward_head(sir_model* m, const Workspace& ws, int B, int W, float* l
     for (int l = 0; l < 2; ++l) {
         const int M = B * Tg;
         if ((rc = tc::tc_gemm_nt(x_hi, x_lo, m->wih_hi[l], m->wih_lo[l], m->bih[l], ws.gi, M, 1536, in_sz, st,
-                                 l == 0 ? "gru_l0_input_gemm" : "gru_l1_input_gemm")))
+                                 l == 0 ? "gru_l0_input_gemm" : "gru_l1_input_gemm", ws.tickets)))
             return rc;
         {
             ProfScope ps(l == 0 ? "gru_l0_recurrence" : "gru_l1_recurrence", st);
@@ -554,6 +558,13 @@ static int model_prepare(sir_model* m, int batch, int n_frames, Workspace& ws, i
     int rc = m->work[slot].reserve(need);
     if (rc != SIR_OK) return rc;
     carve(ws, (uint8_t*)m->work[slot].ptr, chunk, m->n_mels, n_frames, m->gru_in);
+    if (!m->ticket_buf[slot].ptr) {
+        if ((rc = m->ticket_buf[slot].reserve(sizeof(unsigned long long))) != SIR_OK) return rc;
+        SIR_CUDA(cudaMemsetAsync(m->ticket_buf[slot].ptr, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+        m->ticket_src[slot] = tc::TicketSource{(unsigned long long*)m->ticket_buf[slot].ptr, 0};
+    }
+    static const bool static_tiles = getenv("SIR_STATIC_TILES") != nullptr;     // A/B switch (timing experiments)
+    ws.tickets = static_tiles ? nullptr : &m->ticket_src[slot];
     return SIR_OK;
 }
 

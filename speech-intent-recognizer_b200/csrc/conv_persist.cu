@@ -35,12 +35,13 @@ struct CpLayout {
     static constexpr int kStageBytes = 2 * kABytes;
     static constexpr int kOffA = kWBytes;
     static constexpr int kOffBar = kOffA + STAGES * kStageBytes;
-    static constexpr int kSmemBytes = kOffBar + (2 * STAGES + 5) * 8 + 16 + 1024;
+    static constexpr int kSmemBytes = kOffBar + (2 * STAGES + 5) * 8 + (int)sizeof(TileRing) + 16 + 1024;
     static_assert(kTapBytes % 1024 == 0 && kABytes % 1024 == 0, "operand tiles keep 1024-byte alignment");
     static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 struct CpParams {
+    TileTickets tickets;
     int B, H, W, tiles_x, tiles_y, num_tiles;
     const float* shift;
     __half* out_hi;
@@ -61,7 +62,8 @@ __global__ void __launch_bounds__(kCpThreads, 1)
     uint64_t* w_full = empty + STAGES;
     uint64_t* acc_full = w_full + 1;       // [2]
     uint64_t* acc_empty = acc_full + 2;    // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    TileRing* ring = reinterpret_cast<TileRing*>(acc_empty + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring + 1);
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(kCpThreads, 1)
             mbar_init(&acc_full[a], 1);
             mbar_init(&acc_empty[a], 4);           // one arrival per epilogue warp
         }
+        ring_init(ring, 5);                            // MMA warp + 4 epilogue warps
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<2 * COUT>(tmem_slot);
@@ -96,7 +99,8 @@ __global__ void __launch_bounds__(kCpThreads, 1)
                 tma_load_2d(smem + t * 2 * L::kTapBytes + L::kTapBytes, &tm_w_lo, w_full, 0, t * COUT);
             }
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            TileProducer sched(ring, p.tickets, p.num_tiles);
+            for (int tile = sched.pop(); tile >= 0; tile = sched.pop()) {
                 const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
                 const int y0 = (r / p.tiles_x) * 8, x0 = (r % p.tiles_x) * 16;
                 for (int kw = 0; kw < 3; ++kw, ++it) {
@@ -115,8 +119,8 @@ __global__ void __launch_bounds__(kCpThreads, 1)
         mbar_wait(w_full, 0);
         tc_fence_after();
         const uint32_t sbase = smem_u32(smem);
-        uint32_t it = 0, lt = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+        uint32_t it = 0, lt = 0, rt = 0;
+        for (int tile = ring_next(ring, rt, lane); tile >= 0; tile = ring_next(ring, rt, lane), ++lt) {
             const uint32_t acc = lt & 1u;
             mbar_wait(&acc_empty[acc], ((lt >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
             tc_fence_after();
@@ -152,8 +156,8 @@ __global__ void __launch_bounds__(kCpThreads, 1)
         // ---- epilogue warps: TMEM lane quadrant q; rows of the quadrant = pixel rows 2q, 2q+1 of the tile ----------
         const int q = warp & 3;
         const int H2 = p.H / 2, W2 = p.W / 2;
-        uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+        uint32_t lt = 0, rt = 0;
+        for (int tile = ring_next(ring, rt, lane); tile >= 0; tile = ring_next(ring, rt, lane), ++lt) {
             const uint32_t acc = lt & 1u;
             const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
             const int y0 = (r / p.tiles_x) * 8, x0 = (r % p.tiles_x) * 16;
@@ -186,7 +190,8 @@ __global__ void __launch_bounds__(kCpThreads, 1)
 // conv (3x3, s1, p1) + shift + ReLU + 2x2 max-pool, channels-last fp16 hi/lo in and out; weights [9][COUT][CIN].
 template <int CIN, int COUT>
 int tc_conv3x3_persistent(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
-                          __half* out_hi, __half* out_lo, int B, int H, int W, int num_sms, cudaStream_t st, const char* name) {
+                          __half* out_hi, __half* out_lo, int B, int H, int W, int num_sms, cudaStream_t st, const char* name,
+                          TicketSource* tickets) {
     constexpr int STAGES = 6;
     using L = CpLayout<CIN, COUT, STAGES>;
     CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
@@ -215,6 +220,7 @@ int tc_conv3x3_persistent(const __half* in_hi, const __half* in_lo, const __half
         attr = true;
     }
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    p.tickets = tickets ? tickets->take(p.num_tiles, grid) : TileTickets{nullptr, 0};
     {
         ProfScope ps(name, st);
         kern<<<grid, kCpThreads, L::kSmemBytes, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
@@ -238,13 +244,14 @@ struct CsLayout {
     static constexpr int kABytes = 144 * kRowBytes;                 // 8 x 18 pixel halo box, one of (hi, lo): 18 KB
     static constexpr int kOffB = kASt * 2 * kABytes;
     static constexpr int kOffBar = kOffB + kBSt * 2 * kTapBytes;
-    static constexpr int kSmemBytes = kOffBar + (2 * kASt + 2 * kBSt + 4) * 8 + 16 + 1024;
+    static constexpr int kSmemBytes = kOffBar + (2 * kASt + 2 * kBSt + 4) * 8 + (int)sizeof(TileRing) + 16 + 1024;
     static_assert(kRowBytes == 128, "built for 64 input channels (128-byte swizzle rows)");
     static_assert(kTapBytes % 1024 == 0 && kABytes % 1024 == 0, "operand tiles keep 1024-byte alignment");
     static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 struct CsParams {
+    TileTickets tickets;
     int B, H, W, tiles_x, tiles_y, num_tiles, out_whc;
     const float* shift;
     __half* out_hi;
@@ -265,7 +272,8 @@ __global__ void __launch_bounds__(kCpThreads, 1)
     uint64_t* b_empty = b_full + L::kBSt;
     uint64_t* acc_full = b_empty + L::kBSt;   // [2]
     uint64_t* acc_empty = acc_full + 2;       // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    TileRing* ring = reinterpret_cast<TileRing*>(acc_empty + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring + 1);
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -285,6 +293,7 @@ __global__ void __launch_bounds__(kCpThreads, 1)
             mbar_init(&acc_full[a], 1);
             mbar_init(&acc_empty[a], 4);
         }
+        ring_init(ring, 5);                            // MMA warp + 4 epilogue warps
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<2 * COUT>(tmem_slot);
@@ -297,7 +306,8 @@ __global__ void __launch_bounds__(kCpThreads, 1)
     if (warp == 0) {
         if (lane == 0) {
             uint32_t ia = 0, ib = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            TileProducer sched(ring, p.tickets, p.num_tiles);
+            for (int tile = sched.pop(); tile >= 0; tile = sched.pop()) {
                 const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
                 const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
                 for (int kw = 0; kw < 3; ++kw, ++ia) {
@@ -321,8 +331,8 @@ __global__ void __launch_bounds__(kCpThreads, 1)
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc_f16(128, COUT);
         const uint32_t sbase = smem_u32(smem);
-        uint32_t ia = 0, ib = 0, lt = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+        uint32_t ia = 0, ib = 0, lt = 0, rt = 0;
+        for (int tile = ring_next(ring, rt, lane); tile >= 0; tile = ring_next(ring, rt, lane), ++lt) {
             const uint32_t acc = lt & 1u;
             mbar_wait(&acc_empty[acc], ((lt >> 1) & 1u) ^ 1u);
             tc_fence_after();
@@ -361,8 +371,8 @@ __global__ void __launch_bounds__(kCpThreads, 1)
         // epilogue: quadrant q holds tile rows y = 4q .. 4q+3 (lane = dy * 8 + x); pooling partners are lanes ^1 and ^8
         const int q = warp & 3;
         const int H2 = p.H / 2, W2 = p.W / 2;
-        uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+        uint32_t lt = 0, rt = 0;
+        for (int tile = ring_next(ring, rt, lane); tile >= 0; tile = ring_next(ring, rt, lane), ++lt) {
             const uint32_t acc = lt & 1u;
             const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
             const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
@@ -395,7 +405,7 @@ __global__ void __launch_bounds__(kCpThreads, 1)
 template <int CIN, int COUT>
 int tc_conv3x3_stream(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
                       __half* out_hi, __half* out_lo, int B, int H, int W, int out_whc, int num_sms, cudaStream_t st,
-                      const char* name) {
+                      const char* name, TicketSource* tickets) {
     using L = CsLayout<CIN, COUT>;
     CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
     const uint64_t adims[4] = {(uint64_t)CIN, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -424,6 +434,7 @@ int tc_conv3x3_stream(const __half* in_hi, const __half* in_lo, const __half* w_
         attr = true;
     }
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    p.tickets = tickets ? tickets->take(p.num_tiles, grid) : TileTickets{nullptr, 0};
     {
         ProfScope ps(name, st);
         kern<<<grid, kCpThreads, L::kSmemBytes, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
@@ -433,10 +444,10 @@ int tc_conv3x3_stream(const __half* in_hi, const __half* in_lo, const __half* w_
 }
 
 template int tc_conv3x3_stream<64, 128>(const __half*, const __half*, const __half*, const __half*, const float*, __half*,
-                                        __half*, int, int, int, int, int, cudaStream_t, const char*);
+                                        __half*, int, int, int, int, int, cudaStream_t, const char*, TicketSource*);
 
 template int tc_conv3x3_persistent<32, 64>(const __half*, const __half*, const __half*, const __half*, const float*, __half*,
-                                           __half*, int, int, int, int, cudaStream_t, const char*);
+                                           __half*, int, int, int, int, cudaStream_t, const char*, TicketSource*);
 
 }  // namespace tc
 }  // namespace sir

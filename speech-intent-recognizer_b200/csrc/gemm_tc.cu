@@ -298,12 +298,13 @@ struct GpLayout {
     static constexpr int kBBytes = kBN * kBK * 2;                  // activation tile: 11 KB
     static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // 38 KB
     static constexpr int kOffBar = kStages * kStageBytes;
-    static constexpr int kSmemBytes = kOffBar + (2 * kStages + 4) * 8 + 16 + 1024;
+    static constexpr int kSmemBytes = kOffBar + (2 * kStages + 4) * 8 + (int)sizeof(TileRing) + 16 + 1024;
     static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "operand tiles keep 1024-byte alignment");
     static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 struct GpParams {
+    TileTickets tickets;
     int M, N, num_kblocks, tiles_w, tiles_x, num_tiles;   // tiles_w: weight-row tiles (N / 128), tiles_x: activation-row tiles
     const float* bias;
     float* C;
@@ -320,7 +321,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     uint64_t* empty = full + L::kStages;
     uint64_t* acc_full = empty + L::kStages;   // [2]
     uint64_t* acc_empty = acc_full + 2;        // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    TileRing* ring = reinterpret_cast<TileRing*>(acc_empty + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring + 1);
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -336,6 +338,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             mbar_init(&acc_full[a], 1);
             mbar_init(&acc_empty[a], 4);
         }
+        ring_init(ring, 5);                            // MMA warp + 4 epilogue warps
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -348,7 +351,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            TileProducer sched(ring, p.tickets, p.num_tiles);
+            for (int tile = sched.pop(); tile >= 0; tile = sched.pop()) {
                 const int w0 = (tile % p.tiles_w) * 128, x0 = (tile / p.tiles_w) * L::kBN;
                 for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
                     const int s = it % L::kStages;
@@ -365,8 +369,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc_f16(128, L::kBN);
         const uint32_t sbase = smem_u32(smem);
-        uint32_t it = 0, lt = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+        uint32_t it = 0, lt = 0, rt = 0;
+        for (int tile = ring_next(ring, rt, lane); tile >= 0; tile = ring_next(ring, rt, lane), ++lt) {
             const uint32_t acc = lt & 1u;
             mbar_wait(&acc_empty[acc], ((lt >> 1) & 1u) ^ 1u);
             tc_fence_after();
@@ -396,8 +400,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     } else {
         // TMEM lane = weight row (output column n), TMEM column = activation row (output row m)
         const int q = warp & 3;
-        uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+        uint32_t lt = 0, rt = 0;
+        for (int tile = ring_next(ring, rt, lane); tile >= 0; tile = ring_next(ring, rt, lane), ++lt) {
             const uint32_t acc = lt & 1u;
             const int w0 = (tile % p.tiles_w) * 128, x0 = (tile / p.tiles_w) * L::kBN;
             mbar_wait(&acc_full[acc], (lt >> 1) & 1u);
@@ -437,7 +441,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 }
 
 static int tc_gemm_nt_persistent(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo, const float* bias,
-                                 float* C, int M, int N, int K, cudaStream_t st, const char* name) {
+                                 float* C, int M, int N, int K, cudaStream_t st, const char* name, TicketSource* tickets) {
     using L = GpLayout;
     CUtensorMap tw_hi, tw_lo, tx_hi, tx_lo;
     const uint64_t xdims[2] = {(uint64_t)K, (uint64_t)M}, wdims[2] = {(uint64_t)K, (uint64_t)N};
@@ -465,6 +469,7 @@ static int tc_gemm_nt_persistent(const __half* a_hi, const __half* a_lo, const _
         attr = true;
     }
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    p.tickets = tickets ? tickets->take(p.num_tiles, grid) : TileTickets{nullptr, 0};
     {
         ProfScope ps(name, st);
         gemm_persistent_kernel<<<grid, kTcThreads, L::kSmemBytes, st>>>(tw_hi, tw_lo, tx_hi, tx_lo, p);
@@ -475,10 +480,10 @@ static int tc_gemm_nt_persistent(const __half* a_hi, const __half* a_lo, const _
 
 // C[M,N] = A[M,K] W[N,K]^T + bias ; operands as fp16 hi/lo pairs.  N % 128 == 0, K % 64 == 0.
 int tc_gemm_nt(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo, const float* bias,
-               float* C, int M, int N, int K, cudaStream_t st, const char* name) {
+               float* C, int M, int N, int K, cudaStream_t st, const char* name, TicketSource* tickets) {
     if (N % 128 || K % 64) return fail(SIR_ERR_INVALID, "tc_gemm_nt: N %% 128 and K %% 64 required (N %d, K %d)", N, K);
     if ((int64_t)((M + 175) / 176) * (N / 128) >= 32)   // enough tiles to be worth a persistent launch
-        return tc_gemm_nt_persistent(a_hi, a_lo, w_hi, w_lo, bias, C, M, N, K, st, name);
+        return tc_gemm_nt_persistent(a_hi, a_lo, w_hi, w_lo, bias, C, M, N, K, st, name, tickets);
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     const uint64_t adims[2] = {(uint64_t)K, (uint64_t)M}, bdims[2] = {(uint64_t)K, (uint64_t)N};
     const uint32_t abox[2] = {64, 128}, bbox[2] = {64, 128};
@@ -573,7 +578,7 @@ extern "C" int sir_gemm_nt_split_f16(const float* d_a, const float* d_w, const f
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = tc::split_f16_async(d_a, a_hi, a_lo, (int64_t)na, st))) return rc;
     if ((rc = tc::split_f16_async(d_w, w_hi, w_lo, (int64_t)nw, st))) return rc;
-    return tc::tc_gemm_nt(a_hi, a_lo, w_hi, w_lo, d_bias, d_c, M, N, K, st, "gemm_nt_split_f16");
+    return tc::tc_gemm_nt(a_hi, a_lo, w_hi, w_lo, d_bias, d_c, M, N, K, st, "gemm_nt_split_f16", nullptr);
 }
 
 // 3x3 convolution (stride 1, zero padding 1, no bias) on channels-last fp32 tensors through the same implicit-GEMM

@@ -92,6 +92,8 @@ struct sir_model {
     // GRU recurrence of one batch then overlaps the frontend / conv stack of the next
     static constexpr int kMaxStreams = 8;
     sir::DeviceBuffer work[kMaxStreams];
+    sir::DeviceBuffer ticket_buf[kMaxStreams];   // one tile-ticket counter per stream (its launches are stream-ordered)
+    sir::tc::TicketSource ticket_src[kMaxStreams];
     void* work_stream[kMaxStreams] = {};
     int work_used = 0;
     sir::DeviceBuffer train_ws;  // training activations + backward scratch
@@ -115,18 +117,19 @@ namespace sir {
 
 namespace tc {
 int tc_gemm_nt(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo, const float* bias,
-               float* C, int M, int N, int K, cudaStream_t st, const char* name);
+               float* C, int M, int N, int K, cudaStream_t st, const char* name, TicketSource* tickets = nullptr);
 template <int CIN, int COUT>
 int tc_conv3x3(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
                __half* out_hi, __half* out_lo, float* raw_out, int B, int H, int W, int out_whc, cudaStream_t st,
                const char* name);
 template <int CIN, int COUT>
 int tc_conv3x3_persistent(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
-                          __half* out_hi, __half* out_lo, int B, int H, int W, int num_sms, cudaStream_t st, const char* name);
+                          __half* out_hi, __half* out_lo, int B, int H, int W, int num_sms, cudaStream_t st, const char* name,
+                          TicketSource* tickets = nullptr);
 template <int CIN, int COUT>
 int tc_conv3x3_stream(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
                       __half* out_hi, __half* out_lo, int B, int H, int W, int out_whc, int num_sms, cudaStream_t st,
-                      const char* name);
+                      const char* name, TicketSource* tickets = nullptr);
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint32_t* box);
 int gru_layer_tc(const CUtensorMap& tm_w_hi, const CUtensorMap& tm_w_lo, const float* gi, const float* bhh, float* y,
                  __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st);

@@ -68,6 +68,78 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (spin > (1u << 26)) __trap();
 }
 
+// ---- dynamic tile scheduler of the persistent kernels --------------------------------------------------------
+// The producer thread of a CTA DRAWS tile indices from a global ticket counter (the next draw is in flight while the
+// current tile loads) and publishes them through a small shared-memory ring that every consumer warp (MMA issuer,
+// epilogue warps) reads in the same order.  With a static round-robin a CTA that starts late - its SM was busy with
+// another stream's kernel, e.g. the GRU recurrence of the previous batch - still owns 1/grid of the tiles and the
+// SMs that started on time idle until it is done; with tickets the CTAs that run take the tiles.
+// The counter is never reset: every producer draws (its tiles + 1) tickets, so a launch consumes exactly
+// num_tiles + gridDim.x of them and the host passes the launch's first ticket.  counter == nullptr: static order.
+struct TileTickets {
+    unsigned long long* counter;
+    unsigned long long base;
+};
+// Host view of a ticket counter: launches that share one must be stream-ordered; take() reserves a launch's tickets.
+struct TicketSource {
+    unsigned long long* dev = nullptr;
+    unsigned long long next = 0;
+    TileTickets take(long long num_tiles, long long grid) {
+        TileTickets t{dev, next};
+        next += (unsigned long long)(num_tiles + grid);
+        return t;
+    }
+};
+constexpr int kRingDepth = 4;
+struct TileRing {
+    uint64_t full[kRingDepth], empty[kRingDepth];
+    int tile[kRingDepth];
+    int pad[2];
+};
+__device__ __forceinline__ void ring_init(TileRing* r, uint32_t consumer_warps) {      // one thread, before fence_barrier_init
+    for (int i = 0; i < kRingDepth; ++i) {
+        mbar_init(&r->full[i], 1);
+        mbar_init(&r->empty[i], consumer_warps);
+    }
+}
+struct TileProducer {                                       // lives in the registers of the producer thread
+    TileRing* r;
+    TileTickets tk;
+    int num_tiles;
+    uint32_t it = 0, drawn = 0;
+    long long next = 0;
+    __device__ __forceinline__ long long draw() {
+        const long long t = tk.counter ? (long long)(atomicAdd(tk.counter, 1ULL) - tk.base)
+                                       : (long long)blockIdx.x + (long long)drawn * gridDim.x;
+        ++drawn;
+        return t;
+    }
+    __device__ __forceinline__ TileProducer(TileRing* ring, const TileTickets& t, int n) : r(ring), tk(t), num_tiles(n) {
+        next = draw();
+    }
+    // the next tile of this CTA (-1: none left), already published to the consumers
+    __device__ __forceinline__ int pop() {
+        const int tile = next < (long long)num_tiles ? (int)next : -1;
+        const int slot = it % kRingDepth;
+        mbar_wait(&r->empty[slot], ((it / kRingDepth) & 1u) ^ 1u);
+        r->tile[slot] = tile;
+        mbar_arrive(&r->full[slot]);                        // release: the tile index is visible to whoever acquires `full`
+        ++it;
+        if (tile >= 0) next = draw();                       // in flight while this tile's loads are issued
+        return tile;
+    }
+};
+// consumer side: every lane of the warp calls it (uniform), lane 0 frees the slot
+__device__ __forceinline__ int ring_next(TileRing* r, uint32_t& it, int lane) {
+    const int slot = it % kRingDepth;
+    mbar_wait(&r->full[slot], (it / kRingDepth) & 1u);
+    const int tile = r->tile[slot];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&r->empty[slot]);
+    ++it;
+    return tile;
+}
+
 // ---- TMA -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
