@@ -15,10 +15,11 @@
 //   3. every thread updates 8 hidden units of one utterance, writes h' to the layer output y (fp32, plus the
 //      fp16 pair the next layer's input GEMM consumes) and PUSHES the fp16 (hi, lo) of its 8 units - one
 //      16-byte chunk each - into the next-step B operand of all 8 CTAs through distributed shared memory;
-//   4. one cluster barrier (release/acquire) per step.
+//   4. every updater warp fences its pushes towards the async proxy and ARRIVES (release, cluster scope) on the
+//      `h_full` mbarrier of all 8 CTAs; the MMA-issuing thread of each CTA waits (acquire, cluster scope) on its own
+//      `h_full` before the next step's MMAs.  No cluster-wide barrier inside the loop: a CTA only waits for the data it
+//      needs, and the warps that are not on the critical path run ahead.
 // No grid-wide synchronisation, no per-step launch, no L2 round trip on the recurrence's critical path.
-#include <cstdlib>
-
 #include "sir_common.cuh"
 #include "tc_common.cuh"
 
@@ -66,14 +67,16 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
                         const float* __restrict__ gi,                  // [B*T, 1536]
                         const float* __restrict__ bhh,                 // [2][768]
                         float* __restrict__ y,                         // [B, T, 512]
-                        __half* __restrict__ y_hi, __half* __restrict__ y_lo, int B, int T, int dbg) {
+                        __half* __restrict__ y_hi, __half* __restrict__ y_lo, int B, int T) {
     using L = GtLayout<NB>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* s_gate = reinterpret_cast<float*>(smem + L::kOffS);
     uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
     uint64_t* mma_done = w_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
+    uint64_t* h_full = mma_done + 1;          // [2]: operand buffer b holds the complete hidden state of the next step
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_full + 2);
+    constexpr uint32_t kUpdaterWarps = 4 * NB / 32;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = blockIdx.x % kGtCluster;
@@ -86,6 +89,8 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
         prefetch_tmap(&tm_w_lo);
         mbar_init(w_full, 1);
         mbar_init(mma_done, 1);
+        mbar_init(&h_full[0], kGtCluster * kUpdaterWarps);      // one arrival per updater warp of every CTA of the cluster
+        mbar_init(&h_full[1], kGtCluster * kUpdaterWarps);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc<64>(tmem_slot);
@@ -146,10 +151,10 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
                 gin[g][1] = __ldg(gp + g * 64 + 1);
             }
         }
-        if (s > 0 && !(dbg & 2)) {
+        if (s > 0) {
             // (1) D[128 gate rows, NB utterances] = W_slice[128, 256] . h^T   (h: buffer `cur`)
             if (tid == 0) {
-                fence_proxy_async_all();
+                mbar_wait_cluster(&h_full[cur], (uint32_t)((s - 1) >> 1) & 1u);     // all 8 CTAs' pushes of step s-1 landed
                 tc_fence_after();
                 const uint32_t hb = sbase + L::kOffH + cur * 2 * L::kHBytes;
 #pragma unroll
@@ -214,16 +219,9 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
                     az = s_gate[(1 * 32 + u) * L::kSStride + ui];
                     an = s_gate[(2 * 32 + u) * L::kSStride + ui];
                 }
-                float r, z, n;
-                if (dbg & 16) {
-                    r = gr[e] + ar + b_r[e];
-                    z = gz[e] + az + b_z[e];
-                    n = gn[e] + r * (an + b_n[e]);
-                } else {
-                    r = sigmoid_f(gr[e] + ar + b_r[e]);
-                    z = sigmoid_f(gz[e] + az + b_z[e]);
-                    n = tanh_f(gn[e] + r * (an + b_n[e]));
-                }
+                const float r = sigmoid_f(gr[e] + ar + b_r[e]);
+                const float z = sigmoid_f(gz[e] + az + b_z[e]);
+                const float n = tanh_f(gn[e] + r * (an + b_n[e]));
                 hn[e] = (1.f - z) * n + z * hprev[e];
                 hprev[e] = hn[e];
             }
@@ -237,7 +235,7 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
             }
             const uint4 vhi = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
             const uint4 vlo = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
-            if (s + 1 < T && !(dbg & 1)) {
+            if (s + 1 < T) {
                 const uint32_t dst = sbase + L::kOffH + nxt * 2 * L::kHBytes + chunk_off;
 #pragma unroll
                 for (int c = 0; c < kGtCluster; ++c) {
@@ -245,6 +243,11 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
                     st_cluster_v4(ra, vhi);
                     st_cluster_v4(ra + L::kHBytes, vlo);
                 }
+                // (4) generic-proxy stores -> async proxy (the peers' MMAs read them), then one release-arrive per
+                // warp and peer: lane c signals CTA c
+                fence_proxy_async_all();
+                __syncwarp();
+                if (lane < kGtCluster) mbar_arrive_remote(map_to_cta(smem_u32(&h_full[nxt]), (uint32_t)lane));
             }
             if (uvalid) {
                 const int64_t o = ((int64_t)ubb * T + t) * 512 + dir * 256 + j0 + 8 * ug;
@@ -257,15 +260,10 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
                 }
             }
         }
-        // (4) the pushes of all 8 CTAs have landed (and this step's reads of s_gate / TMEM are done)
-        if (!(dbg & 8)) fence_proxy_async_all();
-        if (dbg & 4) {
-            __syncthreads();
-        } else {
-            asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-            asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-        }
     }
+    // no CTA leaves while a peer might still signal it
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -284,8 +282,7 @@ static int launch_gru(const CUtensorMap& tm_w_hi, const CUtensorMap& tm_w_lo, co
         attr = true;
     }
     dim3 grid((unsigned)(kGtCluster * ((B + NB - 1) / NB)), 2);
-    static const int dbg = getenv("SIR_GRU_DEBUG_SKIP") ? atoi(getenv("SIR_GRU_DEBUG_SKIP")) : 0;   // timing experiments only
-    gru_layer_tc_kernel<NB><<<grid, kGtThreads, L::kSmemBytes, st>>>(tm_w_hi, tm_w_lo, gi, bhh, y, y_hi, y_lo, B, T, dbg);
+    gru_layer_tc_kernel<NB><<<grid, kGtThreads, L::kSmemBytes, st>>>(tm_w_hi, tm_w_lo, gi, bhh, y, y_hi, y_lo, B, T);
     SIR_CHECK_LAUNCH("gru_layer_tc_kernel");
     return SIR_OK;
 }
