@@ -153,7 +153,8 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
         }
         if (s > 0) {
             // (1) D[128 gate rows, NB utterances] = W_slice[128, 256] . h^T   (h: buffer `cur`)
-            if (tid == 0) {
+            if (tid == kGtThreads - 32) {          // lane 0 of the last warp, which has no update work: the MMAs of
+                                                   // step s start the moment the state is complete
                 mbar_wait_cluster(&h_full[cur], (uint32_t)((s - 1) >> 1) & 1u);     // all 8 CTAs' pushes of step s-1 landed
                 tc_fence_after();
                 const uint32_t hb = sbase + L::kOffH + cur * 2 * L::kHBytes;
@@ -176,25 +177,21 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
             if (warp < 3) {
                 mbar_wait(mma_done, (uint32_t)(s - 1) & 1u);
                 tc_fence_after();
+                uint32_t r[NB];
 #pragma unroll
                 for (int c = 0; c < NB; c += 16) {
-                    float v[16];
-                    uint32_t r[16];
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-                          "=r"(r[15])
+                        : "=r"(r[c + 0]), "=r"(r[c + 1]), "=r"(r[c + 2]), "=r"(r[c + 3]), "=r"(r[c + 4]), "=r"(r[c + 5]),
+                          "=r"(r[c + 6]), "=r"(r[c + 7]), "=r"(r[c + 8]), "=r"(r[c + 9]), "=r"(r[c + 10]), "=r"(r[c + 11]),
+                          "=r"(r[c + 12]), "=r"(r[c + 13]), "=r"(r[c + 14]), "=r"(r[c + 15])
                         : "r"(tmem_base + ((uint32_t)(warp * 32) << 16) + c)
                         : "memory");
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        v[i] = __uint_as_float(r[i]);
-                        s_gate[(warp * 32 + lane) * L::kSStride + c + i] = v[i];
-                    }
                 }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");      // one wait for all column chunks
+#pragma unroll
+                for (int i = 0; i < NB; ++i) s_gate[(warp * 32 + lane) * L::kSStride + i] = __uint_as_float(r[i]);
                 tc_fence_before();
             }
             __syncthreads();
