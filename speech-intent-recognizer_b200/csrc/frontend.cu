@@ -60,7 +60,7 @@ constexpr int kFeWarps = 4;
 constexpr int kFeThreads = kFeWarps * 32;
 constexpr int kGroupFrames = 2 * kFeWarps;                 // one frame per half-warp
 constexpr int kTileStride = kGroupFrames + 1;              // padded to dodge bank conflicts
-constexpr int kMelWeightCap = 1280;
+constexpr int kMelWeightCap = 1536;              // taps incl. the zero padding of the 4-aligned runs
 
 // shared-memory carve-up (float offsets)
 constexpr int kOffWindow = 0;
@@ -252,7 +252,8 @@ __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_k
                 const int m = mel_of_lane(q, j);
                 if (m < p.n_mels) {
                     float v = mel_band_power(m, scr, st);
-                    if (p.mode != SIR_OUT_MEL_POWER) v = 10.0f * log10f(fmaxf(v, 1e-10f));
+                    // 10 log10(x) = (10 log10 2) lg2(x): lg2.approx is good to ~1e-7 relative here, i.e. ~1e-6 dB
+                    if (p.mode != SIR_OUT_MEL_POWER) v = 3.01029995663981195f * __log2f(fmaxf(v, 1e-10f));
                     tile[m * kTileStride + slot] = v;
                 }
             }

@@ -6,7 +6,9 @@
 //   mel bank  melscale_fbanks(513, 0, sr/2, n_mels, sr, None, htk)  TA:functional/functional.py:518-590
 // The filterbank is kept SPARSE: band m is non-zero on one contiguous run of FFT bins (3..41 bins at the
 // reference settings; 1,000 non-zeros of 32,832), stored CSR-style, pre-multiplied by 0.25 because the
-// post-pass leaves 4|X|^2 (logmel_frame.cuh).
+// post-pass leaves 4|X|^2 (logmel_frame.cuh).  Every run is widened with zero weights to start and end on a
+// multiple of 4 bins (mel_start, mel_count, mel_offset are multiples of 4; bins up to 515 may be referenced, the
+// power array is zero there), so the kernel reads weights and powers as aligned 16-byte vectors.
 #pragma once
 
 #include <cmath>
@@ -73,9 +75,10 @@ inline HostFrontendTables build_frontend_tables(int sample_rate, int n_mels) {
             first = 0;
             last = 0;
         }
-        t.mel_start[m] = first;
-        t.mel_count[m] = last - first + 1;
-        for (int k = first; k <= last; ++k) t.mel_weight.push_back(0.25f * w[k]);
+        const int first4 = first & ~3, end4 = (last + 1 + 3) & ~3;       // end4 <= 516
+        t.mel_start[m] = first4;
+        t.mel_count[m] = end4 - first4;
+        for (int k = first4; k < end4; ++k) t.mel_weight.push_back(k < n_freqs ? 0.25f * w[k] : 0.f);
     }
     return t;
 }

@@ -34,16 +34,19 @@ constexpr int kFrameScratch = 1072;  // floats per frame: 2*16*33 = 1056 transpo
 struct alignas(8) F2 {      // 64-bit shared-memory accesses on the device, plain struct on the host
     float x, y;
 };
+struct alignas(16) F4 {
+    float x, y, z, w;
+};
 
 // Device-resident constant tables, built on the host in double precision (frontend.cu: build_tables).
 struct FrontendTables {
     const float* window;      // [1024] periodic Hann
     const float* tw512;       // [32][16][2]  (cos, -sin) of 2*pi*l*k2/512, index k2*16 + l
     const float* tw1024;      // [257][2]     (cos, sin)  of 2*pi*k/1024
-    const int* mel_start;     // [n_mels] first bin with non-zero weight
-    const int* mel_count;     // [n_mels] number of taps
-    const int* mel_offset;    // [n_mels] offset of the first tap in mel_weight
-    const float* mel_weight;  // taps, already multiplied by 0.25 (the post-pass leaves 4*|X|^2)
+    const int* mel_start;     // [n_mels] first bin of the band's run, rounded down to a multiple of 4
+    const int* mel_count;     // [n_mels] number of taps (a multiple of 4; zero weights pad the run)
+    const int* mel_offset;    // [n_mels] offset of the first tap in mel_weight (a multiple of 4)
+    const float* mel_weight;  // taps, already multiplied by 0.25 (the post-pass leaves 4*|X|^2); 16-byte aligned
 };
 
 // ---- phase A ------------------------------------------------------------------------------------------------
@@ -168,7 +171,10 @@ SIR_HD void frame_phase_c_store(int q, const PhaseCRegs& r, float* __restrict__ 
         p[k] = r.pk[m];
         p[512 - k] = r.pm[m];
     }
-    if (q == 0) p[256] = r.p256;
+    if (q == 0) {
+        p[256] = r.p256;
+        p[513] = p[514] = p[515] = 0.f;      // the 4-aligned mel runs may touch these (with zero weights)
+    }
 }
 
 // ---- phase D ------------------------------------------------------------------------------------------------
@@ -176,13 +182,20 @@ SIR_HD void frame_phase_c_store(int q, const PhaseCRegs& r, float* __restrict__ 
 // bands, so the 16 lanes carry nearly equal tap counts (the HTK triangles span 3..41 bins).
 SIR_HD int mel_of_lane(int q, int j) { return (j & 1) ? 16 * j + 15 - q : 16 * j + q; }
 
+// `p` (the frame's power array) and t.mel_weight must be 16-byte aligned: both runs are read as 4-float vectors.
 SIR_HD float mel_band_power(int m, const float* __restrict__ p, const FrontendTables& t) {
-    const int start = t.mel_start[m];
-    const int count = t.mel_count[m];
-    const float* __restrict__ w = t.mel_weight + t.mel_offset[m];
-    float acc = 0.f;
-    for (int i = 0; i < count; ++i) acc += w[i] * p[start + i];
-    return acc;
+    const int n4 = t.mel_count[m] >> 2;
+    const F4* __restrict__ w4 = reinterpret_cast<const F4*>(t.mel_weight + t.mel_offset[m]);
+    const F4* __restrict__ p4 = reinterpret_cast<const F4*>(p + t.mel_start[m]);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int i = 0; i < n4; ++i) {
+        const F4 w = w4[i], x = p4[i];
+        a0 += w.x * x.x;
+        a1 += w.y * x.y;
+        a2 += w.z * x.z;
+        a3 += w.w * x.w;
+    }
+    return (a0 + a1) + (a2 + a3);
 }
 
 }  // namespace sir

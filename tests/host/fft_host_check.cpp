@@ -1,6 +1,7 @@
 // CPU emulation of the frontend's per-frame pipeline (logmel_frame.cuh) - 16 "lanes" run phase by phase -
 // checked against a direct double-precision DFT.  Built and run by tests/test_host_logic.py with g++.
 #include <cstdio>
+#include <cstdint>
 #include <cstdlib>
 #include <vector>
 #include <cmath>
@@ -23,7 +24,10 @@ int main(int argc, char** argv) {
             float u = (float)((s >> 8) & 0xFFFF) / 65536.f - 0.5f;
             frame[n] = (trial == 3 ? 1e-4f : 0.3f) * u + (trial >= 1 ? 0.4f * std::sin(0.05f * n * (trial + 1)) : 0.f);
         }
-        std::vector<float> scratch(kFrameScratch, 0.f);
+        std::vector<float> scratch_store(kFrameScratch + 4, 0.f);      // 16-byte aligned view, like the kernel's scratch
+        float* scratch_ptr = scratch_store.data();
+        while (reinterpret_cast<uintptr_t>(scratch_ptr) & 15u) ++scratch_ptr;
+        struct { float* p; float* data() { return p; } float& operator[](size_t i) { return p[i]; } } scratch{scratch_ptr};
         float* scr_re = scratch.data();
         float* scr_im = scratch.data() + 16 * kRowPad;
         if (trial & 1) {   // exercise both loaders: contiguous, and reflect with the frame inside the signal
@@ -40,7 +44,7 @@ int main(int argc, char** argv) {
         for (int q = 0; q < 16; ++q) frame_phase_c_compute(q, scratch.data(), t.tw1024, rc[q]);
         for (int q = 0; q < 16; ++q) frame_phase_c_store(q, rc[q], scratch.data());
         // reference: direct DFT in double of the windowed frame
-        std::vector<double> P(513);
+        std::vector<double> P(516, 0.0);
         double pmax = 0;
         for (int k = 0; k <= 512; ++k) {
             double re = 0, im = 0;
