@@ -75,7 +75,9 @@ constexpr int kOffTile = kOffScratch + kGroupFrames * kFrameScratch;
 constexpr int kOffReduce = kOffTile + kMaxMels * kTileStride;
 constexpr int kFeSmemFloats = kOffReduce + 64;
 constexpr size_t kFeSmemBytes = (size_t)kFeSmemFloats * sizeof(float);
-static_assert(kOffScratch % 4 == 0 && kOffTile % 4 == 0, "16-byte alignment of vector regions");
+static_assert(kOffScratch % 4 == 0 && kOffTile % 4 == 0 && kOffTw512 % 4 == 0 && kOffMelWeight % 4 == 0 &&
+                  kMelWeightCap == 3 * 4 * 128 && kMaxMels <= 128,
+              "16-byte alignment of vector regions; table staging shape");
 #ifndef SIR_FE_MIN_CTAS
 #define SIR_FE_MIN_CTAS 3
 #endif
@@ -167,21 +169,46 @@ __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_k
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x;
 
-    // ---- constants into shared memory (once per CTA) -----------------------------------------------------
-    for (int i = tid; i < 1024; i += kFeThreads) {
-        smem[kOffWindow + i] = p.tables.window[i];
-        smem[kOffTw512 + i] = p.tables.tw512[i];
-    }
-    for (int i = tid; i < 514; i += kFeThreads) smem[kOffTw1024 + i] = p.tables.tw1024[i];
+    // ---- constants into shared memory (once per CTA): all loads of a thread are issued before its first store -----
     int* s_mel_start = reinterpret_cast<int*>(smem + kOffMelStart);
     int* s_mel_count = reinterpret_cast<int*>(smem + kOffMelCount);
     int* s_mel_offset = reinterpret_cast<int*>(smem + kOffMelOffset);
-    for (int i = tid; i < p.n_mels; i += kFeThreads) {
-        s_mel_start[i] = p.tables.mel_start[i];
-        s_mel_count[i] = p.tables.mel_count[i];
-        s_mel_offset[i] = p.tables.mel_offset[i];
+    {
+        static_assert(kFeThreads == 128, "table staging below assumes 128 threads");
+        const float4* gw = reinterpret_cast<const float4*>(p.tables.window);      // 256 float4 each (16-byte aligned
+        const float4* gt = reinterpret_cast<const float4*>(p.tables.tw512);       //  sections, sir_frontend_create)
+        const float4* gm = reinterpret_cast<const float4*>(p.tables.mel_weight);
+        const int mel4 = (p.mel_weight_count + 3) >> 2;                           // <= kMelWeightCap / 4 = 3 * 128
+        const float4 w0 = __ldg(gw + tid), w1 = __ldg(gw + tid + 128), t0 = __ldg(gt + tid), t1 = __ldg(gt + tid + 128);
+        float4 m4[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            m4[k] = tid + 128 * k < mel4 ? __ldg(gm + tid + 128 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float tw[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) tw[k] = tid + 128 * k < 514 ? __ldg(p.tables.tw1024 + tid + 128 * k) : 0.f;
+        int ms = 0, mc = 0, mo = 0;
+        if (tid < p.n_mels) {
+            ms = __ldg(p.tables.mel_start + tid);
+            mc = __ldg(p.tables.mel_count + tid);
+            mo = __ldg(p.tables.mel_offset + tid);
+        }
+        reinterpret_cast<float4*>(smem + kOffWindow)[tid] = w0;
+        reinterpret_cast<float4*>(smem + kOffWindow)[tid + 128] = w1;
+        reinterpret_cast<float4*>(smem + kOffTw512)[tid] = t0;
+        reinterpret_cast<float4*>(smem + kOffTw512)[tid + 128] = t1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (tid + 128 * k < mel4) reinterpret_cast<float4*>(smem + kOffMelWeight)[tid + 128 * k] = m4[k];
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (tid + 128 * k < 514) smem[kOffTw1024 + tid + 128 * k] = tw[k];
+        if (tid < p.n_mels) {
+            s_mel_start[tid] = ms;
+            s_mel_count[tid] = mc;
+            s_mel_offset[tid] = mo;
+        }
     }
-    for (int i = tid; i < p.mel_weight_count; i += kFeThreads) smem[kOffMelWeight + i] = p.tables.mel_weight[i];
     const FrontendTables st{smem + kOffWindow, smem + kOffTw512, smem + kOffTw1024, s_mel_start,
                             s_mel_count,       s_mel_offset,     smem + kOffMelWeight};
 
