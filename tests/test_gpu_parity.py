@@ -313,3 +313,58 @@ def test_mfcc_preemphasis_resample_match_oracle(fe):
     feats = fe.forward(native.Resampler(24000, 16000)(dev(x[0:1]))).cpu().numpy()[0]
     want = logmel_np.extract_features(logmel_np.resample(x[0], 24000, 16000), max_duration=None)
     assert rel_to_scale(feats, want) < FEATURE_REL_TOL
+
+
+def test_work_item_scheduling_is_deterministic_and_shape_safe(fe):
+    """The frontend draws (utterance, group) items from a ticket counter and lets whichever CTA completes an utterance
+    normalise it: results must not depend on the draw order (bit-identical across repeats), and one handle must serve
+    launches of changing batch / length / mode back to back (ticket base, partial and counter buffers are reused)."""
+    rng = np.random.default_rng(7)
+    cases = []
+    for B, L, F in ((3, 48000, 200), (300, 16000, 200), (1, 700, 8), (64, 80000, 157), (17, 33333, 66), (300, 16000, 200)):
+        w = dev((rng.standard_normal((B, L)) * 0.1).astype(np.float32))
+        lens = dev(rng.integers(600, L + 1, size=B).astype(np.int32))
+        lens[0] = 100                                                    # one invalid utterance (L <= 512): zeros, status 1
+        cases.append((w, lens, F))
+    first = [fe.forward(w, lengths=lens, out_frames=F).clone() for w, lens, F in cases]
+    for rep in range(3):
+        for (w, lens, F), want in zip(cases, first):
+            got = fe.forward(w, lengths=lens, out_frames=F)
+            assert torch.equal(got, want), (rep, tuple(w.shape))
+    for (w, lens, F), got in zip(cases, first):                          # and they are the right values
+        g = got.cpu().numpy()
+        assert not g[0].any()
+        for i in sorted({1, w.shape[0] - 1} - {0}):
+            if i >= w.shape[0]:
+                continue
+            n = int(lens[i])
+            want = logmel_np.dataset_item(w[i, :n].cpu().numpy(), target=F)
+            assert rel_to_scale(g[i], want) < FEATURE_REL_TOL, (tuple(w.shape), i)
+    # MFCC goes through the same finisher (max merge + DCT): repeatable too
+    a = fe.mfcc(cases[1][0], lengths=cases[1][1], out_frames=40).clone()
+    assert torch.equal(a, fe.mfcc(cases[1][0], lengths=cases[1][1], out_frames=40))
+
+
+def test_concurrent_streams_match_serial_results(fe, model):
+    """One frontend / model handle used from three CUDA streams at once (per-stream workspaces, tile-ticket counters and
+    item counters): every stream's results equal the single-stream results bit for bit."""
+    rng = np.random.default_rng(11)
+    waves = [dev((rng.standard_normal((B, 48000)) * 0.1).astype(np.float32)) for B in (256, 96, 256, 40, 256, 130)]
+    want = []
+    for w in waves:
+        f = fe.forward(w, out_frames=200)
+        want.append((f.clone(), model.forward(f).clone()))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    for rep in range(4):
+        got = [None] * len(waves)
+        for i, w in enumerate(waves):
+            s = streams[(i + rep) % 3]
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                f = fe.forward(w, out_frames=200)
+                got[i] = (f, model.forward(f))
+        torch.cuda.synchronize()
+        for i in range(len(waves)):
+            assert torch.equal(got[i][0], want[i][0]), ("features", rep, i)
+            assert torch.equal(got[i][1], want[i][1]), ("logits", rep, i)
