@@ -18,8 +18,6 @@
 #include <cstring>
 #include <vector>
 
-#include <cstdlib>
-
 #include "model.cuh"
 
 namespace sir {
@@ -563,8 +561,7 @@ static int model_prepare(sir_model* m, int batch, int n_frames, Workspace& ws, i
         SIR_CUDA(cudaMemsetAsync(m->ticket_buf[slot].ptr, 0, sizeof(unsigned long long), (cudaStream_t)stream));
         m->ticket_src[slot] = tc::TicketSource{(unsigned long long*)m->ticket_buf[slot].ptr, 0};
     }
-    static const bool static_tiles = getenv("SIR_STATIC_TILES") != nullptr;     // A/B switch (timing experiments)
-    ws.tickets = static_tiles ? nullptr : &m->ticket_src[slot];
+    ws.tickets = &m->ticket_src[slot];
     return SIR_OK;
 }
 
