@@ -1,8 +1,11 @@
 #!/bin/bash
-# 1 -> 8 GPU scaling of the bench (inference, weak scaling) and of the fused training step (config 4: batch 16 per GPU)
+# 1 -> 8 GPU scaling of the bench (inference, weak scaling) and of the fused training step (config 4: batch 16 per GPU).
+# usage: tools/scale_round.sh <tag> [list of N]     (outputs under gpurun_out/<tag>_*)
 OUT=gpurun_out
 TAG=${1:-scale}
-for n in 1 2 4 8; do
+NS=${2:-"1 2 4 8"}
+mkdir -p $OUT
+for n in $NS; do
   if [ $n -eq 1 ]; then
     python bench.py --gpus 1 --steps 50 --warmup 5 --no-cpu-baseline > $OUT/${TAG}_bench_n1.json 2>$OUT/${TAG}_err.log
     python tools/train_time.py 16 100 > $OUT/${TAG}_train_n1.log 2>>$OUT/${TAG}_err.log
@@ -12,10 +15,9 @@ for n in 1 2 4 8; do
   fi
   python - <<PY
 import json
-for line in open("$OUT/${TAG}_bench_n$n.json"):
-    line=line.strip()
-    if line.startswith("{"):
-        d=json.loads(line); print("N=$n value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "pcm16", round(d["e2e_pcm16"]["value"]), "ms/step", round(d["ms_per_step"],4))
+lines=[l for l in open("$OUT/${TAG}_bench_n$n.json").read().splitlines() if l.startswith("{")]
+print("stdout lines:", len(open("$OUT/${TAG}_bench_n$n.json").read().splitlines()))
+d=json.loads(lines[-1]); print("N=$n value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "bound", d["e2e"]["h2d_copy_bound"]["utt_s"], "pcm16", round(d["e2e_pcm16"]["value"]), "ms/step", round(d["ms_per_step"],4))
 PY
   grep "train step" $OUT/${TAG}_train_n$n.log
 done
