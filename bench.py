@@ -51,11 +51,11 @@ SPLIT_PASSES = {"conv2_bn_relu_pool": 3, "conv3_bn_relu_pool": 3, "gru_l0_input_
                 "gru_l0_recurrence": 3, "gru_l1_recurrence": 3}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of THIS workload
 # (256 utterances; profiles/r1_summary.md names the capture of each row).  None: not captured for this build.
-NCU_TRAFFIC_B256 = {
-    "logmel_frontend_kernel": 53.18e6 + 0.58e6, "conv1_bn_relu_pool": 22.68e6 + 59.04e6,
-    "conv2_bn_relu_pool": 104.96e6 + 26.63e6, "conv3_bn_relu_pool": 52.74e6 + 1.94e6,
-    "gru_l0_input_gemm": 32.54e6 + 1.39e6, "gru_l1_input_gemm": 16.29e6 + 0.94e6,
-    "gru_l0_recurrence": 40.94e6 + 0.81e6, "gru_l1_recurrence": 40.93e6 + 0.03e6,
+NCU_TRAFFIC_B256 = {   # captures r1d (profiles/r1d_ncu_*.txt)
+    "logmel_frontend_kernel": 54.17e6 + 1.05e6, "conv1_bn_relu_pool": 21.85e6 + 59.37e6,
+    "conv2_bn_relu_pool": 104.96e6 + 27.77e6, "conv3_bn_relu_pool": 52.76e6 + 3.45e6,
+    "gru_l0_input_gemm": 32.54e6 + 2.65e6, "gru_l1_input_gemm": 16.28e6 + 0.45e6,
+    "gru_l0_recurrence": 40.93e6 + 1.19e6, "gru_l1_recurrence": 40.93e6 + 0.08e6,
 }
 
 
@@ -430,7 +430,7 @@ def main():
                 gbs = FRONTEND_BYTES_PER_UTT * B / (v["ms_per_step"] * 1e-3) / 1e9
                 return {**base, "bound": "hbm", "achieved": round(gbs, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": round(gbs / peaks["hbm_gbs"], 5), "bytes_per_utt": FRONTEND_BYTES_PER_UTT,
-                        "note": "fp32-issue bound: ~1,400 fp32 instructions per lane per frame (DESIGN.md section 4)"}
+                        "note": "CUDA-core FFT: ~1,300 instructions per lane per frame cap the kernel near 30 % of the HBM roofline; latency bound below that (DESIGN.md section 4)"}
             if name == "conv1_bn_relu_pool":
                 nbytes = (4 * N_MELS * OUT_FRAMES + 4 * 32 * (N_MELS // 2) * (OUT_FRAMES // 2)) * B
                 gbs = nbytes / (v["ms_per_step"] * 1e-3) / 1e9
@@ -444,7 +444,7 @@ def main():
                 out["note"] = ("fp32-accurate 3-pass fp16 hi/lo split: the tensor pipe executes 3x the algorithmic FLOPs "
                                f"({round(3 * ach, 1)} TFLOP/s of fp16 MMA work)")
             if "recurrence" in name:
-                out["note"] = "latency chain of 25 dependent time steps (one launch per layer); " + out.get("note", "")
+                out["note"] = "latency chain of 25 dependent time steps (one launch per layer, 4.7 us per step); " + out.get("note", "")
             return out
 
         rooflines = [stage_roofline(k) for k in stage_out]
