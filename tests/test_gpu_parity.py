@@ -368,3 +368,49 @@ def test_concurrent_streams_match_serial_results(fe, model):
         for i in range(len(waves)):
             assert torch.equal(got[i][0], want[i][0]), ("features", rep, i)
             assert torch.equal(got[i][1], want[i][1]), ("logits", rep, i)
+
+
+def test_config5_shard_80_mels_long_audio():
+    """BASELINE config 5, one GPU's shard: 512 utterances x 10 s @16 kHz, 80-mel frontend + the classifier built for 80
+    mels (models/models.py:23 hard-codes 1024 = 128 * 64 / 8; the 80-mel classifier is that class with
+    gru_input_size = 1280).  Full size through size-independent properties, a few utterances against the oracle."""
+    B, L, n_mels = 512, 160000, 80
+    base = synth.speech_like(21, 8, L)
+    gains = np.linspace(0.2, 1.0, B // 8, dtype=np.float32)
+    gains[-1] = gains[1]                                                # two identical groups at different batch positions
+    w = dev((base[None, :, :] * gains[:, None, None]).reshape(B, L))
+    fe80 = native.Frontend(n_mels=n_mels)
+    feats = fe80.forward(w, out_frames=200)                             # 313 frames normalised, then trimmed to 200
+    assert feats.shape == (B, n_mels, 200)
+    full = fe80.forward(w[:16])                                          # untrimmed: [16, 80, 313]
+    assert full.shape == (16, n_mels, 313)
+    flat = full.reshape(16, -1)
+    assert flat.mean(1).abs().max().item() < 1e-4 and (flat.std(1) - 1).abs().max().item() < 1e-3
+    # trimming does not change the statistics (the two output widths sum their partials in different orders: ulp-level)
+    assert rel_to_scale(feats[:16].cpu().numpy(), full[:, :, :200].cpu().numpy()) < 1e-6
+    assert torch.equal(feats[8:16], feats[504:512])                     # position in the batch does not matter
+    sd = synth.make_weights(77, 31, n_mels)
+    model80 = native.Model(31, n_mels)
+    model80.load_weights(torch.from_numpy(synth.flatten_weights(sd)))
+    logits = model80.forward(feats)
+    assert logits.shape == (B, 31) and torch.isfinite(logits).all().item()
+    for i in (0, 3, 509):
+        want_f = logmel_np.dataset_item(w[i].cpu().numpy(), target=200, n_mels=n_mels, max_duration=None)
+        assert rel_to_scale(feats[i].cpu().numpy(), want_f) < FEATURE_REL_TOL, i
+        want = classifier_np.forward(want_f[None], sd)[0]
+        got = logits[i].cpu().numpy()
+        assert np.max(np.abs(got - want)) < LOGIT_ABS_TOL, (i, float(np.max(np.abs(got - want))))
+
+
+def test_config3_shard_precompute_properties(fe):
+    """BASELINE config 3, one of eight shards: 3,756 utterances x 3 s through the frontend alone (feature precompute)."""
+    B, L = 3756, 48000
+    base = dev(synth.speech_like(31, 12, L))
+    w = base.repeat(B // 12, 1)
+    feats = fe.forward(w)                                               # [B, 64, 94], no padding
+    assert feats.shape == (B, 64, 94)
+    flat = feats.reshape(B, -1)
+    assert flat.mean(1).abs().max().item() < 1e-4 and (flat.std(1) - 1).abs().max().item() < 1e-3
+    assert torch.equal(feats[:12], feats[B - 12:])                      # position in the batch does not matter
+    want = logmel_np.extract_features(base[5].cpu().numpy())
+    assert rel_to_scale(feats[5].cpu().numpy(), want) < FEATURE_REL_TOL
