@@ -13,7 +13,7 @@
  *     synchronises with the host except handle creation, weight upload and workspace growth;
  *   - return value 0 = success, negative = error; sir_last_error() returns a thread-local message;
  *   - a handle is bound to the device that was current when it was created and is not thread-safe on the host;
- *     it keeps its scratch per stream, so calls on up to 8 different streams may overlap on the device;
+ *     it keeps its scratch per stream, so calls on up to 32 different streams may overlap on the device;
  *   - there is NO CPU fallback: every compute entry fails with SIR_ERR_CUDA if no CUDA device is usable.
  */
 #ifndef SIR_B200_H

@@ -572,7 +572,7 @@ struct sir_frontend {
     int mel_weight_count = 0;
     DeviceBuffer tables;
     FrontendTables dev{};
-    static constexpr int kMaxStreams = 8;
+    static constexpr int kMaxStreams = 32;
     FrontendWorkspace work[kMaxStreams];
     int work_used = 0;
     DeviceBuffer dct;            // MFCC: [n_mels][n_mfcc] ortho DCT-II

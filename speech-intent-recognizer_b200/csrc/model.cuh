@@ -90,7 +90,7 @@ struct sir_model {
     // eval activations: one workspace per stream the handle is called on, so that batches enqueued on different
     // streams (IntentPipeline slots, bench.py's alternating steps) run concurrently on the GPU - the latency-bound
     // GRU recurrence of one batch then overlaps the frontend / conv stack of the next
-    static constexpr int kMaxStreams = 8;
+    static constexpr int kMaxStreams = 32;
     sir::DeviceBuffer work[kMaxStreams];
     sir::DeviceBuffer ticket_buf[kMaxStreams];   // one tile-ticket counter per stream (its launches are stream-ordered)
     sir::tc::TicketSource ticket_src[kMaxStreams];
