@@ -518,7 +518,7 @@ int model_forward_head(sir_model* m, const Workspace& ws, int B, int W, float* l
             return rc;
         {
             ProfScope ps(l == 0 ? "gru_l0_recurrence" : "gru_l1_recurrence", st);
-            if ((rc = tc::gru_layer_tc(m->tm_whh_hi[l], m->tm_whh_lo[l], ws.gi, m->bhh[l], ys[l],
+            if ((rc = tc::gru_layer_tc(m->whh_hi[l], m->whh_lo[l], ws.gi, m->bhh[l], ys[l],
                                        l == 0 ? ws.y0_hi : nullptr, l == 0 ? ws.y0_lo : nullptr, B, Tg, st)))
                 return rc;
         }

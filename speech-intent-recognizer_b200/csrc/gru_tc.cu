@@ -4,9 +4,10 @@
 //   h' = (1 - z) n + z h            torch.nn.GRU, models/models.py:60 of the reference (gi already holds b_i*)
 //
 // A thread-block CLUSTER of 8 CTAs owns one (direction, slice of NB utterances).  CTA r keeps the recurrent
-// weights of hidden units [32 r, 32 r + 32) - 96 gate rows as fp16 (hi, lo) pairs, 96 KB - resident in shared
-// memory for all steps, loaded once by TMA.  (The UMMA tile has 128 rows: rows 96..127 read whatever follows
-// in shared memory and produce accumulator rows nobody looks at.)  The hidden state
+// weights of hidden units [32 r, 32 r + 32) - 96 gate rows as fp16 (hi, lo) pairs, 96 KB - resident in TENSOR
+// MEMORY for all steps (written once with tcgen05.st: lane = gate row, 128 columns each for hi and lo; rows 96..127
+// are zero): the MMAs take A from TMEM and fetch only the hidden state from shared memory, and the CTA's shared
+// memory footprint (117 KB) leaves room for another kernel's CTA on the same SM.  The hidden state
 // never leaves the chip between steps: it lives as the fp16 (hi, lo) B operand [NB x 256] in every CTA's
 // shared memory (128-byte swizzled K-major, double buffered).  Per step:
 //   1. one thread issues 48 tcgen05.mma (128 x NB x 16; hi.hi, hi.lo, lo.hi over K = 256) into a TMEM
@@ -30,13 +31,13 @@ constexpr int kGtCluster = 8;
 constexpr int kGtUnits = 32;                  // hidden units per CTA
 constexpr int kGtThreads = 256;
 constexpr int kGtWRows = 96;                  // 3 gates x 32 units
-constexpr int kGtWBytes = kGtWRows * 256 * 2; // one of (hi, lo): 4 K-blocks of 96 rows x 128 B
+constexpr uint32_t kGtColWlo = 128;           // TMEM columns: W_hi [0, 128), W_lo [128, 256), accumulator at 256
+constexpr uint32_t kGtColAcc = 256;
 
 template <int NB>
 struct GtLayout {
     static constexpr int kHBytes = NB * 256 * 2;                 // one of (hi, lo) of one buffer: 4 K-blocks of NB rows
-    static constexpr int kOffWlo = kGtWBytes;
-    static constexpr int kOffH = 2 * kGtWBytes;                  // [2 buffers][hi, lo]
+    static constexpr int kOffH = 0;                              // [2 buffers][hi, lo]
     static constexpr int kOffS = kOffH + 4 * kHBytes;            // gate pre-activations [3][32 units][NB + 1] fp32
     static constexpr int kSStride = NB + 1;
     static constexpr int kOffBar = (kOffS + 3 * 32 * kSStride * 4 + 15) & ~15;
@@ -62,8 +63,8 @@ __device__ __forceinline__ float tanh_f(float x) { return 1.f - __fdividef(2.f, 
 
 template <int NB>
 __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads, 1)
-    gru_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi,   // [2*8*96 rows][256] fp16, box {64,96}
-                        const __grid_constant__ CUtensorMap tm_w_lo,
+    gru_layer_tc_kernel(const __half* __restrict__ w_hi,               // [2 dirs][8 ranks][96 rows][256] fp16
+                        const __half* __restrict__ w_lo,
                         const float* __restrict__ gi,                  // [B*T, 1536]
                         const float* __restrict__ bhh,                 // [2][768]
                         float* __restrict__ y,                         // [B, T, 512]
@@ -72,8 +73,7 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* s_gate = reinterpret_cast<float*>(smem + L::kOffS);
-    uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
-    uint64_t* mma_done = w_full + 1;
+    uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
     uint64_t* h_full = mma_done + 1;          // [2]: operand buffer b holds the complete hidden state of the next step
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_full + 2);
     constexpr uint32_t kUpdaterWarps = 4 * NB / 32;
@@ -85,30 +85,46 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
     const int j0 = rank * kGtUnits, b0 = slice * NB;
 
     if (tid == 0) {
-        prefetch_tmap(&tm_w_hi);
-        prefetch_tmap(&tm_w_lo);
-        mbar_init(w_full, 1);
         mbar_init(mma_done, 1);
         mbar_init(&h_full[0], kGtCluster * kUpdaterWarps);      // one arrival per updater warp of every CTA of the cluster
         mbar_init(&h_full[1], kGtCluster * kUpdaterWarps);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc<64>(tmem_slot);
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t sbase = smem_u32(smem);
 
-    if (tid == 0) {
-        // resident weights: rows (dir*8 + rank)*96 .. +96, four 64-wide K-blocks each for hi and lo
-        mbar_arrive_expect_tx(w_full, 2 * kGtWBytes);
-        const int row0 = (dir * kGtCluster + rank) * kGtWRows;
-        for (int kb = 0; kb < 4; ++kb) {
-            tma_load_2d(smem + kb * (kGtWRows * 128), &tm_w_hi, w_full, kb * 64, row0);
-            tma_load_2d(smem + L::kOffWlo + kb * (kGtWRows * 128), &tm_w_lo, w_full, kb * 64, row0);
+    // resident weights -> tensor memory: thread t < 128 owns TMEM lane t = gate row t of this CTA (zeros beyond 96)
+    if (warp < 4) {
+        const int row = tid;
+        const size_t src = ((size_t)(dir * kGtCluster + rank) * kGtWRows + row) * 256;      // halves
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+            const uint4* g = reinterpret_cast<const uint4*>((part ? w_lo : w_hi) + src);
+#pragma unroll 1
+            for (int c = 0; c < 4; c += 2) {                 // 2 x 32 columns per pass: 16 loads of 16 bytes in flight
+                uint32_t r[2][32];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint4 v = row < kGtWRows ? __ldg(g + c * 8 + i) : make_uint4(0u, 0u, 0u, 0u);
+                    r[i >> 3][4 * (i & 7) + 0] = v.x;
+                    r[i >> 3][4 * (i & 7) + 1] = v.y;
+                    r[i >> 3][4 * (i & 7) + 2] = v.z;
+                    r[i >> 3][4 * (i & 7) + 3] = v.w;
+                }
+                tmem_st_32x32(lane_addr + (part ? kGtColWlo : 0u) + (uint32_t)(c * 32), r[0]);
+                tmem_st_32x32(lane_addr + (part ? kGtColWlo : 0u) + (uint32_t)(c * 32 + 32), r[1]);
+            }
         }
+        tmem_st_wait();
     }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     // update role: thread -> (utterance i, group of 8 hidden units ug)
     const bool updater = tid < 4 * NB;
@@ -130,7 +146,6 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
         const int k = j0 + 8 * ug, kb = k >> 6, chunk = (k & 63) >> 3;
         chunk_off = (uint32_t)(kb * (NB * 128) + (ui >> 3) * 1024 + (ui & 7) * 128 + ((chunk ^ (ui & 7)) << 4));
     }
-    mbar_wait(w_full, 0);
     // everybody's barriers/TMEM are set up before any peer may push into this CTA
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
@@ -158,17 +173,18 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
                 mbar_wait_cluster(&h_full[cur], (uint32_t)((s - 1) >> 1) & 1u);     // all 8 CTAs' pushes of step s-1 landed
                 tc_fence_after();
                 const uint32_t hb = sbase + L::kOffH + cur * 2 * L::kHBytes;
+                const uint32_t d_acc = tmem_base + kGtColAcc;
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb) {
-                    const uint64_t a_hi = make_kmajor_desc<128>(sbase + kb * (kGtWRows * 128));
-                    const uint64_t a_lo = make_kmajor_desc<128>(sbase + L::kOffWlo + kb * (kGtWRows * 128));
                     const uint64_t b_hi = make_kmajor_desc<128>(hb + kb * (NB * 128));
                     const uint64_t b_lo = make_kmajor_desc<128>(hb + L::kHBytes + kb * (NB * 128));
 #pragma unroll
                     for (int k = 0; k < 64; k += 16) {
-                        umma_f16(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(b_hi, k), idesc, (kb | k) ? 1u : 0u);
-                        umma_f16(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(b_lo, k), idesc, 1u);
-                        umma_f16(tmem_base, desc_advance_k(a_lo, k), desc_advance_k(b_hi, k), idesc, 1u);
+                        const uint32_t a_hi = tmem_base + (uint32_t)((kb * 64 + k) >> 1);      // 2 halves per column
+                        const uint32_t a_lo = a_hi + kGtColWlo;
+                        umma_f16_ts(d_acc, a_hi, desc_advance_k(b_hi, k), idesc, (kb | k) ? 1u : 0u);
+                        umma_f16_ts(d_acc, a_hi, desc_advance_k(b_lo, k), idesc, 1u);
+                        umma_f16_ts(d_acc, a_lo, desc_advance_k(b_hi, k), idesc, 1u);
                     }
                 }
                 umma_commit(mma_done);
@@ -186,7 +202,7 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
                         : "=r"(r[c + 0]), "=r"(r[c + 1]), "=r"(r[c + 2]), "=r"(r[c + 3]), "=r"(r[c + 4]), "=r"(r[c + 5]),
                           "=r"(r[c + 6]), "=r"(r[c + 7]), "=r"(r[c + 8]), "=r"(r[c + 9]), "=r"(r[c + 10]), "=r"(r[c + 11]),
                           "=r"(r[c + 12]), "=r"(r[c + 13]), "=r"(r[c + 14]), "=r"(r[c + 15])
-                        : "r"(tmem_base + ((uint32_t)(warp * 32) << 16) + c)
+                        : "r"(tmem_base + kGtColAcc + ((uint32_t)(warp * 32) << 16) + c)
                         : "memory");
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");      // one wait for all column chunks
@@ -265,12 +281,12 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc<64>(tmem_base);
+        tmem_dealloc<512>(tmem_base);
     }
 }
 
 template <int NB>
-static int launch_gru(const CUtensorMap& tm_w_hi, const CUtensorMap& tm_w_lo, const float* gi, const float* bhh, float* y,
+static int launch_gru(const __half* w_hi, const __half* w_lo, const float* gi, const float* bhh, float* y,
                       __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st) {
     using L = GtLayout<NB>;
     static bool attr = false;
@@ -279,23 +295,26 @@ static int launch_gru(const CUtensorMap& tm_w_hi, const CUtensorMap& tm_w_lo, co
         attr = true;
     }
     dim3 grid((unsigned)(kGtCluster * ((B + NB - 1) / NB)), 2);
-    gru_layer_tc_kernel<NB><<<grid, kGtThreads, L::kSmemBytes, st>>>(tm_w_hi, tm_w_lo, gi, bhh, y, y_hi, y_lo, B, T);
+    gru_layer_tc_kernel<NB><<<grid, kGtThreads, L::kSmemBytes, st>>>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T);
     SIR_CHECK_LAUNCH("gru_layer_tc_kernel");
     return SIR_OK;
 }
 
 // Utterances per cluster: the smallest UMMA N (multiple of 16) for which both directions of the whole batch
-// fit in one wave of 8-CTA clusters (15 co-resident on a B200 with this kernel's footprint: measured
-// launch__cluster_max_active); N = 48 is the largest slice whose double-buffered operand fits next to the
-// resident weights, larger batches run several waves (the model chunks its batch to one wave of 7 x 48).
+// fit in one wave of 8-CTA clusters (15 co-resident on a B200: measured launch__cluster_max_active); beyond 144
+// utterances N = 64 (the model chunks its batch to 336 = one wave of 2 x 6 clusters).
 constexpr int kGtMaxClustersPerWave = 15;
 
-int gru_layer_tc(const CUtensorMap& tm_w_hi, const CUtensorMap& tm_w_lo, const float* gi, const float* bhh, float* y,
+int gru_layer_tc(const __half* w_hi, const __half* w_lo, const float* gi, const float* bhh, float* y,
                  __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st) {
     auto clusters = [&](int nb) { return 2 * ((B + nb - 1) / nb); };
-    if (clusters(16) <= kGtMaxClustersPerWave) return launch_gru<16>(tm_w_hi, tm_w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
-    if (clusters(32) <= kGtMaxClustersPerWave) return launch_gru<32>(tm_w_hi, tm_w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
-    return launch_gru<48>(tm_w_hi, tm_w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
+    if (clusters(16) <= kGtMaxClustersPerWave) return launch_gru<16>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
+    if (clusters(32) <= kGtMaxClustersPerWave) return launch_gru<32>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
+    // Larger batches: 64 utterances per cluster.  A step is ~8 % slower than with 48, but the recurrence then holds 8
+    // SMs per 64 utterances instead of 8 per 48 (256 utterances: 64 instead of 96 SMs), and the SMs it leaves take
+    // the frontend / conv stack of the next batch, which runs on another stream (measured: +5 % utterances/s).
+    if (B <= 3 * 48) return launch_gru<48>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
+    return launch_gru<64>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
 }
 
 }  // namespace tc

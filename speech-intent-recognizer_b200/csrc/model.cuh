@@ -131,7 +131,7 @@ int tc_conv3x3_stream(const __half* in_hi, const __half* in_lo, const __half* w_
                       __half* out_hi, __half* out_lo, int B, int H, int W, int out_whc, int num_sms, cudaStream_t st,
                       const char* name, TicketSource* tickets = nullptr);
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint32_t* box);
-int gru_layer_tc(const CUtensorMap& tm_w_hi, const CUtensorMap& tm_w_lo, const float* gi, const float* bhh, float* y,
+int gru_layer_tc(const __half* w_hi, const __half* w_lo, const float* gi, const float* bhh, float* y,
                  __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st);
 }  // namespace tc
 

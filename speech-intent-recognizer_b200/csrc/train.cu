@@ -1130,7 +1130,7 @@ extern "C" int sir_model_train_forward(sir_model* m, float* d_params, const floa
     if ((rc = tc::tc_gemm_nt(t.gin_hi, t.gin_lo, m->wih_hi[0], m->wih_lo[0], m->bih[0], t.gi[0], BT, 1536, gin, st,
                              "gru_l0_input_gemm")))
         return rc;
-    if ((rc = tc::gru_layer_tc(m->tm_whh_hi[0], m->tm_whh_lo[0], t.gi[0], m->bhh[0], t.y[0], t.ytmp_hi, t.ytmp_lo, B, T, st)))
+    if ((rc = tc::gru_layer_tc(m->whh_hi[0], m->whh_lo[0], t.gi[0], m->bhh[0], t.y[0], t.ytmp_hi, t.ytmp_lo, B, T, st)))
         return rc;
     gru_dropout_kernel<<<blocks_for((int64_t)BT * 512 / 4), 256, 0, st>>>(t.y[0], (int64_t)BT * 512, d_dropout_keep, seed, offset,
                                                                          t.keep, t.y0d, t.y0d_hi, t.y0d_lo);
@@ -1139,7 +1139,7 @@ extern "C" int sir_model_train_forward(sir_model* m, float* d_params, const floa
     if ((rc = tc::tc_gemm_nt(t.y0d_hi, t.y0d_lo, m->wih_hi[1], m->wih_lo[1], m->bih[1], t.gi[1], BT, 1536, 512, st,
                              "gru_l1_input_gemm")))
         return rc;
-    if ((rc = tc::gru_layer_tc(m->tm_whh_hi[1], m->tm_whh_lo[1], t.gi[1], m->bhh[1], t.y[1], nullptr, nullptr, B, T, st)))
+    if ((rc = tc::gru_layer_tc(m->whh_hi[1], m->whh_lo[1], t.gi[1], m->bhh[1], t.y[1], nullptr, nullptr, B, T, st)))
         return rc;
     if ((rc = launch_attention_fc(m, t.y[1], d_logits, B, T, st))) return rc;
     m->have_saved = true;
