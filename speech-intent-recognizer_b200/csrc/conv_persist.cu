@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kCpThreads, 1)
         ring_init(ring, 5);                            // MMA warp + 4 epilogue warps
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<2 * COUT>(tmem_slot);
+    if (warp == 1) tmem_alloc<4 * COUT>(tmem_slot);     // 2 accumulators x [hi.hi + lo.hi | hi.lo]
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -334,14 +334,15 @@ __global__ void __launch_bounds__(kCpThreads, 1)
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc_f16(128, COUT);
+        // A_hi x [W_hi; W_lo] (N = 2 COUT, the halves of a tap are adjacent in the ring slot) + A_lo x W_hi, as in conv2
+        constexpr uint32_t idesc = make_idesc_f16(128, COUT), idesc2 = make_idesc_f16(128, 2 * COUT);
         const uint32_t sbase = smem_u32(smem);
         uint32_t ia = 0, ib = 0, lt = 0, rt = 0;
         for (int tile = ring_next(ring, rt, lane); tile >= 0; tile = ring_next(ring, rt, lane), ++lt) {
             const uint32_t acc = lt & 1u;
             mbar_wait(&acc_empty[acc], ((lt >> 1) & 1u) ^ 1u);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * COUT;
+            const uint32_t d_tmem = tmem_base + acc * 2 * COUT;
             for (int kw = 0; kw < 3; ++kw, ++ia) {
                 const int sa = ia % L::kASt;
                 mbar_wait(&a_full[sa], (ia / L::kASt) & 1u);
@@ -356,12 +357,10 @@ __global__ void __launch_bounds__(kCpThreads, 1)
                         const uint64_t a_hi = make_kmajor_desc<128>(a_base + a_off);
                         const uint64_t a_lo = make_kmajor_desc<128>(a_base + L::kABytes + a_off);
                         const uint32_t w_base = sbase + L::kOffB + sb * 2 * L::kTapBytes;
-                        const uint64_t b_hi = make_kmajor_desc<128>(w_base);
-                        const uint64_t b_lo = make_kmajor_desc<128>(w_base + L::kTapBytes);
+                        const uint64_t b_hi = make_kmajor_desc<128>(w_base);          // W_hi rows, W_lo rows right behind
 #pragma unroll
                         for (int k = 0; k < CIN; k += 16) {
-                            umma_f16(d_tmem, desc_advance_k(a_hi, k), desc_advance_k(b_hi, k), idesc, (kw | kh | k) ? 1u : 0u);
-                            umma_f16(d_tmem, desc_advance_k(a_hi, k), desc_advance_k(b_lo, k), idesc, 1u);
+                            umma_f16(d_tmem, desc_advance_k(a_hi, k), desc_advance_k(b_hi, k), idesc2, (kw | kh | k) ? 1u : 0u);
                             umma_f16(d_tmem, desc_advance_k(a_lo, k), desc_advance_k(b_hi, k), idesc, 1u);
                         }
                         umma_commit(&b_empty[sb]);
@@ -383,14 +382,17 @@ __global__ void __launch_bounds__(kCpThreads, 1)
             const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
             mbar_wait(&acc_full[acc], (lt >> 1) & 1u);
             tc_fence_after();
-            const uint32_t trow = tmem_base + acc * COUT + ((uint32_t)(q * 32) << 16);
+            const uint32_t trow = tmem_base + acc * 2 * COUT + ((uint32_t)(q * 32) << 16);
             const int y2 = y0 / 2 + 2 * q + (lane >> 4), x2 = x0 / 2 + ((lane & 7) >> 1);
             const bool inside = y2 < H2 && x2 < W2;
             const int64_t pix = p.out_whc ? ((int64_t)img * W2 + x2) * H2 + y2 : ((int64_t)img * H2 + y2) * W2 + x2;
 #pragma unroll 1
             for (int c = 0; c < COUT; c += 32) {
-                float v[32], o[8];
+                float v[32], v2[32], o[8];
                 tmem_ld_32x32(trow + c, v);
+                tmem_ld_32x32(trow + COUT + c, v2);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += v2[i];
                 const int ch = c + pool2x2_split_channels<8>(v, lane, o);
                 if (inside) shift_relu_split_store8(o, p.shift + ch, p.out_hi + pix * COUT + ch, p.out_lo + pix * COUT + ch);
             }
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(kCpThreads, 1)
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<2 * COUT>(tmem_base);
+        tmem_dealloc<4 * COUT>(tmem_base);
     }
 }
 
