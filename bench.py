@@ -244,7 +244,7 @@ def main():
     ap.add_argument("--sub-batches", type=int, default=1, help="sub-batches of the host-buffer pipeline (e2e)")
     ap.add_argument("--depth", type=int, default=3, help="batches in flight in the host-buffer pipeline (e2e)")
     ap.add_argument("--streams", type=int, default=3, help="CUDA streams consecutive steps alternate over (value)")
-    ap.add_argument("--e2e-repeats", type=int, default=3, help="runs of K end-to-end steps; the median is reported")
+    ap.add_argument("--e2e-repeats", type=int, default=5, help="runs of K end-to-end steps; the median is reported")
     ap.add_argument("--numa-bind", type=int, default=1, help="bind each rank to its GPU's CPU cores before allocating pinned buffers")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work spent on the cpu_baseline sample")
     args = ap.parse_args()
@@ -354,7 +354,7 @@ def main():
     def timed_e2e(src, mark):
         """Median wall-clock time of K end-to-end steps over `e2e_repeats` runs (host-side jitter moves single runs of a
         few tens of milliseconds by a lot when the loop is not copy-bound)."""
-        e2e_loop(max(3, args.depth), src)
+        e2e_loop(max(10, 2 * args.depth), src)
         times, res = [], None
         for _ in range(max(1, args.e2e_repeats)):
             barrier()
@@ -366,8 +366,10 @@ def main():
             times.append(time.perf_counter() - t0)
             if mark:
                 sampler.mark()
+        e2e_runs.append([round(t * 1e3 / args.steps, 4) for t in times])
         return float(np.median(times)), res
 
+    e2e_runs = []                                            # ms per step of every repeat: [fp32 runs, pcm16 runs]
     e2e_s, host_logits = timed_e2e(host, True)
     clocks = sampler.stop()
     e2e_check = float((host_logits.cuda() - step_device(dev_waves[0], feats)).abs().max())   # same kernels, same result
@@ -471,13 +473,15 @@ def main():
                            f"stack and with the previous batch's GRU/head; max |logit diff| vs the device-resident "
                            f"path {e2e_check:.1e}",
                     "repeats": args.e2e_repeats, "statistic": "median of the repeats, each K steps",
+                    "ms_per_step_of_each_repeat": e2e_runs[0],
                     "h2d_copy_bound": {"h2d_gbs_per_gpu": round(B * SAMPLES * 4 / (h2d_ms * 1e-3) / 1e9, 2),
                                        "utt_s": round(total_utts / args.steps / (h2d_ms * 1e-3)),
                                        "note": "pinned host -> device copy of one fp32 batch per step, all ranks copying "
                                                "at once: the ceiling of e2e.value on this host"}},
             "e2e_pcm16": {"value": total_utts / e2e_pcm_s, "unit": "utt/s", "h2d_bytes_per_step": B * SAMPLES * 2,
                           "d2h_bytes_per_step": B * NUM_CLASSES * 4,
-                          "api": "the same submit/collect loop with int16 PCM host buffers (sir_frontend_forward_pcm16)"},
+                          "api": "the same submit/collect loop with int16 PCM host buffers (sir_frontend_forward_pcm16)",
+                          "ms_per_step_of_each_repeat": e2e_runs[1]},
             "roofline": roofline, "frontend_roofline": fr, "rooflines": rooflines, "stages": stage_out,
         }
         if not args.no_cpu_baseline:
