@@ -285,6 +285,268 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Chunk-pipelined variant for large slices: the NB = 32 * NCH utterances of a cluster are NCH independent chains of
+// 32 utterances.  Each chain has its own accumulator columns, its own gate staging buffer, its own `mma_done` and
+// `h_full` barriers and its own four warps (read-back by the first three - TMEM lane quadrants 0..2 - then the update
+// of 32 utterances x 32 units, the DSMEM pushes and the release-arrives); a ninth/fifth warp only issues MMAs.  A
+// chain's MMAs of step s+1 need nothing but that chain's rows of the hidden state, so while one chain is in its
+// update / push phase (CUDA cores, DSMEM) the other one's MMAs run on the tensor core: the phases of a step overlap
+// instead of adding up.  Nothing inside the loop synchronises more than the 128 threads of a chain (named barrier).
+// ---------------------------------------------------------------------------------------------------------------
+template <int NCH>
+struct PpLayout {
+    static constexpr int kNB = 32 * NCH;
+    static constexpr int kThreads = 128 * NCH + 32;
+    static constexpr int kHBytes = kNB * 256 * 2;                // one of (hi, lo) of one buffer: 4 K-blocks of NB rows
+    static constexpr int kOffH = 0;                              // [2 buffers][hi, lo]
+    static constexpr int kGateStride = 33;
+    static constexpr int kGateBytes = 3 * 32 * kGateStride * 4;  // per chain: [3 gates][32 units][32 utterances + 1]
+    static constexpr int kOffS = kOffH + 4 * kHBytes;
+    static constexpr int kOffBar = (kOffS + NCH * kGateBytes + 15) & ~15;
+    static constexpr int kSmemBytes = kOffBar + 8 * (3 * NCH) + 16 + 1024;
+    static_assert(kHBytes % 1024 == 0, "B operand K-blocks must stay 1024-byte aligned");
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int NCH>
+__global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(PpLayout<NCH>::kThreads, 1)
+    gru_layer_pp_kernel(const __half* __restrict__ w_hi,               // [2 dirs][8 ranks][96 rows][256] fp16
+                        const __half* __restrict__ w_lo,
+                        const float* __restrict__ gi,                  // [B*T, 1536]
+                        const float* __restrict__ bhh,                 // [2][768]
+                        float* __restrict__ y,                         // [B, T, 512]
+                        __half* __restrict__ y_hi, __half* __restrict__ y_lo, int B, int T) {
+    using L = PpLayout<NCH>;
+    constexpr int NB = L::kNB;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem + L::kOffBar);      // [NCH]
+    uint64_t* h_full = mma_done + NCH;                                         // [2 buffers][NCH]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_full + 2 * NCH);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = blockIdx.x % kGtCluster;
+    const int slice = blockIdx.x / kGtCluster;
+    const int dir = blockIdx.y;
+    const int j0 = rank * kGtUnits, b0 = slice * NB;
+    const bool issuer = warp == 4 * NCH;
+
+    if (tid == 0) {
+        for (int c = 0; c < NCH; ++c) {
+            mbar_init(&mma_done[c], 1);
+            mbar_init(&h_full[c], kGtCluster * 4);           // one arrival per warp of the chain in every CTA of the cluster
+            mbar_init(&h_full[NCH + c], kGtCluster * 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t sbase = smem_u32(smem);
+
+    // resident weights -> tensor memory: thread t < 128 owns TMEM lane t = gate row t of this CTA (zeros beyond 96)
+    if (warp < 4) {
+        const int row = tid;
+        const size_t src = ((size_t)(dir * kGtCluster + rank) * kGtWRows + row) * 256;      // halves
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+            const uint4* g = reinterpret_cast<const uint4*>((part ? w_lo : w_hi) + src);
+#pragma unroll 1
+            for (int c = 0; c < 4; c += 2) {                 // 2 x 32 columns per pass: 16 loads of 16 bytes in flight
+                uint32_t r[2][32];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint4 v = row < kGtWRows ? __ldg(g + c * 8 + i) : make_uint4(0u, 0u, 0u, 0u);
+                    r[i >> 3][4 * (i & 7) + 0] = v.x;
+                    r[i >> 3][4 * (i & 7) + 1] = v.y;
+                    r[i >> 3][4 * (i & 7) + 2] = v.z;
+                    r[i >> 3][4 * (i & 7) + 3] = v.w;
+                }
+                tmem_st_32x32(lane_addr + (part ? kGtColWlo : 0u) + (uint32_t)(c * 32), r[0]);
+                tmem_st_32x32(lane_addr + (part ? kGtColWlo : 0u) + (uint32_t)(c * 32 + 32), r[1]);
+            }
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // everybody's barriers/TMEM are set up before any peer may push into this CTA
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+
+    if (issuer) {
+        // ---- MMA issue: chain after chain, step after step; each chain's MMAs start when ITS rows are complete ------
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(128, 32);
+            for (int s = 1; s < T; ++s) {
+                const int cur = s & 1;
+                const uint32_t hb = sbase + L::kOffH + cur * 2 * L::kHBytes;
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    mbar_wait_cluster(&h_full[cur * NCH + c], (uint32_t)((s - 1) >> 1) & 1u);   // the chain's pushes of step s-1
+                    tc_fence_after();
+                    const uint32_t d_acc = tmem_base + kGtColAcc + (uint32_t)(c * 32);
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const uint64_t b_hi = make_kmajor_desc<128>(hb + kb * (NB * 128) + c * (32 * 128));
+                        const uint64_t b_lo = make_kmajor_desc<128>(hb + L::kHBytes + kb * (NB * 128) + c * (32 * 128));
+#pragma unroll
+                        for (int k = 0; k < 64; k += 16) {
+                            const uint32_t a_hi = tmem_base + (uint32_t)((kb * 64 + k) >> 1);      // 2 halves per column
+                            const uint32_t a_lo = a_hi + kGtColWlo;
+                            umma_f16_ts(d_acc, a_hi, desc_advance_k(b_hi, k), idesc, (kb | k) ? 1u : 0u);
+                            umma_f16_ts(d_acc, a_hi, desc_advance_k(b_lo, k), idesc, 1u);
+                            umma_f16_ts(d_acc, a_lo, desc_advance_k(b_hi, k), idesc, 1u);
+                        }
+                    }
+                    umma_commit(&mma_done[c]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- one chain: 4 warps, thread -> (utterance ui of the slice, group of 8 hidden units ug) -----------------
+        const int chain = warp >> 2, wq = warp & 3;
+        const int ui = tid >> 2, ug = tid & 3, uc = ui & 31;
+        const int ubb = b0 + ui;
+        const bool uvalid = ubb < B;
+        float* s_gate = reinterpret_cast<float*>(smem + L::kOffS + chain * L::kGateBytes);
+        float b_r[8], b_z[8], b_n[8], hprev[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int u = j0 + 8 * ug + e;
+            b_r[e] = __ldg(bhh + dir * 768 + u);
+            b_z[e] = __ldg(bhh + dir * 768 + 256 + u);
+            b_n[e] = __ldg(bhh + dir * 768 + 512 + u);
+            hprev[e] = 0.f;
+        }
+        // where this thread's 16-byte chunk (8 units of utterance ui) sits inside a swizzled B-operand buffer
+        uint32_t chunk_off = 0;
+        {
+            const int k = j0 + 8 * ug, kb = k >> 6, chunk = (k & 63) >> 3;
+            chunk_off = (uint32_t)(kb * (NB * 128) + (ui >> 3) * 1024 + (ui & 7) * 128 + ((chunk ^ (ui & 7)) << 4));
+        }
+        for (int s = 0; s < T; ++s) {
+            const int t = dir == 0 ? s : T - 1 - s;
+            const int nxt = (s & 1) ^ 1;
+            // gate pre-activations of the input projection (consumed after the MMA: the loads overlap it)
+            float4 gin[3][2];
+            {
+                const float4* gp = reinterpret_cast<const float4*>(
+                    gi + ((int64_t)(uvalid ? ubb : B - 1) * T + t) * 1536 + dir * 768 + j0 + 8 * ug);
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    gin[g][0] = __ldg(gp + g * 64);
+                    gin[g][1] = __ldg(gp + g * 64 + 1);
+                }
+            }
+            if (s > 0) {
+                // accumulator rows of this chain -> its staging buffer, transposed to [gate][unit][utterance]
+                if (wq < 3) {
+                    mbar_wait(&mma_done[chain], (uint32_t)(s - 1) & 1u);
+                    tc_fence_after();
+                    float v[32];
+                    tmem_ld_32x32(tmem_base + kGtColAcc + (uint32_t)(chain * 32) + ((uint32_t)(wq * 32) << 16), v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) s_gate[(wq * 32 + lane) * L::kGateStride + i] = v[i];
+                    tc_fence_before();
+                }
+                named_barrier_sync(1 + chain, 128);
+            }
+            const float gr[8] = {gin[0][0].x, gin[0][0].y, gin[0][0].z, gin[0][0].w,
+                                 gin[0][1].x, gin[0][1].y, gin[0][1].z, gin[0][1].w};
+            const float gz[8] = {gin[1][0].x, gin[1][0].y, gin[1][0].z, gin[1][0].w,
+                                 gin[1][1].x, gin[1][1].y, gin[1][1].z, gin[1][1].w};
+            const float gn[8] = {gin[2][0].x, gin[2][0].y, gin[2][0].z, gin[2][0].w,
+                                 gin[2][1].x, gin[2][1].y, gin[2][1].z, gin[2][1].w};
+            float hn[8];
+            uint32_t hi2[4], lo2[4];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float ar = 0.f, az = 0.f, an = 0.f;
+                if (s > 0) {
+                    const int u = 8 * ug + e;
+                    ar = s_gate[(0 * 32 + u) * L::kGateStride + uc];
+                    az = s_gate[(1 * 32 + u) * L::kGateStride + uc];
+                    an = s_gate[(2 * 32 + u) * L::kGateStride + uc];
+                }
+                const float r = sigmoid_f(gr[e] + ar + b_r[e]);
+                const float z = sigmoid_f(gz[e] + az + b_z[e]);
+                const float n = tanh_f(gn[e] + r * (an + b_n[e]));
+                hn[e] = (1.f - z) * n + z * hprev[e];
+                hprev[e] = hn[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                __half h0, l0, h1, l1;
+                split_f16(hn[e], h0, l0);
+                split_f16(hn[e + 1], h1, l1);
+                hi2[e >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                lo2[e >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            const uint4 vhi = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
+            const uint4 vlo = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
+            if (s + 1 < T) {
+                const uint32_t dst = sbase + L::kOffH + nxt * 2 * L::kHBytes + chunk_off;
+#pragma unroll
+                for (int c = 0; c < kGtCluster; ++c) {
+                    const uint32_t ra = map_to_cta(dst, (uint32_t)c);
+                    st_cluster_v4(ra, vhi);
+                    st_cluster_v4(ra + L::kHBytes, vlo);
+                }
+                // generic-proxy stores -> async proxy (the peers' MMAs read them), then one release-arrive per warp
+                // and peer on the CHAIN's barrier: lane c signals CTA c
+                fence_proxy_async_all();
+                __syncwarp();
+                if (lane < kGtCluster) mbar_arrive_remote(map_to_cta(smem_u32(&h_full[nxt * NCH + chain]), (uint32_t)lane));
+            }
+            if (uvalid) {
+                const int64_t o = ((int64_t)ubb * T + t) * 512 + dir * 256 + j0 + 8 * ug;
+                float4* yo = reinterpret_cast<float4*>(y + o);
+                yo[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                yo[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                if (y_hi) {
+                    *reinterpret_cast<uint4*>(y_hi + o) = vhi;
+                    *reinterpret_cast<uint4*>(y_lo + o) = vlo;
+                }
+            }
+        }
+    }
+    // no CTA leaves while a peer might still signal it
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+template <int NCH>
+static int launch_gru_pp(const __half* w_hi, const __half* w_lo, const float* gi, const float* bhh, float* y,
+                         __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st) {
+    using L = PpLayout<NCH>;
+    static bool attr = false;
+    if (!attr) {
+        SIR_CUDA(cudaFuncSetAttribute(gru_layer_pp_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes));
+        attr = true;
+    }
+    dim3 grid((unsigned)(kGtCluster * ((B + L::kNB - 1) / L::kNB)), 2);
+    gru_layer_pp_kernel<NCH><<<grid, L::kThreads, L::kSmemBytes, st>>>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T);
+    SIR_CHECK_LAUNCH("gru_layer_pp_kernel");
+    return SIR_OK;
+}
+
 template <int NB>
 static int launch_gru(const __half* w_hi, const __half* w_lo, const float* gi, const float* bhh, float* y,
                       __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st) {
@@ -314,7 +576,7 @@ int gru_layer_tc(const __half* w_hi, const __half* w_lo, const float* gi, const 
     // SMs per 64 utterances instead of 8 per 48 (256 utterances: 64 instead of 96 SMs), and the SMs it leaves take
     // the frontend / conv stack of the next batch, which runs on another stream (measured: +5 % utterances/s).
     if (B <= 3 * 48) return launch_gru<48>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
-    return launch_gru<64>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
+    return launch_gru_pp<2>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
 }
 
 }  // namespace tc
