@@ -334,7 +334,7 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(PpLayout<NC
     const int slice = blockIdx.x / kGtCluster;
     const int dir = blockIdx.y;
     const int j0 = rank * kGtUnits, b0 = slice * NB;
-    const bool issuer = warp == 4 * NCH;
+    const bool issuer = uniform_warp_idx() == 4 * NCH;       // provably warp-uniform: the MMA operands stay in uniform registers
 
     if (tid == 0) {
         for (int c = 0; c < NCH; ++c) {
@@ -384,16 +384,17 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(PpLayout<NC
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 
     if (issuer) {
-        // ---- MMA issue: chain after chain, step after step; each chain's MMAs start when ITS rows are complete ------
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(128, 32);
-            for (int s = 1; s < T; ++s) {
-                const int cur = s & 1;
-                const uint32_t hb = sbase + L::kOffH + cur * 2 * L::kHBytes;
+        // ---- MMA issue: chain after chain, step after step; each chain's MMAs start when ITS rows are complete.  All
+        // 32 lanes walk the loop (uniform control flow and operands), one elected lane issues.
+        constexpr uint32_t idesc = make_idesc_f16(128, 32);
+        for (int s = 1; s < T; ++s) {
+            const int cur = s & 1;
+            const uint32_t hb = sbase + L::kOffH + cur * 2 * L::kHBytes;
 #pragma unroll 1
-                for (int c = 0; c < NCH; ++c) {
-                    mbar_wait_cluster(&h_full[cur * NCH + c], (uint32_t)((s - 1) >> 1) & 1u);   // the chain's pushes of step s-1
-                    tc_fence_after();
+            for (int c = 0; c < NCH; ++c) {
+                mbar_wait_cluster(&h_full[cur * NCH + c], (uint32_t)((s - 1) >> 1) & 1u);   // the chain's pushes of step s-1
+                tc_fence_after();
+                if (elect_one_sync()) {
                     const uint32_t d_acc = tmem_base + kGtColAcc + (uint32_t)(c * 32);
 #pragma unroll
                     for (int kb = 0; kb < 4; ++kb) {
@@ -410,9 +411,9 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(PpLayout<NC
                     }
                     umma_commit(&mma_done[c]);
                 }
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else {
         // ---- one chain: 4 warps, thread -> (utterance ui of the slice, group of 8 hidden units ug) -----------------
         const int chain = warp >> 2, wq = warp & 3;
