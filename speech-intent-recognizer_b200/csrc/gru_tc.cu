@@ -151,6 +151,7 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 
     constexpr uint32_t idesc = make_idesc_f16(128, NB);
+    const bool issue_warp = uniform_warp_idx() == kGtThreads / 32 - 1;      // provably warp-uniform
 
     for (int s = 0; s < T; ++s) {
         const int t = dir == 0 ? s : T - 1 - s;
@@ -168,26 +169,29 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
         }
         if (s > 0) {
             // (1) D[128 gate rows, NB utterances] = W_slice[128, 256] . h^T   (h: buffer `cur`)
-            if (tid == kGtThreads - 32) {          // lane 0 of the last warp, which has no update work: the MMAs of
-                                                   // step s start the moment the state is complete
+            if (issue_warp) {                      // the last warp has no update work: the MMAs of step s start the
+                                                   // moment the state is complete; all lanes walk, one elected lane issues
                 mbar_wait_cluster(&h_full[cur], (uint32_t)((s - 1) >> 1) & 1u);     // all 8 CTAs' pushes of step s-1 landed
                 tc_fence_after();
-                const uint32_t hb = sbase + L::kOffH + cur * 2 * L::kHBytes;
-                const uint32_t d_acc = tmem_base + kGtColAcc;
+                if (elect_one_sync()) {
+                    const uint32_t hb = sbase + L::kOffH + cur * 2 * L::kHBytes;
+                    const uint32_t d_acc = tmem_base + kGtColAcc;
 #pragma unroll
-                for (int kb = 0; kb < 4; ++kb) {
-                    const uint64_t b_hi = make_kmajor_desc<128>(hb + kb * (NB * 128));
-                    const uint64_t b_lo = make_kmajor_desc<128>(hb + L::kHBytes + kb * (NB * 128));
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const uint64_t b_hi = make_kmajor_desc<128>(hb + kb * (NB * 128));
+                        const uint64_t b_lo = make_kmajor_desc<128>(hb + L::kHBytes + kb * (NB * 128));
 #pragma unroll
-                    for (int k = 0; k < 64; k += 16) {
-                        const uint32_t a_hi = tmem_base + (uint32_t)((kb * 64 + k) >> 1);      // 2 halves per column
-                        const uint32_t a_lo = a_hi + kGtColWlo;
-                        umma_f16_ts(d_acc, a_hi, desc_advance_k(b_hi, k), idesc, (kb | k) ? 1u : 0u);
-                        umma_f16_ts(d_acc, a_hi, desc_advance_k(b_lo, k), idesc, 1u);
-                        umma_f16_ts(d_acc, a_lo, desc_advance_k(b_hi, k), idesc, 1u);
+                        for (int k = 0; k < 64; k += 16) {
+                            const uint32_t a_hi = tmem_base + (uint32_t)((kb * 64 + k) >> 1);      // 2 halves per column
+                            const uint32_t a_lo = a_hi + kGtColWlo;
+                            umma_f16_ts(d_acc, a_hi, desc_advance_k(b_hi, k), idesc, (kb | k) ? 1u : 0u);
+                            umma_f16_ts(d_acc, a_hi, desc_advance_k(b_lo, k), idesc, 1u);
+                            umma_f16_ts(d_acc, a_lo, desc_advance_k(b_hi, k), idesc, 1u);
+                        }
                     }
+                    umma_commit(mma_done);
                 }
-                umma_commit(mma_done);
+                __syncwarp();
             }
             // (2) accumulator rows -> shared memory, transposed to [gate][unit][utterance]
             if (warp < 3) {
