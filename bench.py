@@ -51,11 +51,11 @@ SPLIT_PASSES = {"conv2_bn_relu_pool": 3, "conv3_bn_relu_pool": 3, "gru_l0_input_
                 "gru_l0_recurrence": 3, "gru_l1_recurrence": 3}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of THIS workload
 # (256 utterances; profiles/r1_summary.md names the capture of each row).  None: not captured for this build.
-NCU_TRAFFIC_B256 = {   # captures r1f (profiles/r1f_ncu_*.txt)
-    "logmel_frontend_kernel": 54.19e6 + 1.19e6, "conv1_bn_relu_pool": 21.83e6 + 58.64e6,
-    "conv2_bn_relu_pool": 104.96e6 + 27.19e6, "conv3_bn_relu_pool": 52.76e6 + 3.09e6,
-    "gru_l0_input_gemm": 32.54e6 + 2.50e6, "gru_l1_input_gemm": 16.28e6 + 0.31e6,
-    "gru_l0_recurrence": 40.93e6 + 0.30e6, "gru_l1_recurrence": 40.93e6 + 0.03e6,
+NCU_TRAFFIC_B256 = {   # captures r1g (profiles/r1g_ncu_*.txt)
+    "logmel_frontend_kernel": 54.17e6 + 0.85e6, "conv1_bn_relu_pool": 22.68e6 + 63.17e6,
+    "conv2_bn_relu_pool": 104.97e6 + 30.97e6, "conv3_bn_relu_pool": 52.76e6 + 4.88e6,
+    "gru_l0_input_gemm": 32.53e6 + 3.28e6, "gru_l1_input_gemm": 16.28e6 + 0.34e6,
+    "gru_l0_recurrence": 40.92e6 + 0.27e6, "gru_l1_recurrence": 40.92e6 + 0.03e6,
 }
 
 
@@ -242,7 +242,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="utterances per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sub-batches", type=int, default=1, help="sub-batches of the host-buffer pipeline (e2e)")
-    ap.add_argument("--depth", type=int, default=3, help="batches in flight in the host-buffer pipeline (e2e)")
+    ap.add_argument("--depth", type=int, default=4, help="batches in flight in the host-buffer pipeline (e2e)")
     ap.add_argument("--streams", type=int, default=3, help="CUDA streams consecutive steps alternate over (value)")
     ap.add_argument("--e2e-repeats", type=int, default=5, help="runs of K end-to-end steps; the median is reported")
     ap.add_argument("--numa-bind", type=int, default=1, help="bind each rank to its GPU's CPU cores before allocating pinned buffers")
@@ -446,7 +446,7 @@ def main():
                 out["note"] = ("fp32-accurate 3-pass fp16 hi/lo split: the tensor pipe executes 3x the algorithmic FLOPs "
                                f"({round(3 * ach, 1)} TFLOP/s of fp16 MMA work)")
             if "recurrence" in name:
-                out["note"] = "latency chain of 25 dependent time steps (one launch per layer, 5.4 us per step at 64 utterances per cluster); " + out.get("note", "")
+                out["note"] = "latency chain of 25 dependent time steps (one launch per layer, 4.05 us per step, two 32-utterance chains per cluster); " + out.get("note", "")
             return out
 
         rooflines = [stage_roofline(k) for k in stage_out]

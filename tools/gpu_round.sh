@@ -16,7 +16,7 @@ if [ "${NCU:-1}" = "1" ]; then
   # full capture of the tensor-core contractions of one warm step (conv2, conv3, gemm l0, gemm l1) and the frontend
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv3x3_persistent|conv3x3_stream|gemm_persistent" --launch-skip 16 -c 4 \
       -o $OUT/${TAG}_tc -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_tc.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"logmel_frontend|gru_layer_tc|conv1_bn" --launch-skip 16 -c 4 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"logmel_frontend|gru_layer|conv1_bn" --launch-skip 16 -c 4 \
       -o $OUT/${TAG}_fe -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_fe.log 2>&1
   for r in tc fe; do
     ncu -i $OUT/${TAG}_$r.ncu-rep --page raw --csv > $OUT/${TAG}_${r}_raw.csv 2>/dev/null
