@@ -409,13 +409,6 @@ extern "C" int sir_model_create(sir_model** out, int num_classes, int n_mels) {
         m->wih_lo[l] = hb + h_ih[l][1];
         m->whh_hi[l] = hb + h_hh[l][0];
         m->whh_lo[l] = hb + h_hh[l][1];
-        const uint64_t wd[2] = {256, 2 * 8 * 96};
-        const uint32_t wb[2] = {64, 96};
-        if ((rc = tc::make_tmap(&m->tm_whh_hi[l], m->whh_hi[l], 2, wd, wb)) ||
-            (rc = tc::make_tmap(&m->tm_whh_lo[l], m->whh_lo[l], 2, wd, wb))) {
-            sir_model_destroy(m);
-            return rc;
-        }
     }
     *out = m;
     return SIR_OK;

@@ -7,7 +7,7 @@
 // weights of hidden units [32 r, 32 r + 32) - 96 gate rows as fp16 (hi, lo) pairs, 96 KB - resident in TENSOR
 // MEMORY for all steps (written once with tcgen05.st: lane = gate row, 128 columns each for hi and lo; rows 96..127
 // are zero): the MMAs take A from TMEM and fetch only the hidden state from shared memory, and the CTA's shared
-// memory footprint (117 KB) leaves room for another kernel's CTA on the same SM.  The hidden state
+// memory footprint no longer includes them.  The hidden state
 // never leaves the chip between steps: it lives as the fp16 (hi, lo) B operand [NB x 256] in every CTA's
 // shared memory (128-byte swizzled K-major, double buffered).  Per step:
 //   1. one thread issues 48 tcgen05.mma (128 x NB x 16; hi.hi, hi.lo, lo.hi over K = 256) into a TMEM
@@ -21,6 +21,7 @@
 //      `h_full` before the next step's MMAs.  No cluster-wide barrier inside the loop: a CTA only waits for the data it
 //      needs, and the warps that are not on the critical path run ahead.
 // No grid-wide synchronisation, no per-step launch, no L2 round trip on the recurrence's critical path.
+// Slices of 64 utterances (batches > 144) run the chain-pipelined variant further down (gru_layer_pp_kernel).
 #include "sir_common.cuh"
 #include "tc_common.cuh"
 
@@ -56,8 +57,8 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
                  : "memory");
 }
 // Gate non-linearities on the SFU: ex2.approx + rcp.approx (relative error ~1e-6, far inside the 1e-3 logit bar)
-// instead of expf / tanhf / IEEE division, which cost ~1.2 us of the ~7 us per time step (measured by switching
-// them off, tools/gru_experiments.sh).  tanh(x) = 1 - 2 / (1 + e^{2x}) saturates correctly for large |x|.
+// instead of expf / tanhf / IEEE division, which cost ~1.2 us of the ~7 us per time step of the first version
+// (measured by switching them off).  tanh(x) = 1 - 2 / (1 + e^{2x}) saturates correctly for large |x|.
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_f(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 

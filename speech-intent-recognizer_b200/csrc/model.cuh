@@ -107,7 +107,6 @@ struct sir_model {
     __half *w2t_hi = nullptr, *w2t_lo = nullptr, *w3t_hi = nullptr, *w3t_lo = nullptr;
     __half *wih_hi[2] = {nullptr, nullptr}, *wih_lo[2] = {nullptr, nullptr};
     __half *whh_hi[2] = {nullptr, nullptr}, *whh_lo[2] = {nullptr, nullptr};
-    CUtensorMap tm_whh_hi[2], tm_whh_lo[2];
     sir::TrainSaved ts;
     bool have_saved = false;
     int num_sms = 148;
