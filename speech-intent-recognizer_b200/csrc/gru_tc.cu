@@ -56,6 +56,14 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
     asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
 }
+// Asynchronous 16-byte store into a peer CTA's shared memory that completes 16 transaction bytes on an mbarrier of
+// that CTA when the data has landed: the store and its completion signal travel together, the issuing thread neither
+// fences nor waits (a release-arrive after plain st.shared::cluster costs a MEMBAR.ALL.GPU per warp and step).
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint4 v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr),
+                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar)
+                 : "memory");
+}
 // Gate non-linearities on the SFU: ex2.approx + rcp.approx (relative error ~1e-6, far inside the 1e-3 logit bar)
 // instead of expf / tanhf / IEEE division, which cost ~1.2 us of the ~7 us per time step of the first version
 // (measured by switching them off).  tanh(x) = 1 - 2 / (1 + e^{2x}) saturates correctly for large |x|.
@@ -344,8 +352,8 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(PpLayout<NC
     if (tid == 0) {
         for (int c = 0; c < NCH; ++c) {
             mbar_init(&mma_done[c], 1);
-            mbar_init(&h_full[c], kGtCluster * 4);           // one arrival per warp of the chain in every CTA of the cluster
-            mbar_init(&h_full[NCH + c], kGtCluster * 4);
+            mbar_init(&h_full[c], 1);                        // the issuer's arrive.expect_tx; the pushes complete the bytes
+            mbar_init(&h_full[NCH + c], 1);
         }
         fence_barrier_init();
     }
@@ -392,14 +400,20 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(PpLayout<NC
         // ---- MMA issue: chain after chain, step after step; each chain's MMAs start when ITS rows are complete.  All
         // 32 lanes walk the loop (uniform control flow and operands), one elected lane issues.
         constexpr uint32_t idesc = make_idesc_f16(128, 32);
+        constexpr uint32_t kChainBytes = 32 * 256 * 2 * 2;   // a chain's rows of the hidden state, hi + lo: what 8 CTAs push
+        if (T > 1 && elect_one_sync())
+            for (int c = 0; c < NCH; ++c) mbar_arrive_expect_tx(&h_full[NCH + c], kChainBytes);   // the pushes of step 0
+        __syncwarp();
         for (int s = 1; s < T; ++s) {
             const int cur = s & 1;
             const uint32_t hb = sbase + L::kOffH + cur * 2 * L::kHBytes;
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
                 mbar_wait_cluster(&h_full[cur * NCH + c], (uint32_t)((s - 1) >> 1) & 1u);   // the chain's pushes of step s-1
+                fence_proxy_async_all();                     // the pushes were generic-proxy writes; the MMAs read through the async proxy
                 tc_fence_after();
                 if (elect_one_sync()) {
+                    if (s + 1 < T) mbar_arrive_expect_tx(&h_full[(cur ^ 1) * NCH + c], kChainBytes);   // the pushes of step s
                     const uint32_t d_acc = tmem_base + kGtColAcc + (uint32_t)(c * 32);
 #pragma unroll
                     for (int kb = 0; kb < 4; ++kb) {
@@ -503,17 +517,13 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(PpLayout<NC
             const uint4 vlo = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
             if (s + 1 < T) {
                 const uint32_t dst = sbase + L::kOffH + nxt * 2 * L::kHBytes + chunk_off;
+                const uint32_t bar = smem_u32(&h_full[nxt * NCH + chain]);
 #pragma unroll
-                for (int c = 0; c < kGtCluster; ++c) {
-                    const uint32_t ra = map_to_cta(dst, (uint32_t)c);
-                    st_cluster_v4(ra, vhi);
-                    st_cluster_v4(ra + L::kHBytes, vlo);
+                for (int c = 0; c < kGtCluster; ++c) {       // each store completes its 16 bytes on the CHAIN's barrier of CTA c
+                    const uint32_t ra = map_to_cta(dst, (uint32_t)c), rb = map_to_cta(bar, (uint32_t)c);
+                    st_async_v4(ra, vhi, rb);
+                    st_async_v4(ra + L::kHBytes, vlo, rb);
                 }
-                // generic-proxy stores -> async proxy (the peers' MMAs read them), then one release-arrive per warp
-                // and peer on the CHAIN's barrier: lane c signals CTA c
-                fence_proxy_async_all();
-                __syncwarp();
-                if (lane < kGtCluster) mbar_arrive_remote(map_to_cta(smem_u32(&h_full[nxt * NCH + chain]), (uint32_t)lane));
             }
             if (uvalid) {
                 const int64_t o = ((int64_t)ubb * T + t) * 512 + dir * 256 + j0 + 8 * ug;
