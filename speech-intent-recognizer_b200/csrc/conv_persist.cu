@@ -225,12 +225,13 @@ int tc_conv3x3_persistent(const __half* in_hi, const __half* in_lo, const __half
         attr = true;
     }
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    p.tickets = tickets ? tickets->take(p.num_tiles, grid) : TileTickets{nullptr, 0};
+    p.tickets = tickets ? tickets->first() : TileTickets{nullptr, 0};
     {
         ProfScope ps(name, st);
         kern<<<grid, kCpThreads, L::kSmemBytes, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
     }
     SIR_CHECK_LAUNCH(name);
+    if (tickets) tickets->consumed(p.num_tiles, grid);
     return SIR_OK;
 }
 
@@ -441,12 +442,13 @@ int tc_conv3x3_stream(const __half* in_hi, const __half* in_lo, const __half* w_
         attr = true;
     }
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    p.tickets = tickets ? tickets->take(p.num_tiles, grid) : TileTickets{nullptr, 0};
+    p.tickets = tickets ? tickets->first() : TileTickets{nullptr, 0};
     {
         ProfScope ps(name, st);
         kern<<<grid, kCpThreads, L::kSmemBytes, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
     }
     SIR_CHECK_LAUNCH(name);
+    if (tickets) tickets->consumed(p.num_tiles, grid);
     return SIR_OK;
 }
 

@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(kFeThreads, SIR_FE_MIN_CTAS) logmel_frontend_k
         if (tid == 0) *s_item = fetched;
         __syncthreads();                                    // also: tables visible (first pass), previous item fully done
         const long long item = *s_item;
-        if (item >= total_items) break;
+        if (item < 0 || item >= total_items) break;         // (negative: the host's ticket base is ahead of the counter)
         if (tid == 0) fetched = (long long)(atomicAdd(p.work_counter, 1ULL) - p.work_base);
         process_item(item);
         __syncthreads();                                    // tile / red[] / scratch / s_item consumed
@@ -783,7 +783,6 @@ static int frontend_launch(sir_frontend* fe, const void* d_wave, bool pcm16, int
     }
     p.work_counter = (unsigned long long*)ws.tickets.ptr;
     p.work_base = ws.next_ticket;
-    ws.next_ticket += (unsigned long long)(items + grid);   // every CTA draws its items + 1 tickets
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kFeThreads);
@@ -799,6 +798,7 @@ static int frontend_launch(sir_frontend* fe, const void* d_wave, bool pcm16, int
             SIR_CUDA(cudaLaunchKernelEx(&cfg, logmel_frontend_kernel<float>, p));
     }
     SIR_CHECK_LAUNCH("logmel_frontend_kernel");
+    ws.next_ticket += (unsigned long long)(items + grid);   // every CTA draws its items + 1 tickets (a failed launch: none)
     return SIR_OK;
 }
 

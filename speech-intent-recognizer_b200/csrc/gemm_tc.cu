@@ -469,12 +469,13 @@ static int tc_gemm_nt_persistent(const __half* a_hi, const __half* a_lo, const _
         attr = true;
     }
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    p.tickets = tickets ? tickets->take(p.num_tiles, grid) : TileTickets{nullptr, 0};
+    p.tickets = tickets ? tickets->first() : TileTickets{nullptr, 0};
     {
         ProfScope ps(name, st);
         gemm_persistent_kernel<<<grid, kTcThreads, L::kSmemBytes, st>>>(tw_hi, tw_lo, tx_hi, tx_lo, p);
     }
     SIR_CHECK_LAUNCH(name);
+    if (tickets) tickets->consumed(p.num_tiles, grid);
     return SIR_OK;
 }
 

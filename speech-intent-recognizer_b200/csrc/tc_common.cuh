@@ -100,15 +100,14 @@ struct TileTickets {
     unsigned long long* counter;
     unsigned long long base;
 };
-// Host view of a ticket counter: launches that share one must be stream-ordered; take() reserves a launch's tickets.
+// Host view of a ticket counter: launches that share one must be stream-ordered.  first() is the launch's first
+// ticket; consumed() is called once the launch has been accepted (a failed launch draws nothing, so the host's
+// idea of the counter must not move either).
 struct TicketSource {
     unsigned long long* dev = nullptr;
     unsigned long long next = 0;
-    TileTickets take(long long num_tiles, long long grid) {
-        TileTickets t{dev, next};
-        next += (unsigned long long)(num_tiles + grid);
-        return t;
-    }
+    TileTickets first() const { return TileTickets{dev, next}; }
+    void consumed(long long num_tiles, long long grid) { next += (unsigned long long)(num_tiles + grid); }
 };
 constexpr int kRingDepth = 4;
 struct TileRing {
