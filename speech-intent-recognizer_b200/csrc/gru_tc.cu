@@ -16,10 +16,10 @@
 //   3. every thread updates 8 hidden units of one utterance, writes h' to the layer output y (fp32, plus the
 //      fp16 pair the next layer's input GEMM consumes) and PUSHES the fp16 (hi, lo) of its 8 units - one
 //      16-byte chunk each - into the next-step B operand of all 8 CTAs through distributed shared memory;
-//   4. every updater warp fences its pushes towards the async proxy and ARRIVES (release, cluster scope) on the
-//      `h_full` mbarrier of all 8 CTAs; the MMA-issuing thread of each CTA waits (acquire, cluster scope) on its own
-//      `h_full` before the next step's MMAs.  No cluster-wide barrier inside the loop: a CTA only waits for the data it
-//      needs, and the warps that are not on the critical path run ahead.
+//   4. the pushes are st.async stores that complete their bytes on the `h_full` mbarrier of the CTA they land in; the
+//      MMA-issuing warp of each CTA posts the expected byte count, waits (acquire, cluster scope) on its own `h_full`,
+//      fences towards the async proxy and issues the next step's MMAs.  No cluster-wide barrier, no fence and no
+//      arrive on the pushing warps: a CTA only waits for the data it needs.
 // No grid-wide synchronisation, no per-step launch, no L2 round trip on the recurrence's critical path.
 // Slices of 64 utterances (batches > 144) run the chain-pipelined variant further down (gru_layer_pp_kernel).
 #include "sir_common.cuh"
@@ -52,10 +52,6 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                 : "memory");
-}
 // Asynchronous 16-byte store into a peer CTA's shared memory that completes 16 transaction bytes on an mbarrier of
 // that CTA when the data has landed: the store and its completion signal travel together, the issuing thread neither
 // fences nor waits (a release-arrive after plain st.shared::cluster costs a MEMBAR.ALL.GPU per warp and step).
@@ -85,7 +81,6 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
     uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
     uint64_t* h_full = mma_done + 1;          // [2]: operand buffer b holds the complete hidden state of the next step
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_full + 2);
-    constexpr uint32_t kUpdaterWarps = 4 * NB / 32;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = blockIdx.x % kGtCluster;
@@ -95,8 +90,8 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
 
     if (tid == 0) {
         mbar_init(mma_done, 1);
-        mbar_init(&h_full[0], kGtCluster * kUpdaterWarps);      // one arrival per updater warp of every CTA of the cluster
-        mbar_init(&h_full[1], kGtCluster * kUpdaterWarps);
+        mbar_init(&h_full[0], 1);                               // the issuer's arrive.expect_tx; the pushes complete the bytes
+        mbar_init(&h_full[1], 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -160,7 +155,12 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 
     constexpr uint32_t idesc = make_idesc_f16(128, NB);
+    constexpr uint32_t kStateBytes = NB * 256 * 2 * 2;                      // the slice's hidden state, hi + lo: what 8 CTAs push
     const bool issue_warp = uniform_warp_idx() == kGtThreads / 32 - 1;      // provably warp-uniform
+    if (issue_warp) {
+        if (T > 1 && elect_one_sync()) mbar_arrive_expect_tx(&h_full[1], kStateBytes);      // the pushes of step 0
+        __syncwarp();
+    }
 
     for (int s = 0; s < T; ++s) {
         const int t = dir == 0 ? s : T - 1 - s;
@@ -181,8 +181,10 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
             if (issue_warp) {                      // the last warp has no update work: the MMAs of step s start the
                                                    // moment the state is complete; all lanes walk, one elected lane issues
                 mbar_wait_cluster(&h_full[cur], (uint32_t)((s - 1) >> 1) & 1u);     // all 8 CTAs' pushes of step s-1 landed
+                fence_proxy_async_all();             // the pushes were generic-proxy writes; the MMAs read through the async proxy
                 tc_fence_after();
                 if (elect_one_sync()) {
+                    if (s + 1 < T) mbar_arrive_expect_tx(&h_full[nxt], kStateBytes);          // the pushes of step s
                     const uint32_t hb = sbase + L::kOffH + cur * 2 * L::kHBytes;
                     const uint32_t d_acc = tmem_base + kGtColAcc;
 #pragma unroll
@@ -263,17 +265,13 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(kGtThreads,
             const uint4 vlo = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
             if (s + 1 < T) {
                 const uint32_t dst = sbase + L::kOffH + nxt * 2 * L::kHBytes + chunk_off;
+                const uint32_t bar = smem_u32(&h_full[nxt]);
 #pragma unroll
-                for (int c = 0; c < kGtCluster; ++c) {
-                    const uint32_t ra = map_to_cta(dst, (uint32_t)c);
-                    st_cluster_v4(ra, vhi);
-                    st_cluster_v4(ra + L::kHBytes, vlo);
+                for (int c = 0; c < kGtCluster; ++c) {       // (4) each store completes its 16 bytes on h_full of CTA c
+                    const uint32_t ra = map_to_cta(dst, (uint32_t)c), rb = map_to_cta(bar, (uint32_t)c);
+                    st_async_v4(ra, vhi, rb);
+                    st_async_v4(ra + L::kHBytes, vlo, rb);
                 }
-                // (4) generic-proxy stores -> async proxy (the peers' MMAs read them), then one release-arrive per
-                // warp and peer: lane c signals CTA c
-                fence_proxy_async_all();
-                __syncwarp();
-                if (lane < kGtCluster) mbar_arrive_remote(map_to_cta(smem_u32(&h_full[nxt]), (uint32_t)lane));
             }
             if (uvalid) {
                 const int64_t o = ((int64_t)ubb * T + t) * 512 + dir * 256 + j0 + 8 * ug;
