@@ -414,3 +414,38 @@ def test_config3_shard_precompute_properties(fe):
     assert torch.equal(feats[:12], feats[B - 12:])                      # position in the batch does not matter
     want = logmel_np.extract_features(base[5].cpu().numpy())
     assert rel_to_scale(feats[5].cpu().numpy(), want) < FEATURE_REL_TOL
+
+
+def test_config1_mic_recording_durations_batch1_and_ragged(fe, model):
+    """BASELINE config 1: 95 clips with the durations of the reference's mic_recordings (1.27-3.36 s at 16 kHz), one
+    utterance per call with its own T (scripts/test_model.py:106-139: features -> pad to 200 -> model -> arg-max),
+    against the same clips as ONE ragged batch and, for a sample of them, against the oracle."""
+    lens = synth.config1_lengths()
+    assert len(lens) == 95 and lens.min() == 20352 and lens.max() == 53760
+    waves = synth.speech_like(41, len(lens), int(lens.max()), lengths=lens)
+    d_w = dev(waves)
+    feats = fe.forward(d_w, lengths=dev(lens.astype(np.int32)), out_frames=200)        # ragged batch
+    logits = model.forward(feats)
+    sd = synth.make_weights(1234)
+    checked = 0
+    for i in range(len(lens)):
+        n = int(lens[i])
+        f1 = fe.forward(d_w[i:i + 1, :n].contiguous())                                 # batch 1, unpadded [1, 64, T_i]
+        T = 1 + n // 512
+        assert f1.shape == (1, 64, T)
+        # a batch of one and the ragged batch agree to rounding (different output widths sum partials differently)
+        assert rel_to_scale(f1[0].cpu().numpy(), feats[i, :, :T].cpu().numpy()) < 1e-6, i
+        assert not feats[i, :, T:].any().item()
+        l1 = model.forward(torch.nn.functional.pad(f1, (0, 200 - T)))
+        assert float((l1[0] - logits[i]).abs().max()) < 1e-4, i
+        if i % 12 == 0:                                                                 # 8 clips against the oracle
+            want_f = logmel_np.dataset_item(waves[i, :n], target=200, max_duration=None)
+            assert rel_to_scale(feats[i].cpu().numpy(), want_f) < FEATURE_REL_TOL, i
+            want = classifier_np.forward(want_f[None], sd)[0]
+            got = logits[i].cpu().numpy()
+            assert np.max(np.abs(got - want)) < LOGIT_ABS_TOL, (i, float(np.max(np.abs(got - want))))
+            top = np.sort(want)
+            if top[-1] - top[-2] > 4 * LOGIT_ABS_TOL:
+                assert int(got.argmax()) == int(want.argmax()), i
+            checked += 1
+    assert checked == 8
