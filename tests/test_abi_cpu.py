@@ -115,3 +115,18 @@ def test_wav_reader_roundtrip(tmp_path):
     (tmp_path / "bad.wav").write_bytes(b"\xff\xf3\x84\xc4" + b"\0" * 64)             # MP3 frame header, like the reference clips
     with pytest.raises(ValueError):
         io._read_riff_wav(str(tmp_path / "bad.wav"))
+
+
+def test_host_binding_helper_is_optional():
+    """bind_host_to_gpu is an optimisation for multi-socket hosts: without NVML / a GPU it reports None and leaves the
+    process affinity alone (bench.py and IntentPipeline users carry on unbound)."""
+    import importlib
+    import os
+    pipeline = importlib.import_module("speech-intent-recognizer_b200.pipeline")
+    before = os.sched_getaffinity(0)
+    got = pipeline.bind_host_to_gpu(0)
+    assert got is None or (isinstance(got, list) and set(got) <= before)
+    if got is None:
+        assert os.sched_getaffinity(0) == before
+    else:
+        os.sched_setaffinity(0, before)
