@@ -55,7 +55,7 @@ NCU_TRAFFIC_B256 = {   # captures r1g (profiles/r1g_ncu_*.txt)
     "logmel_frontend_kernel": 54.17e6 + 0.85e6, "conv1_bn_relu_pool": 22.68e6 + 63.17e6,
     "conv2_bn_relu_pool": 104.97e6 + 30.97e6, "conv3_bn_relu_pool": 52.76e6 + 4.88e6,
     "gru_l0_input_gemm": 32.53e6 + 3.28e6, "gru_l1_input_gemm": 16.28e6 + 0.34e6,
-    "gru_l0_recurrence": 40.92e6 + 0.27e6, "gru_l1_recurrence": 40.92e6 + 0.03e6,
+    "gru_l0_recurrence": 40.92e6 + 0.27e6, "gru_l1_recurrence": 40.92e6 + 0.03e6,     # r1j capture: unchanged
 }
 
 
@@ -446,7 +446,7 @@ def main():
                 out["note"] = ("fp32-accurate 3-pass fp16 hi/lo split: the tensor pipe executes 3x the algorithmic FLOPs "
                                f"({round(3 * ach, 1)} TFLOP/s of fp16 MMA work)")
             if "recurrence" in name:
-                out["note"] = "latency chain of 25 dependent time steps (one launch per layer, 4.05 us per step, two 32-utterance chains per cluster); " + out.get("note", "")
+                out["note"] = "latency chain of 25 dependent time steps (one launch per layer, 3.6 us per step, two 32-utterance chains per cluster); " + out.get("note", "")
             return out
 
         rooflines = [stage_roofline(k) for k in stage_out]
