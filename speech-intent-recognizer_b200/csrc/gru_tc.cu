@@ -576,20 +576,16 @@ static int launch_gru(const __half* w_hi, const __half* w_lo, const float* gi, c
     return SIR_OK;
 }
 
-// Utterances per cluster: the smallest UMMA N (multiple of 16) for which both directions of the whole batch
-// fit in one wave of 8-CTA clusters (15 co-resident on a B200: measured launch__cluster_max_active); beyond 144
-// utterances N = 64 (the model chunks its batch to 336 = one wave of 2 x 6 clusters).
-constexpr int kGtMaxClustersPerWave = 15;
+// Utterances per cluster.  Up to 112 utterances: slices of 16 (the smallest UMMA N), both directions of the whole
+// batch in one wave of <= 14 clusters - the shortest step for a batch that is served alone (training at batch 16,
+// single-file inference).  Beyond that: slices of 64 as two 32-utterance chains (gru_layer_pp_kernel) - 8 SMs per 64
+// utterances (256 utterances: 64 SMs; the model chunks its batch to 336 = one wave of 2 x 6 clusters), a step of 3.6 us,
+// and the SMs it leaves take the frontend / conv stack of the next batch, which runs on another stream.
+constexpr int kGtMaxClustersPerWave = 15;     // co-resident 8-CTA clusters on a B200 (measured launch__cluster_max_active)
 
 int gru_layer_tc(const __half* w_hi, const __half* w_lo, const float* gi, const float* bhh, float* y,
                  __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st) {
-    auto clusters = [&](int nb) { return 2 * ((B + nb - 1) / nb); };
-    if (clusters(16) <= kGtMaxClustersPerWave) return launch_gru<16>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
-    if (clusters(32) <= kGtMaxClustersPerWave) return launch_gru<32>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
-    // Larger batches: 64 utterances per cluster.  A step is ~8 % slower than with 48, but the recurrence then holds 8
-    // SMs per 64 utterances instead of 8 per 48 (256 utterances: 64 instead of 96 SMs), and the SMs it leaves take
-    // the frontend / conv stack of the next batch, which runs on another stream (measured: +5 % utterances/s).
-    if (B <= 3 * 48) return launch_gru<48>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
+    if (2 * ((B + 15) / 16) <= kGtMaxClustersPerWave) return launch_gru<16>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
     return launch_gru_pp<2>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T, st);
 }
 
