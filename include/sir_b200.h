@@ -197,7 +197,9 @@ int sir_model_backward(sir_model* m, const float* d_params, const float* d_dlogi
 
 /* sir_cross_entropy  <->  nn.CrossEntropyLoss()(output, label) + its backward    scripts/train.py:96,106,243
  *   d_loss[0] = mean_b( logsumexp(logits_b) - logits_b[label_b] );
- *   d_dlogits (may be NULL) = scale * (softmax(logits) - onehot(label)) / batch   (scale = the GradScaler loss scale) */
+ *   d_dlogits (may be NULL) = scale * (softmax(logits) - onehot(label)) / n_valid (scale = the GradScaler loss scale).
+ *   Labels: -100 (torch's ignore_index) rows add neither loss nor gradient and leave the mean (n_valid counts the
+ *   rest); any other label outside [0, num_classes) masks its row and returns d_loss[0] = NaN (torch asserts). */
 int sir_cross_entropy(const float* d_logits, const int64_t* d_labels, int batch, int num_classes, float scale,
                       float* d_loss, float* d_dlogits, void* stream);
 
@@ -239,7 +241,7 @@ int sir_conv3x3_nhwc_split_f16(const float* d_in, const float* d_w, float* d_out
                                void* stream);
 
 /* sir_pipeline_forward: frontend (SIR_OUT_LOGMEL_NORM, pad/trim to out_frames) + classifier in one call.
- * d_features may be NULL (features then live only in the model's workspace). */
+ * d_features [batch, n_mels, out_frames] is required (the classifier reads the features from it). */
 int sir_pipeline_forward(sir_frontend* fe, sir_model* m, const float* d_wave, int64_t wave_stride,
                          const int32_t* d_lengths, int n_samples, int batch, int max_samples, int out_frames,
                          float* d_features, float* d_logits, void* stream);

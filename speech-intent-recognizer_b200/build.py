@@ -38,16 +38,26 @@ def _stale() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
-    objs = []
+    from concurrent.futures import ThreadPoolExecutor
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    for src in SOURCES:
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers += [os.path.join(HERE, "..", "include", "sir_b200.h"), os.path.abspath(__file__)]
+    newest_header = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src):
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
+        path = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), newest_header):
+            return obj
+        cmd = [_nvcc(), *flags, "-c", path, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))
         subprocess.check_call(cmd)
-        objs.append(obj)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-cudart", "static"]
     subprocess.check_call(cmd)
     return LIB

@@ -219,11 +219,7 @@ int tc_conv3x3_persistent(const __half* in_hi, const __half* in_lo, const __half
     p.out_hi = out_hi;
     p.out_lo = out_lo;
     auto kern = conv3x3_persistent_kernel<CIN, COUT, STAGES>;
-    static bool attr = false;
-    if (!attr) {
-        SIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes));
-        attr = true;
-    }
+    SIR_SMEM_OPTIN(kern, L::kSmemBytes);
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     p.tickets = tickets ? tickets->first() : TileTickets{nullptr, 0};
     {
@@ -436,11 +432,7 @@ int tc_conv3x3_stream(const __half* in_hi, const __half* in_lo, const __half* w_
     p.out_hi = out_hi;
     p.out_lo = out_lo;
     auto kern = conv3x3_stream_kernel<CIN, COUT>;
-    static bool attr = false;
-    if (!attr) {
-        SIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes));
-        attr = true;
-    }
+    SIR_SMEM_OPTIN(kern, L::kSmemBytes);
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     p.tickets = tickets ? tickets->first() : TileTickets{nullptr, 0};
     {

@@ -270,11 +270,7 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
                      const TcParams& p, dim3 grid, cudaStream_t st, const char* name) {
     using L = TcLayout<MODE, BLOCK_N, BLOCK_K, STAGES>;
     auto kern = tc_contract_kernel<MODE, BLOCK_N, BLOCK_K, STAGES>;
-    static bool attr = false;
-    if (!attr) {
-        SIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes));
-        attr = true;
-    }
+    SIR_SMEM_OPTIN(kern, L::kSmemBytes);
     {
         ProfScope ps(name, st);
         kern<<<grid, kTcThreads, L::kSmemBytes, st>>>(a_hi, a_lo, b_hi, b_lo, p);
@@ -459,15 +455,8 @@ static int tc_gemm_nt_persistent(const __half* a_hi, const __half* a_lo, const _
     p.num_tiles = p.tiles_w * p.tiles_x;
     p.bias = bias;
     p.C = C;
-    static bool attr = false;
-    static int num_sms = 148;
-    if (!attr) {
-        SIR_CUDA(cudaFuncSetAttribute(gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes));
-        int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (num_sms < 1) num_sms = 148;
-        attr = true;
-    }
+    SIR_SMEM_OPTIN(gemm_persistent_kernel, L::kSmemBytes);
+    const int num_sms = device_sm_count();
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     p.tickets = tickets ? tickets->first() : TileTickets{nullptr, 0};
     {

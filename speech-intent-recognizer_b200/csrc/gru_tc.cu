@@ -550,11 +550,7 @@ template <int NCH>
 static int launch_gru_pp(const __half* w_hi, const __half* w_lo, const float* gi, const float* bhh, float* y,
                          __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st) {
     using L = PpLayout<NCH>;
-    static bool attr = false;
-    if (!attr) {
-        SIR_CUDA(cudaFuncSetAttribute(gru_layer_pp_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes));
-        attr = true;
-    }
+    SIR_SMEM_OPTIN(gru_layer_pp_kernel<NCH>, L::kSmemBytes);
     dim3 grid((unsigned)(kGtCluster * ((B + L::kNB - 1) / L::kNB)), 2);
     gru_layer_pp_kernel<NCH><<<grid, L::kThreads, L::kSmemBytes, st>>>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T);
     SIR_CHECK_LAUNCH("gru_layer_pp_kernel");
@@ -565,11 +561,7 @@ template <int NB>
 static int launch_gru(const __half* w_hi, const __half* w_lo, const float* gi, const float* bhh, float* y,
                       __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st) {
     using L = GtLayout<NB>;
-    static bool attr = false;
-    if (!attr) {
-        SIR_CUDA(cudaFuncSetAttribute(gru_layer_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes));
-        attr = true;
-    }
+    SIR_SMEM_OPTIN(gru_layer_tc_kernel<NB>, L::kSmemBytes);
     dim3 grid((unsigned)(kGtCluster * ((B + NB - 1) / NB)), 2);
     gru_layer_tc_kernel<NB><<<grid, kGtThreads, L::kSmemBytes, st>>>(w_hi, w_lo, gi, bhh, y, y_hi, y_lo, B, T);
     SIR_CHECK_LAUNCH("gru_layer_tc_kernel");

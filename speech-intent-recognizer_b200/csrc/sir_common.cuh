@@ -56,6 +56,40 @@ struct ProfScope {
         ::sir::count_launch();                                                                           \
     } while (0)
 
+// cudaFuncSetAttribute and the SM count are per DEVICE, a process may hold handles on several: one-time setup is
+// remembered per device ordinal, not per process.
+struct DeviceOnce {
+    std::atomic<uint64_t> done{0};
+    bool need(int& dev) {
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+        return ((done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull) == 0;
+    }
+    void mark(int dev) { done.fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
+
+#define SIR_SMEM_OPTIN(kern, bytes)                                                                      \
+    do {                                                                                                 \
+        static ::sir::DeviceOnce _once;                                                                  \
+        int _dev = 0;                                                                                    \
+        if (_once.need(_dev)) {                                                                          \
+            SIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            _once.mark(_dev);                                                                            \
+        }                                                                                                \
+    } while (0)
+
+// SM count of the current device (cached per device ordinal).
+inline int device_sm_count() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    int n = cache[dev & 63].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        cache[dev & 63].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
 // Grow-only device buffer owned by a handle.
 struct DeviceBuffer {
     void* ptr = nullptr;

@@ -186,15 +186,40 @@ __global__ void gru_dropout_kernel(const float* __restrict__ y, int64_t n, const
 // loss
 // =========================================================================================================
 
-// CrossEntropyLoss (mean) + its gradient: dlogits = scale * (softmax - onehot) / B.  One CTA, warp per utterance.
+// CrossEntropyLoss (mean) + its gradient: dlogits = scale * (softmax - onehot) / n_valid.  One CTA, warp per utterance.
+// Labels follow nn.CrossEntropyLoss: -100 (ignore_index) rows contribute neither loss nor gradient and leave the mean's
+// denominator; any other label outside [0, C) is an error - torch raises a device assert, here the row is masked and the
+// loss comes back NaN so that the caller's per-step loss read-back (scripts/train.py:112-116) sees it.
 __global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
                                                             int B, int C, float scale, float* __restrict__ loss,
                                                             float* __restrict__ dlogits) {
     __shared__ float s_part[8];
+    __shared__ int s_valid, s_bad;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_valid = s_bad = 0;
+    __syncthreads();
+    int n_ok = 0, n_bad = 0;
+    for (int b = threadIdx.x; b < B; b += 256) {
+        const int64_t y = labels[b];
+        if (y >= 0 && y < C) ++n_ok;
+        else if (y != -100) ++n_bad;
+    }
+    if (n_ok) atomicAdd(&s_valid, n_ok);
+    if (n_bad) atomicAdd(&s_bad, n_bad);
+    __syncthreads();
+    const int n_valid = s_valid;
+    const float g = n_valid > 0 ? scale / (float)n_valid : 0.f;
     float part = 0.f;
     for (int b = warp; b < B; b += 8) {
         const float* row = logits + (int64_t)b * C;
+        const int64_t y64 = labels[b];
+        const bool ok = y64 >= 0 && y64 < C;
+        if (!ok) {
+            if (dlogits)
+                for (int c = lane; c < C; c += 32) dlogits[(int64_t)b * C + c] = 0.f;
+            continue;
+        }
+        const int y = (int)y64;
         float mx = -INFINITY;
         for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
 #pragma unroll
@@ -203,11 +228,9 @@ __global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restr
         for (int c = lane; c < C; c += 32) sum += expf(row[c] - mx);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const int y = (int)labels[b];
         const float lse = mx + logf(sum);
         if (lane == 0) part += lse - row[y];
         if (dlogits) {
-            const float g = scale / (float)B;
             for (int c = lane; c < C; c += 32)
                 dlogits[(int64_t)b * C + c] = g * (expf(row[c] - lse) - (c == y ? 1.f : 0.f));
         }
@@ -217,7 +240,7 @@ __global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restr
     if (threadIdx.x == 0) {
         float t = 0.f;
         for (int w = 0; w < 8; ++w) t += s_part[w];
-        loss[0] = t / (float)B;
+        loss[0] = s_bad ? __int_as_float(0x7fc00000) : t / (float)n_valid;       // 0/0 = NaN when every row is ignored, as torch
     }
 }
 
@@ -1041,11 +1064,7 @@ static int gru_layer_backward(sir_model* m, int layer, const float* params, cons
             return rc;
     }
     {
-        static bool attr = false;
-        if (!attr) {
-            SIR_CUDA(cudaFuncSetAttribute(gru_layer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSmemBytes));
-            attr = true;
-        }
+        SIR_SMEM_OPTIN(gru_layer_bwd_kernel, kGbSmemBytes);
         dim3 grid((unsigned)(kGbCluster * ((B + kGbNB - 1) / kGbNB)), 2);
         ProfScope ps(layer == 0 ? "gru_l0_bptt" : "gru_l1_bptt", st);
         gru_layer_bwd_kernel<<<grid, kGbThreads, kGbSmemBytes, st>>>(params + m->off.whh[layer][0], params + m->off.whh[layer][1],
@@ -1242,8 +1261,9 @@ extern "C" int sir_adam_step(float* d_params, const float* d_grads, float* d_exp
         total += seg.count[s];
     }
     if (total == 0) return SIR_OK;
-    const float bc1 = 1.f - powf(beta1, (float)step);
-    const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    // bias corrections in double like torch.optim.Adam (1 - 0.999^step loses ~6e-5 relative in fp32 during the first steps)
+    const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     adam_kernel<<<blocks_for(total, 256 * 4, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
         d_params, d_grads, d_exp_avg, d_exp_avg_sq, seg, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, inv_scale, d_found_inf);
     SIR_CHECK_LAUNCH("adam_kernel");

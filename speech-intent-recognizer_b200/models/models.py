@@ -34,13 +34,24 @@ class _TrainStep(torch.autograd.Function):
         model._dropout_offset += (feats.shape[0] * (feats.shape[2] // 8) * 512 + 3) // 4
         model._native_dirty = True                      # running statistics changed, eval weights are stale
         ctx.model, ctx.feats = model, feats             # the kernels read `feats` again in the backward
+        # the handle keeps ONE set of saved activations: remember which forward they belong to
+        model._train_generation += 1
+        ctx.generation = model._train_generation
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         model = ctx.model
+        if ctx.generation != model._train_generation:
+            raise _native.NativeError("CNNAudioGRU.backward: the activations saved by this forward were overwritten by a "
+                                      "later train-mode forward (the native handle keeps one set); run backward before "
+                                      "the next training forward")
         model._native_model.backward(model._flat, dlogits.contiguous(), model._flat_grad)
-        grads = [model._flat_grad[o:o + n].view(shape) for (o, n, shape) in model._param_slices]
+        # One copy of the flat buffer, then views into the COPY: sir_model_backward overwrites `_flat_grad` on every call,
+        # and autograd may keep what it is handed here as p.grad - views into the live buffer would make a second
+        # backward (gradient accumulation, zero_grad(set_to_none=False)) add the buffer to itself.
+        snap = model._flat_grad.clone()
+        grads = [snap[o:o + n].view(shape) for (o, n, shape) in model._param_slices]
         return (None, None, *grads)
 
 
@@ -67,6 +78,7 @@ class CNNAudioGRU(nn.Module):
         self.dropout_seed = 0                       # Philox key of the GRU dropout; set per rank for data parallelism
         self._dropout_offset = 0
         self._next_dropout_keep = None              # tests: explicit keep mask for the next training forward
+        self._train_generation = 0                  # which train-mode forward the handle's saved activations belong to
         self._native_model = None
         self._uploaded_versions = None
         self._native_dirty = True

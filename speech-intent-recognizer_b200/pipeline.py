@@ -58,6 +58,7 @@ def bind_host_to_gpu(device_index: int = None):
 class _Slot:
     def __init__(self):
         self.key = None
+        self.waves = {}                          # (B, L, dtype) -> device staging buffer, kept across dtype changes
         self.d_wave = self.feats = self.logits = self.host_logits = None
         self.done = torch.cuda.Event()
         self.busy = False
@@ -73,18 +74,35 @@ class IntentPipeline:
         self._next = 0
 
     def _prepare(self, slot, B, L, num_classes, device, dtype):
-        if slot.key != (B, L, dtype):
-            slot.key = (B, L, dtype)
-            slot.d_wave = torch.empty((B, L), device=device, dtype=dtype)
+        """Slot buffers for a ``[B, L]`` batch of ``dtype``.  The waveform staging buffer is kept per (B, L, dtype), so a
+        caller that alternates fp32 and PCM16 batches (or ``reserve``s both up front) never re-allocates in the loop."""
+        if (B, L, dtype) not in slot.waves:
+            if len(slot.waves) >= 4:
+                slot.waves.clear()
+            slot.waves[(B, L, dtype)] = torch.empty((B, L), device=device, dtype=dtype)
+        slot.d_wave = slot.waves[(B, L, dtype)]
+        if slot.key != (B, num_classes):
+            slot.key = (B, num_classes)
             slot.feats = torch.empty((B, self.extractor.n_mels, self.out_frames), device=device, dtype=torch.float32)
             slot.logits = torch.empty((B, num_classes), device=device, dtype=torch.float32)
             slot.host_logits = torch.empty((B, num_classes), dtype=torch.float32).pin_memory()
+
+    def reserve(self, B, L, dtypes=(torch.float32, torch.int16)):
+        """Allocate every slot's buffers for ``[B, L]`` batches of each of ``dtypes`` before the first ``submit``."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        for slot in self._slots:
+            for dt in dtypes:
+                self._prepare(slot, B, L, self.model.num_classes, dev, dt)
 
     @torch.no_grad()
     def submit(self, waves: torch.Tensor, lengths: torch.Tensor = None):
         """Enqueue one batch (``waves [B, L]``, fp32 or int16 PCM, in - ideally pinned - host memory); returns a ticket
         for ``collect``.  PCM16 input is scaled by 1/32768 on the device (what torchaudio.load does on the host) and
         halves the PCIe bytes per utterance.
+
+        ``lengths`` (optional) is a CUDA int32 tensor ``[B]`` of valid samples per row (the kernels read it on the
+        device; ``waves`` itself stays on the host).  ``waves`` is copied asynchronously on a side stream: the caller
+        must not overwrite or free it before ``collect`` has returned for this ticket.
 
         Nothing here waits for the GPU unless all ``depth`` slots are still in flight.
         """

@@ -108,6 +108,17 @@ def sync_flat_gradients(flat_grad: torch.Tensor, group=None):
     return world
 
 
+def broadcast_initial_state(flat: torch.Tensor, group=None, src_rank_in_group: int = 0):
+    """Make every rank of ``group`` start from rank 0's parameters and buffers (what DistributedDataParallel's
+    constructor does): ONE broadcast of the flat buffer.  CUDA tensors over NCCL, CPU tensors over gloo."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) <= 1:
+        return False
+    src = dist.get_global_rank(group, src_rank_in_group) if group is not None else src_rank_in_group
+    dist.broadcast(flat, src=src, group=group)
+    return True
+
+
 class LossScaler:
     """Host half of ``torch.cuda.amp.GradScaler`` (scripts/train.py:258): scale growth / back-off bookkeeping."""
 
@@ -148,6 +159,12 @@ class DataParallelTrainer:
         self.scaler = LossScaler(enabled=use_amp)
         model._ensure_native()
         flat = model.flatten_parameters_()
+        # Replicas must START identical: like DistributedDataParallel's constructor, broadcast rank 0's parameters and
+        # buffers (the flat buffer holds both, BatchNorm running statistics included) - ranks that built the model with an
+        # unseeded init would otherwise apply the same averaged gradient to different weights and drift apart silently.
+        # The Adam moments start at zero everywhere.
+        if broadcast_initial_state(flat, process_group):
+            model._native_dirty = True
         model.dropout_seed = (int(seed) << 8) + self.rank         # distinct dropout streams per rank
         self.n = model.weight_count()
         self.exp_avg = torch.zeros_like(flat)
@@ -157,6 +174,10 @@ class DataParallelTrainer:
         self.skipped_steps = 0
         self._scalars = torch.zeros(2, device="cuda", dtype=torch.float32)        # [loss, found_inf]
         self._host_scalars = torch.zeros(2, dtype=torch.float32).pin_memory()
+        # optional device timing of the collective (bench.py): CUDA events around the all-reduce of every step
+        self.time_collective = False
+        self.collective_ms = []
+        self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
 
     def step(self, mel: torch.Tensor, label: torch.Tensor, dropout_keep: torch.Tensor = None) -> float:
         m = self.model
@@ -169,11 +190,16 @@ class DataParallelTrainer:
                                                offset=m._dropout_offset, bn_momentum=m.bn1.momentum, bn_eps=m.bn1.eps)
         m._dropout_offset += (B * (T // 8) * 512 + 3) // 4
         m._native_dirty = True
+        m._train_generation += 1                                   # an older autograd graph's activations are gone
         _, dlogits = _native.cross_entropy(logits, label, scale=self.scaler.scale, loss_out=self._scalars[0:1])
         m._native_model.backward(flat, dlogits, grads)
         grads[self.n:].zero_()
         _native.grad_nonfinite(grads, self.n, grads[self.n:])
+        if self.time_collective:
+            self._ev[0].record()
         world = sync_flat_gradients(grads, self.group)
+        if self.time_collective:
+            self._ev[1].record()
         _native.adam_step(flat, grads, self.exp_avg, self.exp_avg_sq, self.segments, self.lr, self.betas, self.eps,
                           self.weight_decay, step=self.adam_steps + 1, inv_scale=1.0 / (self.scaler.scale * world),
                           found_inf=grads[self.n:])
@@ -181,6 +207,8 @@ class DataParallelTrainer:
         self._host_scalars.copy_(self._scalars, non_blocking=True)
         torch.cuda.current_stream().synchronize()                 # the reference reads loss.item() every step
         loss, found_inf = float(self._host_scalars[0]), bool(self._host_scalars[1] != 0)
+        if self.time_collective:
+            self.collective_ms.append(self._ev[0].elapsed_time(self._ev[1]))
         if found_inf:
             self.skipped_steps += 1
         else:

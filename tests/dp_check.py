@@ -71,6 +71,21 @@ def main():
     assert tr.skipped_steps == 1 and tr.adam_steps == 1
     for o, k in model.param_segments():
         assert torch.equal(model._flat[o:o + k], before[o:o + k])
+    # (d) replicas built from DIFFERENT seeds (the reference never seeds its init): the trainer's constructor broadcasts
+    # rank 0's parameters and BatchNorm buffers, so the ranks start - and after a step remain - identical
+    torch.manual_seed(100 + rank)
+    m2 = models.CNNAudioGRU(31).cuda()
+    tr2 = train.DataParallelTrainer(m2, lr=1e-3, weight_decay=1e-4, use_amp=True)
+    for when in ("after construction", "after one step"):
+        mine = m2._flat.clone()
+        other = mine.clone()
+        dist.broadcast(other, src=0)
+        if when == "after construction":
+            assert torch.equal(mine, other), "initial state (parameters + buffers) not broadcast"
+            tr2.step(xs, ls, dropout_keep=ks)
+        else:
+            for o, k in m2.param_segments():
+                assert torch.equal(mine[o:o + k], other[o:o + k]), "differently seeded replicas diverged"
     dist.barrier()
     if rank == 0:
         print("dp_check ok")

@@ -99,6 +99,9 @@ def _dp_worker(rank, world, port, out_dir):
         flat[n] = 1.0 if rank == 1 else 0.0
         train.sync_flat_gradients(flat)
         assert flat[n] == 1.0
+        # replicas that were initialised differently start from rank 0's state (no silent divergence)
+        state = torch.full((50,), float(10 + rank))
+        assert train.broadcast_initial_state(state) and torch.all(state == 10.0)
         a, b = train.shard_range(30043, rank, world)
         counts = torch.tensor([b - a])
         dist.all_reduce(counts)
