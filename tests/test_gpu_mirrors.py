@@ -62,7 +62,7 @@ def test_config2_full_batch_matches_oracle():
     assert np.max(np.abs(logits - want)) < LOGIT_ABS_TOL, float(np.max(np.abs(logits - want)))
     top = np.sort(want, axis=1)
     safe = (top[:, -1] - top[:, -2]) > 4 * LOGIT_ABS_TOL
-    assert safe.sum() >= 240, int(safe.sum())                 # how many rows have an arg-max that 1e-3 cannot flip
+    assert safe.sum() >= 250, int(safe.sum())                 # how many rows have an arg-max that 1e-3 cannot flip
     assert np.array_equal(logits.argmax(1)[safe], want.argmax(1)[safe])
     assert len(set(want.argmax(1).tolist())) >= 10            # not vacuous: many classes predicted
     # the numpy restatement agrees with the torchaudio port on a sample of rows (two independent checkers)
@@ -199,7 +199,7 @@ def test_apply_spec_augmentation_matches_reference_draw_order():
     import random
     base = logmel_np.extract_features(synth.speech_like(3, 1, 48000)[0])
     hits = 0
-    for seed in range(6):
+    for seed in range(12):
         random.seed(seed)
         torch.manual_seed(seed)
         got = augment.apply_spec_augmentation(torch.from_numpy(base))
@@ -209,7 +209,7 @@ def test_apply_spec_augmentation_matches_reference_draw_order():
         want = logmel_np.apply_masks(base, params)
         assert got.device.type == "cpu" and np.array_equal(got.numpy(), want), seed
         hits += int(params[1] > params[0]) + int(params[3] > params[2])
-    assert hits >= 3
+    assert hits >= 6
 
 
 def test_predict_from_file_matches_oracle(wav_corpus):
