@@ -23,7 +23,9 @@
 #include <cmath>
 #include <vector>
 
+#include "frontend_params.cuh"
 #include "frontend_tables.h"
+#include "frontend_tc.h"
 #include "logmel_frame.cuh"
 #include "philox.cuh"
 #include "sir_common.cuh"
@@ -83,37 +85,6 @@ static_assert(kOffScratch % 4 == 0 && kOffTile % 4 == 0 && kOffTw512 % 4 == 0 &&
 #endif
 static_assert(SIR_FE_MIN_CTAS * (kFeSmemBytes + 1024) <= 232448, "resident CTAs per SM");
 
-struct FrontendParams {
-    const void* wave;          // fp32 or int16 samples (template parameter of the kernel)
-    int64_t wave_stride;
-    const int32_t* lengths;
-    int n_samples;
-    int max_samples;
-    int n_mels;
-    int mode;
-    int out_frames;
-    float* out;
-    const int32_t* masks;
-    int32_t* status;
-    FrontendTables tables;
-    int mel_weight_count;
-    // SIR_OUT_MFCC: dB values are staged in db_stage [batch][n_mels][stage_frames]; after the per-utterance maximum is
-    // known each frame is clamped at max - top_db and projected with dct [n_mels][n_mfcc] (ortho DCT-II)
-    float* db_stage;
-    int stage_frames;
-    const float* dct;
-    int n_mfcc;
-    float top_db;
-    // work items: utterance i / groups_max, 8-frame group i % groups_max; per-item partial statistics and the
-    // per-utterance count of finished items (zero between launches)
-    int batch;
-    int groups_max;
-    struct ItemPartial* partials;
-    int* counters;
-    unsigned long long* work_counter;   // ticket counter (never reset) and the first ticket of this launch
-    unsigned long long work_base;
-};
-
 // Interior frames read their 1024 samples straight from global memory: lane l takes the 8-byte words
 // l + 16 j, so a half-warp covers 128 contiguous bytes per request, and the 50 % overlap with the neighbouring
 // frame (the other half of the same warp) is served by L1/L2 - HBM still sees every sample once.
@@ -145,14 +116,6 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-
-// One (utterance, 8-frame group) work item's contribution to the utterance statistics, written to global memory by
-// the CTA that processed the item and merged in group order by the CTA that finishes the utterance.
-struct alignas(32) ItemPartial {
-    double s1, s2;             // sums of (v - shift) and (v - shift)^2 over the item's values
-    float shift, vmax;
-    int n, pad;                // number of values
-};
 
 // Persistent grid (SIR_FE_MIN_CTAS CTAs per SM) over work items: item i is the 8-frame group i % groups_max of
 // utterance i / groups_max.  CTAs DRAW items from a global ticket counter (the next ticket is fetched while the
@@ -577,7 +540,19 @@ struct sir_frontend {
     int work_used = 0;
     DeviceBuffer dct;            // MFCC: [n_mels][n_mfcc] ortho DCT-II
     int dct_n_mfcc = 0;
+    DeviceBuffer tc_tables;      // tensor-core DFT kernel: operand images, twiddles, unscaled mel taps
+    TcDeviceTables tc_dev{};
 };
+
+// Which kernel serves sir_frontend_forward*: the tensor-core DFT (default) or the CUDA-core FFT of round 1
+// (SIR_FRONTEND_KERNEL=cuda in the environment; kept for A/B measurements - both are CUDA, there is no CPU path).
+static bool use_tc_kernel() {
+    static const bool tc = [] {
+        const char* v = getenv("SIR_FRONTEND_KERNEL");
+        return !(v && (v[0] == 'c' || v[0] == 'C'));
+    }();
+    return tc;
+}
 
 extern "C" const char* sir_last_error(void) { return g_error; }
 extern "C" int sir_version(void) { return 100; }
@@ -678,6 +653,13 @@ extern "C" int sir_frontend_create(sir_frontend** out, int sample_rate, int n_me
         delete fe;
         return fail(SIR_ERR_CUDA, "cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
     }
+    rc = frontend_tc_upload_tables(fe->tc_tables, fe->tc_dev, sample_rate, n_mels);
+    if (rc != SIR_OK) {
+        fe->tables.release();
+        fe->tc_tables.release();
+        delete fe;
+        return rc;
+    }
     *out = fe;
     return SIR_OK;
 }
@@ -685,6 +667,7 @@ extern "C" int sir_frontend_create(sir_frontend** out, int sample_rate, int n_me
 extern "C" void sir_frontend_destroy(sir_frontend* fe) {
     if (!fe) return;
     fe->tables.release();
+    fe->tc_tables.release();
     for (auto& w : fe->work) {
         w.partials.release();
         w.counters.release();
@@ -730,8 +713,10 @@ static int frontend_launch(sir_frontend* fe, const void* d_wave, bool pcm16, int
     p.status = d_status;
     p.tables = fe->dev;
     p.mel_weight_count = fe->mel_weight_count;
+    const bool tc_kernel = use_tc_kernel();
+    p.tc = fe->tc_dev;
     if (mode == SIR_OUT_MFCC) {
-        if (n_mfcc < 1 || n_mfcc > fe->n_mels || fe->n_mels * n_mfcc > kGroupFrames * kFrameScratch)
+        if (n_mfcc < 1 || n_mfcc > fe->n_mels || fe->n_mels * n_mfcc > 7936)
             return fail(SIR_ERR_INVALID, "sir_frontend_mfcc: n_mfcc must be in [1, n_mels] (got %d)", n_mfcc);
         if (fe->dct_n_mfcc != n_mfcc) {                      // create_dct(n_mfcc, n_mels, "ortho"), TA:functional.py:636-665
             const double pi = 3.14159265358979323846;
@@ -759,7 +744,7 @@ static int frontend_launch(sir_frontend* fe, const void* d_wave, bool pcm16, int
     }
     // work items: (utterance, 8-frame group); a persistent grid of SIR_FE_MIN_CTAS CTAs per SM takes them round-robin
     int eff = max_samples > 0 && max_samples < n_samples ? max_samples : n_samples;
-    const int groups = eff > kNfft / 2 ? (1 + eff / kHop + kGroupFrames - 1) / kGroupFrames : 1;
+    const int groups = eff > kNfft / 2 ? (tc_kernel ? frontend_tc_groups(1 + eff / kHop) : (1 + eff / kHop + kGroupFrames - 1) / kGroupFrames) : 1;
     const int64_t items = (int64_t)batch * groups;
     p.batch = batch;
     p.groups_max = groups;
@@ -773,7 +758,7 @@ static int frontend_launch(sir_frontend* fe, const void* d_wave, bool pcm16, int
         p.partials = (ItemPartial*)ws.partials.ptr;
         p.counters = (int*)ws.counters.ptr;
     }
-    const int64_t slots = (int64_t)fe->num_sms * SIR_FE_MIN_CTAS;
+    const int64_t slots = tc_kernel ? (int64_t)fe->num_sms : (int64_t)fe->num_sms * SIR_FE_MIN_CTAS;
     const int64_t grid = items < slots ? items : slots;
     if (!ws.tickets.ptr) {
         int rc = ws.tickets.reserve(sizeof(unsigned long long));
@@ -792,13 +777,17 @@ static int frontend_launch(sir_frontend* fe, const void* d_wave, bool pcm16, int
     cfg.numAttrs = 0;
     {
         ProfScope ps("logmel_frontend_kernel", cfg.stream);
-        if (pcm16)
+        if (tc_kernel) {
+            const int rc = frontend_tc_launch(p, pcm16, fe->num_sms, cfg.stream);
+            if (rc != SIR_OK) return rc;
+        } else if (pcm16)
             SIR_CUDA(cudaLaunchKernelEx(&cfg, logmel_frontend_kernel<short>, p));
         else
             SIR_CUDA(cudaLaunchKernelEx(&cfg, logmel_frontend_kernel<float>, p));
     }
     SIR_CHECK_LAUNCH("logmel_frontend_kernel");
-    ws.next_ticket += (unsigned long long)(items + grid);   // every CTA draws its items + 1 tickets (a failed launch: none)
+    // tickets a launch consumes (a failed launch: none): items + 1 per CTA, items + 2 per CTA for the tensor-core kernel
+    ws.next_ticket += tc_kernel ? (unsigned long long)frontend_tc_tickets(items, grid) : (unsigned long long)(items + grid);
     return SIR_OK;
 }
 
