@@ -8,21 +8,25 @@
 // are MMAs and ~550 warp instructions per frame remain.  Numerics: frontend_tc_tables.h, tests/host/tc_dft_host_check.cpp
 // (within ~2x of an fp32 FFT's own rounding error).
 //
-// One persistent CTA per SM, 13 warps, work item = 15 consecutive frames of one utterance (15 x 17 stage-2 rows = 255 = two
+// One persistent CTA per SM, 16 warps, work item = 15 consecutive frames of one utterance (15 x 17 stage-2 rows = 255 = two
 // 128-row UMMA tiles), drawn from a ticket counter:
 //   warps 0-3   "A": load samples (lane = n2, one coalesced 128-byte request per 32 samples; a 512-sample block is loaded
 //                once and serves the two frames that overlap it), per-frame power-of-two scale to max|x| in [1, 2), Hann
 //                window, fp16 (hi, lo) split, write the stage-1 operand rows (frame, n2) x K = n1 (hi | lo in one 128-byte
 //                swizzled row).  Warp w fills sub-tile w = frames 4w..4w+3.
 //   warp 4      issues the MMAs: stage 1 per sub-tile: D1 = A_hi [B1_hi; B1_lo] (N = 64) + A_lo B1_hi (N = 32);
-//                stage 2 per 128-row tile: D2 = A2_hi [B2_hi; B2_lo] (N = 128) + A2_lo B2_hi (N = 64).  Stage 2 of item i is
-//                issued after stage 1 of item i+1, so the two stages of consecutive items overlap.
+//                stage 2 per 128-row tile: D2 = A2_hi [B2_hi; B2_lo] (N = 128) + A2_lo B2_hi (N = 64).  The warp polls the
+//                barriers of both stages and issues whichever is ready, so stage 1 of later items never queues behind a
+//                stage 2 that waits for its consumers.
 //   warps 5-8   "C": read D1 (lane = n2, 32 real numbers = Y[0..16]), multiply by the twiddles W1024^(n2 k1), split, and
 //                write the stage-2 operand rows (frame, k1) x K = (n2, re/im): for a fixed k1 the 32 lanes write 32
 //                consecutive words of one row - the transposition between the stages costs no bank conflict.
 //   warps 9-12  "D/E": read D2 (lane = (frame, k1), 32 complex bins k1 + 32 k2), |X|^2 into the one-sided power spectrum
-//                (the bins with k mod 32 > 16 are mirrors), sparse mel taps, dB, tile -> global, the item's partial
-//                statistics, and - for the item that completes an utterance - the normalisation pass (as in frontend.cu).
+//                (the bins with k mod 32 > 16 are mirrors), sparse mel taps, dB -> one of two [n_mels][16] tiles in shared
+//                memory.  These warps never touch global memory.
+//   warps 13-15 "F": tile -> global, the item's partial statistics, the counting atomic and - for the item that completes
+//                an utterance - the normalisation pass (as in frontend.cu).  The fence / atomic / L2 round trips of this
+//                group (~2 us per item) run beside the next item's arithmetic instead of in front of it.
 // Every hand-off is an mbarrier; every wait is bounded and traps.
 #include <cuda_fp16.h>
 
@@ -40,9 +44,10 @@ namespace fetc {
 
 using namespace tc;
 
-constexpr int kNumWarps = 13;
+constexpr int kNumWarps = 16;
 constexpr int kThreads = kNumWarps * 32;
-constexpr int kWarpMma = 4, kWarpD0 = 9;       // warps 0-3: A, 4: MMA, 5-8: C, 9-12: D/E
+constexpr int kWarpMma = 4, kWarpD0 = 9, kWarpF0 = 13;       // warps 0-3: A, 4: MMA, 5-8: C, 9-12: D/E, 13-15: F
+constexpr int kFThreads = 96;
 constexpr int kRing = 8;                       // item slots between the ticket drawer and the other warps
 constexpr int kMelWeightCap = 1536;
 
@@ -55,6 +60,7 @@ struct Control {
     uint64_t ring_full[kRing], ring_empty[kRing], sc_full[kRing];
     uint64_t a1_full[4], a1_empty[4], d1_full[4], d1_empty[4];
     uint64_t a2_full[2], a2_empty, d2_full[2], d2_empty[2];
+    uint64_t tile_full[2], tile_empty[2];
     ItemSlot slot[kRing];
     uint32_t tmem_base;
     int unit_counter;
@@ -72,15 +78,38 @@ constexpr uint32_t kOffP = 155648;                               // 15 x 528 flo
 constexpr uint32_t kPBytes = 31744;
 constexpr uint32_t kOffMelW = kOffP + kPBytes;                   // 1536 floats
 constexpr uint32_t kOffMelIdx = kOffMelW + kMelWeightCap * 4;    // start / count / offset: 3 x 128 ints
-constexpr uint32_t kOffTile = kOffMelIdx + 3 * kMaxMels * 4;     // [n_mels][16] floats
-constexpr uint32_t kOffWin = kOffTile + kMaxMels * 16 * 4;       // Hann window as [8][32 lanes][4]: lane's w[32 n1 + lane], n1 = 4c..4c+3
+constexpr uint32_t kOffTile = kOffMelIdx + 3 * kMaxMels * 4;     // two [n_mels][16] float tiles (D/E -> F)
+constexpr uint32_t kTileFloats = kMaxMels * 16;
+constexpr uint32_t kOffWin = kOffTile + 2 * kTileFloats * 4;       // Hann window as [8][32 lanes][4]: lane's w[32 n1 + lane], n1 = 4c..4c+3
 constexpr uint32_t kOffCtl = kOffWin + 4096;
 constexpr uint32_t kSmemBytes = kOffCtl + ((sizeof(Control) + 127) & ~127u) + 1024;   // + slack for the 1024-byte alignment
 static_assert(kTileFrames * kPStride * 4 <= kPBytes, "power buffer");
 static_assert(kSmemBytes <= 232448, "shared memory per CTA");
 static_assert(kOffA2Hi % 1024 == 0 && kOffA2Lo % 1024 == 0 && kOffB1 % 1024 == 0 && kOffB2 % 1024 == 0, "swizzle atoms");
 
+// mbarrier wait for the pipeline hand-offs: try_wait with a suspend-time hint, so a waiting warp sleeps in hardware until the
+// phase completes (or 20 us pass) instead of re-issuing the probe - with 16 warps of 5 roles on one SM the plain spin loops
+// were a third of all issued instructions.  Bounded: a protocol bug traps.
+__device__ __forceinline__ void pipe_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+        if (ok) return;
+        if (spin > (1u << 20)) __trap();
+    }
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ void group_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the four D/E warps
+__device__ __forceinline__ void f_barrier() { asm volatile("bar.sync 2, 96;" ::: "memory"); }        // the three F warps
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -159,7 +188,9 @@ __device__ __forceinline__ float store_frame(const float (&first)[16], const flo
 template <typename SampleT>
 __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const FrontendParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array: the compiler keeps the address space (LDS / STS,
+    // not generic loads - an integer round trip made every shared access of this kernel a generic one)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     Control* ctl = reinterpret_cast<Control*>(smem + kOffCtl);
     float* s_P = reinterpret_cast<float*>(smem + kOffP);
     float* s_melw = reinterpret_cast<float*>(smem + kOffMelW);
@@ -174,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
     if (tid == 0) {
         for (int i = 0; i < kRing; ++i) {
             mbar_init(&ctl->ring_full[i], 1);
-            mbar_init(&ctl->ring_empty[i], 12);                  // A warps 1-3, MMA warp, 4 C warps, 4 D/E warps
+            mbar_init(&ctl->ring_empty[i], 15);                  // A warps 1-3, MMA warp, 4 C warps, 4 D/E warps, 3 F warps
             mbar_init(&ctl->sc_full[i], 4);
         }
         for (int i = 0; i < 4; ++i) {
@@ -189,6 +220,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
         for (int i = 0; i < 2; ++i) {
             mbar_init(&ctl->d2_full[i], 1);
             mbar_init(&ctl->d2_empty[i], 4);
+            mbar_init(&ctl->tile_full[i], 4);
+            mbar_init(&ctl->tile_empty[i], 3);
         }
         ctl->unit_counter = 0;
         fence_barrier_init();
@@ -234,17 +267,32 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
             return L;
         };
         auto draw = [&]() -> long long { return (long long)(atomicAdd(p.work_counter, 1ULL) - p.work_base); };
+        // Request the samples of a coming item into L2 (one bulk-prefetch instruction for its 16 blocks): the A warps hold
+        // only 8 KB of loads in flight per SM, which at HBM latency is ~1 TB/s for the whole chip; at L2 latency it is enough.
+        auto prefetch_item = [&](long long item, int Li) {
+            if (item < 0 || item >= total_items || Li <= kNfft / 2) return;
+            const int b = (int)(item / p.groups_max), g = (int)(item - (long long)b * p.groups_max);
+            const int n_lo = max(0, (g * kTileFrames - 1) * kHop), n_hi = min(Li, (g * kTileFrames + kTileFrames) * kHop);
+            if (n_hi <= n_lo) return;
+            const char* base = reinterpret_cast<const char*>(static_cast<const SampleT*>(p.wave) + (int64_t)b * p.wave_stride);
+            uintptr_t lo = reinterpret_cast<uintptr_t>(base + (size_t)n_lo * sizeof(SampleT));
+            uintptr_t hi = reinterpret_cast<uintptr_t>(base + (size_t)n_hi * sizeof(SampleT));
+            lo = (lo + 15) & ~(uintptr_t)15;
+            hi &= ~(uintptr_t)15;
+            if (hi > lo) prefetch_l2_bulk(reinterpret_cast<const void*>(lo), (uint32_t)(hi - lo));
+        };
         if (warp == 0 && lane == 0) {
             i0 = draw();
             i1 = draw();
             L0 = length_of(i0);
+            prefetch_item(i0, L0);
         }
         for (uint32_t it = 0;; ++it) {
             const int rs = it % kRing;
             const uint32_t rph = (it / kRing) & 1u;
             if (warp == 0) {
                 if (lane == 0) {
-                    mbar_wait(&ctl->ring_empty[rs], rph ^ 1u);
+                    pipe_wait(&ctl->ring_empty[rs], rph ^ 1u);
                     ItemSlot& sl = ctl->slot[rs];
                     for (;;) {                                   // skip tickets beyond an utterance's last group (ragged batches)
                         if (i0 < 0 || i0 >= total_items) {
@@ -271,8 +319,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                         i1 = draw();
                     }
                     mbar_arrive(&ctl->ring_full[rs]);
-                    if (sl.item >= 0) {                          // advance: the next length load and the next draw are in
-                        const int L1 = length_of(i1);            // flight while this item is processed
+                    if (sl.item >= 0) {                          // advance: the next item's samples are requested into L2, the
+                        const int L1 = length_of(i1);            // draw after it is in flight while this item is processed
+                        prefetch_item(i1, L1);
                         i0 = i1;
                         L0 = L1;
                         i1 = draw();
@@ -280,39 +329,35 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                 }
                 __syncwarp();
             }
-            mbar_wait(&ctl->ring_full[rs], rph);
+            pipe_wait(&ctl->ring_full[rs], rph);
             ItemSlot& sl = ctl->slot[rs];
             if (sl.item < 0) break;
             const int L = sl.L, t0 = sl.t0, nfr = sl.nfr;
             const SampleT* __restrict__ row = static_cast<const SampleT*>(p.wave) + (int64_t)sl.b * p.wave_stride;
-            mbar_wait(&ctl->a1_empty[warp], (it & 1u) ^ 1u);     // stage 1 of the previous item has read this sub-tile
             const int f0 = 4 * warp;
             if (f0 < nfr) {
                 const uint32_t tile_addr = sbase + kOffA1 + (uint32_t)warp * 16384u;
-                // blocks t0 + f0 - 1 .. t0 + f0 + 3 in three rotating register buffers: frame j = (block j, block j + 1), and
-                // block j + 2 is requested before frame j is processed
-                float x0[16], x1[16], x2[16];
+                // blocks t0 + f0 - 1 .. t0 + f0 + 3: frame j = (block j, block j + 1); block j + 2 is requested before frame j
+                // is processed
+                float xa[16], xb[16], xc[16];
                 const int jb = t0 + f0 - 1, nf = min(4, nfr - f0);
-                load_block(row, L, jb, lane, x0);
-                load_block(row, L, jb + 1, lane, x1);
-                if (nf > 1) load_block(row, L, jb + 2, lane, x2);
-                float i2 = store_frame(x0, x1, s_win, tile_addr, lane);
-                if (lane == 0) sl.inv2[f0] = i2;
-                if (nf > 1) {
-                    if (nf > 2) load_block(row, L, jb + 3, lane, x0);
-                    i2 = store_frame(x1, x2, s_win, tile_addr, 32 + lane);
-                    if (lane == 0) sl.inv2[f0 + 1] = i2;
-                }
-                if (nf > 2) {
-                    if (nf > 3) load_block(row, L, jb + 4, lane, x1);
-                    i2 = store_frame(x2, x0, s_win, tile_addr, 64 + lane);
-                    if (lane == 0) sl.inv2[f0 + 2] = i2;
-                }
-                if (nf > 3) {
-                    i2 = store_frame(x0, x1, s_win, tile_addr, 96 + lane);
-                    if (lane == 0) sl.inv2[f0 + 3] = i2;
+                load_block(row, L, jb, lane, xa);
+                load_block(row, L, jb + 1, lane, xb);
+                pipe_wait(&ctl->a1_empty[warp], (it & 1u) ^ 1u); // stage 1 of the previous item has read this sub-tile
+#pragma unroll 1
+                for (int j = 0; j < nf; ++j) {                   // (rolled: four inlined copies of the frame code thrash the I-cache)
+                    if (j + 1 < nf) load_block(row, L, jb + j + 2, lane, xc);
+                    const float i2 = store_frame(xa, xb, s_win, tile_addr, 32 * j + lane);
+                    if (lane == 0) sl.inv2[f0 + j] = i2;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        xa[i] = xb[i];
+                        xb[i] = xc[i];
+                    }
                 }
                 fence_proxy_async();                             // generic-proxy stores -> visible to the tensor core
+            } else {
+                pipe_wait(&ctl->a1_empty[warp], (it & 1u) ^ 1u); // (keeps the barrier phases in step)
             }
             __syncwarp();
             if (lane == 0) {
@@ -323,56 +368,75 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
         }
     } else if (warp == kWarpMma) {
         // =============================== MMA issue ===================================================================
+        // Two streams of work, polled in turn: stage 1 of item i1 (sub-tile s1) and stage 2 of item i2 (row tile m2), i2
+        // trailing i1.  All 32 lanes walk the loop (uniform), one elected lane issues.
         constexpr uint32_t id1a = make_idesc_f16(128, 64), id1b = make_idesc_f16(128, 32);
         constexpr uint32_t id2a = make_idesc_f16(128, 128), id2b = make_idesc_f16(128, 64);
         const uint64_t b1 = make_kmajor_desc<128>(sbase + kOffB1), b2 = make_kmajor_desc<128>(sbase + kOffB2);
-        bool have_prev = false;
-        for (uint32_t it = 0;; ++it) {
-            const int rs = it % kRing;
-            mbar_wait(&ctl->ring_full[rs], (it / kRing) & 1u);
-            const bool more = ctl->slot[rs].item >= 0;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->ring_empty[rs]);
-            if (more) {
-                for (int s = 0; s < 4; ++s) {
-                    mbar_wait(&ctl->a1_full[s], it & 1u);
-                    mbar_wait(&ctl->d1_empty[s], (it & 1u) ^ 1u);
+        uint32_t i1 = 0, s1 = 0, i2 = 0, m2 = 0, idle = 0;
+        bool have_slot = false, end1 = false;
+        for (;;) {
+            bool progressed = false;
+            if (i2 < i1 && mbar_test_wait(&ctl->a2_full[m2], i2 & 1u) && mbar_test_wait(&ctl->d2_empty[m2], (i2 & 1u) ^ 1u)) {
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint64_t ah = make_kmajor_desc<128>(sbase + kOffA2Hi + m2 * 16384u);
+                    const uint64_t al = make_kmajor_desc<128>(sbase + kOffA2Lo + m2 * 16384u);
+                    const uint32_t d = tmem_base + 256u + m2 * 128u;
+#pragma unroll
+                    for (int k = 0; k < 64; k += 16) umma_f16(d, desc_advance_k(ah, k), desc_advance_k(b2, k), id2a, k ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 64; k += 16) umma_f16(d, desc_advance_k(al, k), desc_advance_k(b2, k), id2b, 1u);
+                    umma_commit(&ctl->d2_full[m2]);
+                    if (m2 == 1) umma_commit(&ctl->a2_empty);
+                }
+                __syncwarp();
+                if (++m2 == 2) {
+                    m2 = 0;
+                    ++i2;
+                }
+                progressed = true;
+            }
+            if (!end1) {
+                if (!have_slot) {
+                    const int rs = i1 % kRing;
+                    if (mbar_test_wait(&ctl->ring_full[rs], (i1 / kRing) & 1u)) {
+                        const bool more = ctl->slot[rs].item >= 0;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&ctl->ring_empty[rs]);
+                        if (more) have_slot = true;
+                        else end1 = true;
+                        progressed = true;
+                    }
+                }
+                if (have_slot && mbar_test_wait(&ctl->a1_full[s1], i1 & 1u) && mbar_test_wait(&ctl->d1_empty[s1], (i1 & 1u) ^ 1u)) {
                     tc_fence_after();
                     if (elect_one_sync()) {
-                        const uint64_t a = make_kmajor_desc<128>(sbase + kOffA1 + (uint32_t)s * 16384u);
-                        const uint32_t d = tmem_base + (uint32_t)s * 64u;
+                        const uint64_t a = make_kmajor_desc<128>(sbase + kOffA1 + s1 * 16384u);
+                        const uint32_t d = tmem_base + s1 * 64u;
                         umma_f16(d, desc_advance_k(a, 0), desc_advance_k(b1, 0), id1a, 0u);      // hi . [B_hi; B_lo]
                         umma_f16(d, desc_advance_k(a, 16), desc_advance_k(b1, 16), id1a, 1u);
                         umma_f16(d, desc_advance_k(a, 32), desc_advance_k(b1, 0), id1b, 1u);     // lo . B_hi
                         umma_f16(d, desc_advance_k(a, 48), desc_advance_k(b1, 16), id1b, 1u);
-                        umma_commit(&ctl->a1_empty[s]);
-                        umma_commit(&ctl->d1_full[s]);
+                        umma_commit(&ctl->a1_empty[s1]);
+                        umma_commit(&ctl->d1_full[s1]);
                     }
                     __syncwarp();
-                }
-            }
-            if (have_prev) {                                     // stage 2 of the previous item
-                const uint32_t pit = it - 1;
-                for (int m = 0; m < 2; ++m) {
-                    mbar_wait(&ctl->a2_full[m], pit & 1u);
-                    mbar_wait(&ctl->d2_empty[m], (pit & 1u) ^ 1u);
-                    tc_fence_after();
-                    if (elect_one_sync()) {
-                        const uint64_t ah = make_kmajor_desc<128>(sbase + kOffA2Hi + (uint32_t)m * 16384u);
-                        const uint64_t al = make_kmajor_desc<128>(sbase + kOffA2Lo + (uint32_t)m * 16384u);
-                        const uint32_t d = tmem_base + 256u + (uint32_t)m * 128u;
-#pragma unroll
-                        for (int k = 0; k < 64; k += 16) umma_f16(d, desc_advance_k(ah, k), desc_advance_k(b2, k), id2a, k ? 1u : 0u);
-#pragma unroll
-                        for (int k = 0; k < 64; k += 16) umma_f16(d, desc_advance_k(al, k), desc_advance_k(b2, k), id2b, 1u);
-                        umma_commit(&ctl->d2_full[m]);
-                        if (m == 1) umma_commit(&ctl->a2_empty);
+                    if (++s1 == 4) {
+                        s1 = 0;
+                        ++i1;
+                        have_slot = false;
                     }
-                    __syncwarp();
+                    progressed = true;
                 }
             }
-            if (!more) break;
-            have_prev = true;
+            if (end1 && i2 == i1) break;
+            if (progressed) {
+                idle = 0;
+            } else {
+                __nanosleep(40);                                 // nothing ready: leave the issue slots to the working warps
+                if (++idle > (1u << 24)) __trap();               // a protocol bug must surface as an error, never as a hang
+            }
         }
     } else if (warp < kWarpD0) {
         // =============================== C: D1 -> twiddle -> stage-2 operand ========================================
@@ -385,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
         for (int c = 0; c < 8; ++c) lane_off[c] = (uint32_t)((((lane >> 2) ^ c) << 4) | ((lane & 3) << 2));
         for (uint32_t it = 0;; ++it) {
             const int rs = it % kRing;
-            mbar_wait(&ctl->ring_full[rs], (it / kRing) & 1u);
+            pipe_wait(&ctl->ring_full[rs], (it / kRing) & 1u);
             const long long item = ctl->slot[rs].item;
             const int nfr = ctl->slot[rs].nfr;
             __syncwarp();
@@ -395,14 +459,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
             for (int s = 0; s < 4; ++s) {
                 const int f = 4 * s + q;
                 const bool valid = f < nfr;
-                mbar_wait(&ctl->d1_full[s], it & 1u);
+                pipe_wait(&ctl->d1_full[s], it & 1u);
                 tc_fence_after();
                 float y[32];
                 if (valid) {
                     float u[32];
                     const uint32_t trow = tmem_base + (uint32_t)s * 64u + ((uint32_t)(q * 32) << 16);
-                    tmem_ld_32x32(trow, y);                      // hi.hi + lo.hi
-                    tmem_ld_32x32(trow + 32, u);                 // hi.lo
+                    tmem_ld_32x32_pair(trow, trow + 32, y, u);   // (hi.hi + lo.hi), (hi.lo)
 #pragma unroll
                     for (int i = 0; i < 32; ++i) y[i] += u[i];
                 }
@@ -410,7 +473,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctl->d1_empty[s]);
                 if (!a2_ready) {                                 // stage 2 of the previous item has read the operand
-                    mbar_wait(&ctl->a2_empty, (it & 1u) ^ 1u);
+                    pipe_wait(&ctl->a2_empty, (it & 1u) ^ 1u);
                     a2_ready = true;
                 }
                 if (valid) {
@@ -449,31 +512,24 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                 }
             }
         }
-    } else {
-        // =============================== D/E: D2 -> power -> mel -> dB -> statistics -> finisher ====================
+    } else if (warp < kWarpF0) {
+        // =============================== D/E: D2 -> power -> mel -> dB -> tile (shared memory only) ==================
         const int q = warp & 3;
         const int dt = (warp - kWarpD0) * 32 + lane;             // 0..127
-        constexpr int kET = 128;
-        float* red = ctl->red;
-        const bool mfcc = p.mode == SIR_OUT_MFCC;
-        const bool needs_finish = mfcc || p.mode == SIR_OUT_LOGMEL_NORM;
-        const int out_rows = mfcc ? p.n_mfcc : p.n_mels;
-        const int row_stride = mfcc ? p.stage_frames : p.out_frames;
         const int n_units = 3 * ((p.n_mels + 31) >> 5);
         for (uint32_t it = 0;; ++it) {
             const int rs = it % kRing;
-            mbar_wait(&ctl->ring_full[rs], (it / kRing) & 1u);
+            pipe_wait(&ctl->ring_full[rs], (it / kRing) & 1u);
             const ItemSlot& sl = ctl->slot[rs];
-            const long long item = sl.item;
-            if (item < 0) {
+            if (sl.item < 0) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctl->ring_empty[rs]);
                 break;
             }
-            const int b = sl.b, t0 = sl.t0, nfr = sl.nfr, T = sl.T, n_groups = sl.n_groups;
+            const int nfr = sl.nfr;
             // ---- power spectrum of the item's frames ------------------------------------------------------------
             for (int m = 0; m < 2; ++m) {
-                mbar_wait(&ctl->d2_full[m], it & 1u);
+                pipe_wait(&ctl->d2_full[m], it & 1u);
                 tc_fence_after();
                 const int R = 128 * m + 32 * q + lane;
                 const int f = R < 240 ? R >> 4 : R - 240, k1 = R < 240 ? R & 15 : 16;
@@ -484,8 +540,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         float v[32], u[32];
-                        tmem_ld_32x32(trow + 32 * j, v);
-                        tmem_ld_32x32(trow + 64 + 32 * j, u);
+                        tmem_ld_32x32_pair(trow + 32 * j, trow + 64 + 32 * j, v, u);
                         if (valid) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
@@ -506,18 +561,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctl->d2_empty[m]);
             }
-            mbar_wait(&ctl->sc_full[rs], (it / kRing) & 1u);     // the A warps' per-frame scales
+            pipe_wait(&ctl->sc_full[rs], (it / kRing) & 1u);     // the A warps' per-frame scales
+            const uint32_t buf = it & 1u;
+            float* tile = s_tile + buf * kTileFloats;
+            pipe_wait(&ctl->tile_empty[buf], ((it >> 1) & 1u) ^ 1u);   // the F warps have drained this tile
             group_barrier();                                     // P complete
-
-            const bool valid_utt = T > 0;
-            float* __restrict__ final_out = p.out + (int64_t)b * out_rows * p.out_frames;
-            float* __restrict__ out = mfcc ? p.db_stage + (int64_t)b * p.n_mels * p.stage_frames : final_out;
-            if (t0 == 0 && dt == 0 && p.status) p.status[b] = valid_utt ? 0 : 1;
-            bool last = false;
-            if (!valid_utt) {
-                for (int i = dt; i < out_rows * p.out_frames; i += kET) final_out[i] = 0.f;
-            } else {
-                // ---- sparse mel taps: units = (32 bands, 5 frames), most expensive bands first ------------------------
+            // ---- sparse mel taps: units = (32 bands, 5 frames), most expensive bands first ----------------------------
+            if (nfr > 0) {
                 for (;;) {
                     int u = 0;
                     if (lane == 0) u = atomicAdd(&ctl->unit_counter, 1);
@@ -532,15 +582,15 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                     const float4* __restrict__ p4 = reinterpret_cast<const float4*>(s_P + f_lo * kPStride + (active ? s_mel_start[band] : 0));
                     float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
                     const int nf = min(5, nfr - f_lo);
+#pragma unroll 2
                     for (int i = 0; i < n4; ++i) {
                         const float4 w = w4[i];
+                        float4 x[5];
 #pragma unroll
-                        for (int ff = 0; ff < 5; ++ff) {
-                            if (ff < nf) {
-                                const float4 x = p4[ff * (kPStride / 4) + i];
-                                acc[ff] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, acc[ff]))));
-                            }
-                        }
+                        for (int ff = 0; ff < 5; ++ff) x[ff] = p4[(ff < nf ? ff : 0) * (kPStride / 4) + i];
+#pragma unroll
+                        for (int ff = 0; ff < 5; ++ff)
+                            acc[ff] = fmaf(w.x, x[ff].x, fmaf(w.y, x[ff].y, fmaf(w.z, x[ff].z, fmaf(w.w, x[ff].w, acc[ff]))));
                     }
                     if (active) {
 #pragma unroll
@@ -549,21 +599,58 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                                 float v = acc[ff] * sl.inv2[f_lo + ff];
                                 // 10 log10(x) = (10 log10 2) lg2(x): lg2.approx is good to ~1e-7 relative here, i.e. ~1e-6 dB
                                 if (p.mode != SIR_OUT_MEL_POWER) v = 3.01029995663981195f * __log2f(fmaxf(v, 1e-10f));
-                                s_tile[band * 16 + f_lo + ff] = v;
+                                tile[band * 16 + f_lo + ff] = v;
                             }
                         }
                     }
                 }
-                group_barrier();                                 // tile complete
-                if (dt == 0) ctl->unit_counter = 0;              // (next use is behind the next item's barriers)
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->tile_full[buf]);    // release: this warp's tile entries
+            group_barrier();                                     // every warp is done with P (and with the unit counter)
+            if (dt == 0) ctl->unit_counter = 0;                  // (next use is behind the next item's barrier)
+            if (lane == 0) mbar_arrive(&ctl->ring_empty[rs]);
+        }
+    } else {
+        // =============================== F: tile -> global, statistics, counting atomic, finisher ====================
+        const int ft = (warp - kWarpF0) * 32 + lane;             // 0..95
+        constexpr int kET = kFThreads;
+        float* red = ctl->red;
+        const bool mfcc = p.mode == SIR_OUT_MFCC;
+        const bool needs_finish = mfcc || p.mode == SIR_OUT_LOGMEL_NORM;
+        const int out_rows = mfcc ? p.n_mfcc : p.n_mels;
+        const int row_stride = mfcc ? p.stage_frames : p.out_frames;
+        for (uint32_t it = 0;; ++it) {
+            const int rs = it % kRing;
+            pipe_wait(&ctl->ring_full[rs], (it / kRing) & 1u);
+            const ItemSlot& sl = ctl->slot[rs];
+            const long long item = sl.item;
+            if (item < 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->ring_empty[rs]);
+                break;
+            }
+            const int b = sl.b, t0 = sl.t0, nfr = sl.nfr, T = sl.T;
+            const uint32_t buf = it & 1u;
+            const float* tile = s_tile + buf * kTileFloats;
+            pipe_wait(&ctl->tile_full[buf], (it >> 1) & 1u);
 
+            const bool valid_utt = T > 0;
+            float* __restrict__ final_out = p.out + (int64_t)b * out_rows * p.out_frames;
+            float* __restrict__ out = mfcc ? p.db_stage + (int64_t)b * p.n_mels * p.stage_frames : final_out;
+            if (t0 == 0 && ft == 0 && p.status) p.status[b] = valid_utt ? 0 : 1;
+            if (!valid_utt) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->tile_empty[buf]);
+                for (int i = ft; i < out_rows * p.out_frames; i += kET) final_out[i] = 0.f;
+            } else {
                 // ---- tile -> global + the item's statistics ----------------------------------------------------------
-                const float shift = s_tile[0];
+                const float shift = tile[0];
                 float s1 = 0.f, s2 = 0.f, vmax = -INFINITY;
-                for (int idx = dt; idx < p.n_mels * 16; idx += kET) {
+                for (int idx = ft; idx < p.n_mels * 16; idx += kET) {
                     const int mrow = idx >> 4, s = idx & 15;
                     if (s < nfr) {
-                        const float v = s_tile[idx];
+                        const float v = tile[idx];
                         if (t0 + s < row_stride) out[(int64_t)mrow * row_stride + t0 + s] = v;
                         vmax = fmaxf(vmax, v);
                         const float d = v - shift;
@@ -571,10 +658,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                         s2 = fmaf(d, d, s2);
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->tile_empty[buf]);        // the D/E warps may refill this tile
                 if (!needs_finish) {
                     if (t0 == 0)                                 // zero padding behind the last frame, all rows
                         for (int mrow = 0; mrow < p.n_mels; ++mrow)
-                            for (int tt = T + dt; tt < p.out_frames; tt += kET) out[(int64_t)mrow * p.out_frames + tt] = 0.f;
+                            for (int tt = T + ft; tt < p.out_frames; tt += kET) out[(int64_t)mrow * p.out_frames + tt] = 0.f;
                 } else {
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
@@ -582,156 +671,26 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                         vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
                     }
-                    const int w = warp - kWarpD0;
+                    const int w = warp - kWarpF0;
                     if (lane == 0) {
                         red[w] = s1;
                         red[8 + w] = s2;
                         red[16 + w] = vmax;
                     }
-                    group_barrier();                             // every thread's feature stores happen before the fence below
-                    if (dt == 0) {
+                    f_barrier();
+                    if (ft == 0) {                               // the item's partial statistics; frontend_finish_kernel merges them
                         ItemPartial part;
-                        part.s1 = ((double)red[0] + (double)red[1]) + ((double)red[2] + (double)red[3]);
-                        part.s2 = ((double)red[8] + (double)red[9]) + ((double)red[10] + (double)red[11]);
+                        part.s1 = ((double)red[0] + (double)red[1]) + (double)red[2];
+                        part.s2 = ((double)red[8] + (double)red[9]) + (double)red[10];
                         part.shift = shift;
-                        part.vmax = fmaxf(fmaxf(red[16], red[17]), fmaxf(red[18], red[19]));
+                        part.vmax = fmaxf(fmaxf(red[16], red[17]), red[18]);
                         part.n = nfr * p.n_mels;
                         part.pad = 0;
                         p.partials[item] = part;
-                        __threadfence();                         // release: the group's stores (barrier above) and the partial
-                        const bool l = atomicAdd(p.counters + b, 1) == n_groups - 1;
-                        if (l) __threadfence();                  // acquire: the other items' stores
-                        ctl->flag = l;
-                    }
-                    group_barrier();
-                    last = ctl->flag != 0;
-                }
-            }
-            if (last) {
-                // ---- finisher: every item of utterance b is in global memory (same merge as frontend.cu) -------------
-                if (warp == kWarpD0) {
-                    if (lane == 0) p.counters[b] = 0;            // ready for the next launch
-                    const ItemPartial* parts = p.partials + (int64_t)b * p.groups_max;
-                    double n = 0, mean = 0, m2 = 0;
-                    float mx = -INFINITY;
-                    for (int base = 0; base < n_groups; base += 32) {
-                        double ni = 0, mi = 0, m2i = 0;
-                        if (base + lane < n_groups) {
-                            const double2 a = __ldcg(reinterpret_cast<const double2*>(parts + base + lane));       // (s1, s2)
-                            const float2 c = __ldcg(reinterpret_cast<const float2*>(parts + base + lane) + 2);     // (shift, vmax)
-                            const int cnt = __ldcg(reinterpret_cast<const int*>(parts + base + lane) + 6);
-                            ni = (double)cnt;
-                            const double r = a.x / ni;
-                            mi = (double)c.x + r;
-                            m2i = fmax(a.y - a.x * r, 0.0);
-                            mx = fmaxf(mx, c.y);
-                        }
-                        const int cnt_items = min(32, n_groups - base);
-                        for (int gg = 0; gg < cnt_items; ++gg) {     // merge in GROUP order: deterministic whichever CTA finishes
-                            const double nb = __shfl_sync(0xffffffffu, ni, gg), mb = __shfl_sync(0xffffffffu, mi, gg),
-                                         m2b = __shfl_sync(0xffffffffu, m2i, gg);
-                            const double nt = n + nb, delta = mb - mean, qd = delta * nb / nt;
-                            mean += qd;
-                            m2 += m2b + delta * qd * n;
-                            n = nt;
-                        }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                    if (lane == 0) {
-                        red[33] = (float)mean;
-                        red[34] = (float)(1.0 / (sqrt(m2 / (n - 1.0)) + 1e-5));
-                        red[35] = mx;
-                    }
-                }
-                if (mfcc) {
-                    float* s_dct = s_P;                          // the power buffer is free between items: [n_mels][n_mfcc]
-                    for (int i = dt; i < p.n_mels * p.n_mfcc; i += kET) s_dct[i] = p.dct[i];
-                    group_barrier();
-                    const float floor_db = p.top_db > 0.f ? red[35] - p.top_db : -INFINITY;
-                    const int Tn = min(T, p.out_frames);
-                    for (int idx = dt; idx < p.n_mfcc * Tn; idx += kET) {
-                        const int c = idx / Tn, tt = idx - c * Tn;
-                        float acc = 0.f;
-                        for (int mrow = 0; mrow < p.n_mels; ++mrow)
-                            acc = fmaf(fmaxf(__ldcg(out + (int64_t)mrow * row_stride + tt), floor_db), s_dct[mrow * p.n_mfcc + c], acc);
-                        final_out[(int64_t)c * p.out_frames + tt] = acc;
-                    }
-                    for (int c = 0; c < p.n_mfcc; ++c)
-                        for (int tt = T + dt; tt < p.out_frames; tt += kET) final_out[(int64_t)c * p.out_frames + tt] = 0.f;
-                    group_barrier();
-                    for (int i = dt; i < (int)(kPBytes / 4); i += kET) s_P[i] = 0.f;     // the pad bins must read as zero again
-                } else {
-                    group_barrier();
-                    const float fmean = red[33], inv = red[34];
-                    int mt0 = 0, mt1 = 0, mf0 = 0, mf1 = 0;
-                    if (p.masks) {
-                        mt0 = p.masks[4 * b + 0];
-                        mt1 = p.masks[4 * b + 1];
-                        mf0 = p.masks[4 * b + 2];
-                        mf1 = p.masks[4 * b + 3];
-                    }
-                    // normalise + mask + pad the whole utterance; its values are still L2-resident (plain loads are safe
-                    // behind the acquire fence).  Loads of a batch are issued before its first store.
-                    const bool out_vec = (p.out_frames % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
-                    constexpr int kU = 8;
-                    const int cols = out_vec ? p.out_frames >> 2 : p.out_frames;
-                    const int dq = kET / cols, dr = kET % cols;
-                    int m_ld = dt / cols, c_ld = dt % cols;
-                    while (m_ld < p.n_mels) {
-                        int mm[kU], cc[kU];
-#pragma unroll
-                        for (int u = 0; u < kU; ++u) {
-                            mm[u] = m_ld;
-                            cc[u] = c_ld;
-                            m_ld += dq;
-                            c_ld += dr;
-                            if (c_ld >= cols) {
-                                c_ld -= cols;
-                                ++m_ld;
-                            }
-                        }
-                        if (out_vec) {
-                            float4 x[kU];
-#pragma unroll
-                            for (int u = 0; u < kU; ++u) {
-                                x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (mm[u] < p.n_mels && 4 * cc[u] < T)
-                                    x[u] = *reinterpret_cast<const float4*>(out + (int64_t)mm[u] * p.out_frames + 4 * cc[u]);
-                            }
-#pragma unroll
-                            for (int u = 0; u < kU; ++u) {
-                                if (mm[u] < p.n_mels) {
-                                    const int mrow = mm[u], tt = 4 * cc[u];
-                                    const bool fm = mrow >= mf0 && mrow < mf1;
-                                    float4 v;
-                                    v.x = (tt >= T || fm || (tt >= mt0 && tt < mt1)) ? 0.f : (x[u].x - fmean) * inv;
-                                    v.y = (tt + 1 >= T || fm || (tt + 1 >= mt0 && tt + 1 < mt1)) ? 0.f : (x[u].y - fmean) * inv;
-                                    v.z = (tt + 2 >= T || fm || (tt + 2 >= mt0 && tt + 2 < mt1)) ? 0.f : (x[u].z - fmean) * inv;
-                                    v.w = (tt + 3 >= T || fm || (tt + 3 >= mt0 && tt + 3 < mt1)) ? 0.f : (x[u].w - fmean) * inv;
-                                    *reinterpret_cast<float4*>(out + (int64_t)mrow * p.out_frames + tt) = v;
-                                }
-                            }
-                        } else {
-                            float x[kU];
-#pragma unroll
-                            for (int u = 0; u < kU; ++u) {
-                                x[u] = 0.f;
-                                if (mm[u] < p.n_mels && cc[u] < T) x[u] = out[(int64_t)mm[u] * p.out_frames + cc[u]];
-                            }
-#pragma unroll
-                            for (int u = 0; u < kU; ++u) {
-                                if (mm[u] < p.n_mels) {
-                                    const int mrow = mm[u], tt = cc[u];
-                                    const bool masked = (tt >= mt0 && tt < mt1) || (mrow >= mf0 && mrow < mf1);
-                                    out[(int64_t)mrow * p.out_frames + tt] = (tt >= T || masked) ? 0.f : (x[u] - fmean) * inv;
-                                }
-                            }
-                        }
                     }
                 }
             }
-            group_barrier();                                     // P / tile / red / flag consumed; slot data no longer needed
+            f_barrier();                                         // red consumed; slot data no longer needed
             if (lane == 0) mbar_arrive(&ctl->ring_empty[rs]);
         }
     }
@@ -741,6 +700,123 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
     if (warp == kWarpMma) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// Second launch of the NORM / MFCC modes: one CTA per utterance merges the item partials in GROUP order (Chan's formula,
+// fp64: deterministic), re-reads the utterance's un-normalised dB values (L2-resident for all but the largest batches),
+// normalises, applies the SpecAugment bands and writes the zero padding; MFCC: floor at max - top_db, ortho DCT-II.
+// (The CUDA-core kernel does this inside the main launch, behind a fence + counting atomic per item; with one CTA per SM
+// that latency chain - ~2 us per item - sat in front of the next item's arithmetic.)
+constexpr int kFinThreads = 128;
+__global__ void __launch_bounds__(kFinThreads) frontend_finish_kernel(const FrontendParams p) {
+    __shared__ float red[8];
+    extern __shared__ float s_dct[];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int L = p.lengths ? min(p.lengths[b], p.n_samples) : p.n_samples;
+    if (p.max_samples > 0) L = min(L, p.max_samples);
+    if (L <= kNfft / 2) return;                                  // invalid utterance: zero-filled by the main kernel
+    const int T = 1 + L / kHop, n_groups = (T + kTileFrames - 1) / kTileFrames;
+    const bool mfcc = p.mode == SIR_OUT_MFCC;
+    const int out_rows = mfcc ? p.n_mfcc : p.n_mels;
+    const int row_stride = mfcc ? p.stage_frames : p.out_frames;
+    float* __restrict__ final_out = p.out + (int64_t)b * out_rows * p.out_frames;
+    float* __restrict__ out = mfcc ? p.db_stage + (int64_t)b * p.n_mels * p.stage_frames : final_out;
+    if (mfcc)
+        for (int i = tid; i < p.n_mels * p.n_mfcc; i += kFinThreads) s_dct[i] = p.dct[i];
+    if (warp == 0) {
+        const ItemPartial* parts = p.partials + (int64_t)b * p.groups_max;
+        double n = 0, mean = 0, m2 = 0;
+        float mx = -INFINITY;
+        for (int base = 0; base < n_groups; base += 32) {
+            double ni = 0, mi = 0, m2i = 0;
+            if (base + lane < n_groups) {
+                const ItemPartial part = parts[base + lane];
+                ni = (double)part.n;
+                const double r = part.s1 / ni;
+                mi = (double)part.shift + r;
+                m2i = fmax(part.s2 - part.s1 * r, 0.0);
+                mx = fmaxf(mx, part.vmax);
+            }
+            const int cnt_items = min(32, n_groups - base);
+            for (int gg = 0; gg < cnt_items; ++gg) {
+                const double nb = __shfl_sync(0xffffffffu, ni, gg), mb = __shfl_sync(0xffffffffu, mi, gg),
+                             m2b = __shfl_sync(0xffffffffu, m2i, gg);
+                const double nt = n + nb, delta = mb - mean, qd = delta * nb / nt;
+                mean += qd;
+                m2 += m2b + delta * qd * n;
+                n = nt;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) {
+            red[0] = (float)mean;
+            red[1] = (float)(1.0 / (sqrt(m2 / (n - 1.0)) + 1e-5));
+            red[2] = mx;
+        }
+    }
+    __syncthreads();
+    if (mfcc) {
+        const float floor_db = p.top_db > 0.f ? red[2] - p.top_db : -INFINITY;
+        const int Tn = min(T, p.out_frames);
+        for (int idx = tid; idx < p.n_mfcc * Tn; idx += kFinThreads) {
+            const int c = idx / Tn, tt = idx - c * Tn;
+            float acc = 0.f;
+            for (int mrow = 0; mrow < p.n_mels; ++mrow)
+                acc = fmaf(fmaxf(out[(int64_t)mrow * row_stride + tt], floor_db), s_dct[mrow * p.n_mfcc + c], acc);
+            final_out[(int64_t)c * p.out_frames + tt] = acc;
+        }
+        for (int c = 0; c < p.n_mfcc; ++c)
+            for (int tt = T + tid; tt < p.out_frames; tt += kFinThreads) final_out[(int64_t)c * p.out_frames + tt] = 0.f;
+        return;
+    }
+    const float fmean = red[0], inv = red[1];
+    int mt0 = 0, mt1 = 0, mf0 = 0, mf1 = 0;
+    if (p.masks) {
+        mt0 = p.masks[4 * b + 0];
+        mt1 = p.masks[4 * b + 1];
+        mf0 = p.masks[4 * b + 2];
+        mf1 = p.masks[4 * b + 3];
+    }
+    const bool out_vec = (p.out_frames % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+    if (out_vec) {
+        const int cols = p.out_frames >> 2, total = p.n_mels * cols;
+        constexpr int kU = 4;
+        for (int i0 = tid; i0 < total; i0 += kU * kFinThreads) {
+            float4 x[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {                      // the loads of a batch are issued before its first store
+                const int i = i0 + u * kFinThreads;
+                x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < total) {
+                    const int mrow = i / cols, tt = 4 * (i - mrow * cols);
+                    if (tt < T) x[u] = *reinterpret_cast<const float4*>(out + (int64_t)mrow * p.out_frames + tt);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int i = i0 + u * kFinThreads;
+                if (i < total) {
+                    const int mrow = i / cols, tt = 4 * (i - mrow * cols);
+                    const bool fm = mrow >= mf0 && mrow < mf1;
+                    float4 v;
+                    v.x = (tt >= T || fm || (tt >= mt0 && tt < mt1)) ? 0.f : (x[u].x - fmean) * inv;
+                    v.y = (tt + 1 >= T || fm || (tt + 1 >= mt0 && tt + 1 < mt1)) ? 0.f : (x[u].y - fmean) * inv;
+                    v.z = (tt + 2 >= T || fm || (tt + 2 >= mt0 && tt + 2 < mt1)) ? 0.f : (x[u].z - fmean) * inv;
+                    v.w = (tt + 3 >= T || fm || (tt + 3 >= mt0 && tt + 3 < mt1)) ? 0.f : (x[u].w - fmean) * inv;
+                    *reinterpret_cast<float4*>(out + (int64_t)mrow * p.out_frames + tt) = v;
+                }
+            }
+        }
+    } else {
+        const int total = p.n_mels * p.out_frames;
+        for (int i = tid; i < total; i += kFinThreads) {
+            const int mrow = i / p.out_frames, tt = i - mrow * p.out_frames;
+            const bool masked = (tt >= mt0 && tt < mt1) || (mrow >= mf0 && mrow < mf1);
+            const float x = tt < T ? out[(int64_t)mrow * p.out_frames + tt] : 0.f;
+            out[(int64_t)mrow * p.out_frames + tt] = (tt >= T || masked) ? 0.f : (x - fmean) * inv;
+        }
     }
 }
 
@@ -779,6 +855,13 @@ int frontend_tc_launch(const FrontendParams& p, bool pcm16, int num_sms, cudaStr
         fetc::logmel_frontend_tc_kernel<short><<<grid, fetc::kThreads, fetc::kSmemBytes, stream>>>(p);
     else
         fetc::logmel_frontend_tc_kernel<float><<<grid, fetc::kThreads, fetc::kSmemBytes, stream>>>(p);
+    if (p.mode == SIR_OUT_LOGMEL_NORM || p.mode == SIR_OUT_MFCC) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(SIR_ERR_CUDA, "launch of logmel_frontend_tc_kernel failed: %s", cudaGetErrorString(e));
+        count_launch();
+        const size_t dct_bytes = p.mode == SIR_OUT_MFCC ? (size_t)p.n_mels * p.n_mfcc * sizeof(float) : 0;
+        fetc::frontend_finish_kernel<<<p.batch, fetc::kFinThreads, dct_bytes, stream>>>(p);
+    }
     return SIR_OK;
 }
 
