@@ -746,6 +746,7 @@ static int frontend_launch(sir_frontend* fe, const void* d_wave, bool pcm16, int
     int eff = max_samples > 0 && max_samples < n_samples ? max_samples : n_samples;
     const int groups = eff > kNfft / 2 ? (tc_kernel ? frontend_tc_groups(1 + eff / kHop) : (1 + eff / kHop + kGroupFrames - 1) / kGroupFrames) : 1;
     const int64_t items = (int64_t)batch * groups;
+    if (items >= ((int64_t)1 << 31)) return fail(SIR_ERR_UNSUPPORTED, "sir_frontend_forward: %lld work items in one launch", (long long)items);
     p.batch = batch;
     p.groups_max = groups;
     if (mode == SIR_OUT_LOGMEL_NORM || mode == SIR_OUT_MFCC) {

@@ -12,7 +12,11 @@ struct TcDeviceTables {
     const uint16_t* b1_img;      // 8 KB   stage-1 operand image (fp16, swizzled, hi rows then lo rows)
     const uint16_t* b2_img;      // 16 KB  stage-2 operand image
     const float* twiddle;        // [32][16][2] (cos, -sin)(2 pi n2 k1 / 1024), k1 = 1..16
-    const float* mel_weight;     // the sparse filterbank taps WITHOUT the 0.25 of the CUDA-core post-pass
+    const float* mel_weight;     // the sparse filterbank taps WITHOUT the 0.25 of the CUDA-core post-pass, the runs of a band
+                                 // quad (4q .. 4q+3) zero-padded to the same length; 1536 floats, zero behind the taps
+    const int32_t* mel_start;    // [n_mels] first bin / padded tap count / offset into mel_weight (multiples of 4)
+    const int32_t* mel_count;
+    const int32_t* mel_offset;
 };
 
 // One (utterance, 8-frame group) work item's contribution to the utterance statistics, written to global memory by

@@ -75,7 +75,7 @@ constexpr uint32_t kOffA2Hi = 65536, kOffA2Lo = 98304;           // 256 rows x 1
 constexpr uint32_t kOffB1 = 131072;                              // 64 rows x 128 B
 constexpr uint32_t kOffB2 = 139264;                              // 128 rows x 128 B
 constexpr uint32_t kOffP = 155648;                               // 15 x 528 floats
-constexpr uint32_t kPBytes = 31744;
+constexpr uint32_t kPBytes = 32256;
 constexpr uint32_t kOffMelW = kOffP + kPBytes;                   // 1536 floats
 constexpr uint32_t kOffMelIdx = kOffMelW + kMelWeightCap * 4;    // start / count / offset: 3 x 128 ints
 constexpr uint32_t kOffTile = kOffMelIdx + 3 * kMaxMels * 4;     // two [n_mels][16] float tiles (D/E -> F)
@@ -101,7 +101,8 @@ __device__ __forceinline__ void pipe_wait(uint64_t* bar, uint32_t parity) {
             : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
             : "memory");
         if (ok) return;
-        if (spin > (1u << 20)) __trap();
+        __nanosleep(32);                                         // (the hint alone still re-issued the probe every ~100 cycles)
+        if (spin > (1u << 22)) __trap();
     }
 }
 __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
@@ -234,11 +235,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
         uint4* s2 = reinterpret_cast<uint4*>(smem + kOffB2);
         for (int i = tid; i < 512; i += kThreads) s1[i] = __ldg(g1 + i);
         for (int i = tid; i < 1024; i += kThreads) s2[i] = __ldg(g2 + i);
-        for (int i = tid; i < kMelWeightCap; i += kThreads) s_melw[i] = i < p.mel_weight_count ? __ldg(p.tc.mel_weight + i) : 0.f;
+        for (int i = tid; i < kMelWeightCap; i += kThreads) s_melw[i] = __ldg(p.tc.mel_weight + i);   // (zero behind the taps)
         for (int i = tid; i < p.n_mels; i += kThreads) {
-            s_mel_start[i] = __ldg(p.tables.mel_start + i);
-            s_mel_count[i] = __ldg(p.tables.mel_count + i);
-            s_mel_offset[i] = __ldg(p.tables.mel_offset + i);
+            s_mel_start[i] = __ldg(p.tc.mel_start + i);
+            s_mel_count[i] = __ldg(p.tc.mel_count + i);
+            s_mel_offset[i] = __ldg(p.tc.mel_offset + i);
         }
         for (int i = tid; i < 1024; i += kThreads) {               // window[32 n1 + l] -> [n1 / 4][l][n1 % 4]
             const int n1 = i >> 5, l = i & 31;
@@ -251,27 +252,32 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
-    const int64_t total_items = (int64_t)p.batch * p.groups_max;
+    const int64_t total_items = (int64_t)p.batch * p.groups_max;        // (the host refuses launches with >= 2^31 items)
 
     if (warp < 4) {
         // =============================== A: samples -> stage-1 operand ===============================================
         const float4* s_win = reinterpret_cast<const float4*>(smem + kOffWin) + lane;
         // ticket pipeline of the drawing lane: i0 / L0 = this iteration's item and its length, i1 = the next item
-        long long i0 = -1, i1 = -1;
+        // (32-bit item indices: one launch has fewer than 2^31 items; a ticket outside [0, total) means "no more work")
+        const int total_i = (int)total_items;
+        int i0 = -1, i1 = -1;
         int L0 = 0;
-        auto length_of = [&](long long item) -> int {
-            if (item < 0 || item >= total_items) return 0;
-            const int b = (int)(item / p.groups_max);
+        auto length_of = [&](int item) -> int {
+            if (item < 0) return 0;
+            const int b = item / p.groups_max;
             int L = p.lengths ? min(__ldg(p.lengths + b), p.n_samples) : p.n_samples;
             if (p.max_samples > 0) L = min(L, p.max_samples);
             return L;
         };
-        auto draw = [&]() -> long long { return (long long)(atomicAdd(p.work_counter, 1ULL) - p.work_base); };
+        auto draw = [&]() -> int {
+            const unsigned long long t = atomicAdd(p.work_counter, 1ULL) - p.work_base;      // wraps to huge if the base is ahead
+            return t < (unsigned long long)total_i ? (int)t : -1;
+        };
         // Request the samples of a coming item into L2 (one bulk-prefetch instruction for its 16 blocks): the A warps hold
         // only 8 KB of loads in flight per SM, which at HBM latency is ~1 TB/s for the whole chip; at L2 latency it is enough.
-        auto prefetch_item = [&](long long item, int Li) {
-            if (item < 0 || item >= total_items || Li <= kNfft / 2) return;
-            const int b = (int)(item / p.groups_max), g = (int)(item - (long long)b * p.groups_max);
+        auto prefetch_item = [&](int item, int Li) {
+            if (item < 0 || Li <= kNfft / 2) return;
+            const int b = item / p.groups_max, g = item - b * p.groups_max;
             const int n_lo = max(0, (g * kTileFrames - 1) * kHop), n_hi = min(Li, (g * kTileFrames + kTileFrames) * kHop);
             if (n_hi <= n_lo) return;
             const char* base = reinterpret_cast<const char*>(static_cast<const SampleT*>(p.wave) + (int64_t)b * p.wave_stride);
@@ -287,44 +293,52 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
             L0 = length_of(i0);
             prefetch_item(i0, L0);
         }
+        uint32_t pub = 0;                                        // slots published so far (drawing lane)
+        bool pub_end = false;
         for (uint32_t it = 0;; ++it) {
             const int rs = it % kRing;
             const uint32_t rph = (it / kRing) & 1u;
             if (warp == 0) {
                 if (lane == 0) {
-                    pipe_wait(&ctl->ring_empty[rs], rph ^ 1u);
-                    ItemSlot& sl = ctl->slot[rs];
-                    for (;;) {                                   // skip tickets beyond an utterance's last group (ragged batches)
-                        if (i0 < 0 || i0 >= total_items) {
-                            sl.item = -1;
-                            break;
+                    // publish ONE ITEM AHEAD: the other warps never wait for this warp to finish its own frames first
+                    while (!pub_end && pub <= it + 1) {
+                        const int ps = pub % kRing;
+                        pipe_wait(&ctl->ring_empty[ps], ((pub / kRing) & 1u) ^ 1u);
+                        ItemSlot& sl = ctl->slot[ps];
+                        for (;;) {                               // skip tickets beyond an utterance's last group (ragged batches)
+                            if (i0 < 0) {
+                                sl.item = -1;
+                                pub_end = true;
+                                break;
+                            }
+                            const int b = i0 / p.groups_max, g = i0 - b * p.groups_max;
+                            const bool valid = L0 > kNfft / 2;
+                            const int T = valid ? 1 + L0 / kHop : 0;
+                            const int n_groups = valid ? (T + kTileFrames - 1) / kTileFrames : 1;
+                            if (g < n_groups) {
+                                sl.item = i0;
+                                sl.b = b;
+                                sl.t0 = g * kTileFrames;
+                                sl.nfr = valid ? min(kTileFrames, T - g * kTileFrames) : 0;
+                                sl.T = T;
+                                sl.L = L0;
+                                sl.n_groups = n_groups;
+                                break;
+                            }
+                            const int L1 = length_of(i1);
+                            i0 = i1;
+                            L0 = L1;
+                            i1 = draw();
                         }
-                        const int b = (int)(i0 / p.groups_max), g = (int)(i0 - (long long)b * p.groups_max);
-                        const bool valid = L0 > kNfft / 2;
-                        const int T = valid ? 1 + L0 / kHop : 0;
-                        const int n_groups = valid ? (T + kTileFrames - 1) / kTileFrames : 1;
-                        if (g < n_groups) {
-                            sl.item = i0;
-                            sl.b = b;
-                            sl.t0 = g * kTileFrames;
-                            sl.nfr = valid ? min(kTileFrames, T - g * kTileFrames) : 0;
-                            sl.T = T;
-                            sl.L = L0;
-                            sl.n_groups = n_groups;
-                            break;
+                        mbar_arrive(&ctl->ring_full[ps]);
+                        ++pub;
+                        if (!pub_end) {                          // advance: the next item's samples are requested into L2, the
+                            const int L1 = length_of(i1);        // draw after it is in flight while this item is processed
+                            prefetch_item(i1, L1);
+                            i0 = i1;
+                            L0 = L1;
+                            i1 = draw();
                         }
-                        const int L1 = length_of(i1);
-                        i0 = i1;
-                        L0 = L1;
-                        i1 = draw();
-                    }
-                    mbar_arrive(&ctl->ring_full[rs]);
-                    if (sl.item >= 0) {                          // advance: the next item's samples are requested into L2, the
-                        const int L1 = length_of(i1);            // draw after it is in flight while this item is processed
-                        prefetch_item(i1, L1);
-                        i0 = i1;
-                        L0 = L1;
-                        i1 = draw();
                     }
                 }
                 __syncwarp();
@@ -341,14 +355,17 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                 // is processed
                 float xa[16], xb[16], xc[16];
                 const int jb = t0 + f0 - 1, nf = min(4, nfr - f0);
-                load_block(row, L, jb, lane, xa);
-                load_block(row, L, jb + 1, lane, xb);
-                pipe_wait(&ctl->a1_empty[warp], (it & 1u) ^ 1u); // stage 1 of the previous item has read this sub-tile
+                // step s requests block jb + s and - from s = 2 on - turns blocks (s - 2, s - 1) into frame s - 2: one copy of
+                // the load code and one of the frame code (rolled: the inlined copies thrashed the instruction cache), and
+                // every block is requested two frames before it is needed
 #pragma unroll 1
-                for (int j = 0; j < nf; ++j) {                   // (rolled: four inlined copies of the frame code thrash the I-cache)
-                    if (j + 1 < nf) load_block(row, L, jb + j + 2, lane, xc);
-                    const float i2 = store_frame(xa, xb, s_win, tile_addr, 32 * j + lane);
-                    if (lane == 0) sl.inv2[f0 + j] = i2;
+                for (int step = 0; step < nf + 2; ++step) {
+                    if (step <= nf) load_block(row, L, jb + step, lane, xc);
+                    if (step == 2) pipe_wait(&ctl->a1_empty[warp], (it & 1u) ^ 1u);   // stage 1 of the previous item has read this sub-tile
+                    if (step >= 2) {
+                        const float i2 = store_frame(xa, xb, s_win, tile_addr, 32 * (step - 2) + lane);
+                        if (lane == 0) sl.inv2[f0 + step - 2] = i2;
+                    }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         xa[i] = xb[i];
@@ -515,8 +532,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
     } else if (warp < kWarpF0) {
         // =============================== D/E: D2 -> power -> mel -> dB -> tile (shared memory only) ==================
         const int q = warp & 3;
-        const int dt = (warp - kWarpD0) * 32 + lane;             // 0..127
-        const int n_units = 3 * ((p.n_mels + 31) >> 5);
         for (uint32_t it = 0;; ++it) {
             const int rs = it % kRing;
             pipe_wait(&ctl->ring_full[rs], (it / kRing) & 1u);
@@ -528,6 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
             }
             const int nfr = sl.nfr;
             // ---- power spectrum of the item's frames ------------------------------------------------------------
+#pragma unroll 1
             for (int m = 0; m < 2; ++m) {
                 pipe_wait(&ctl->d2_full[m], it & 1u);
                 tc_fence_after();
@@ -537,23 +553,27 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                 if (__any_sync(0xffffffffu, valid)) {
                     const uint32_t trow = tmem_base + 256u + (uint32_t)m * 128u + ((uint32_t)(q * 32) << 16);
                     float* Pf = s_P + f * kPStride;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
+#pragma unroll 1
+                    for (int j = 0; j < 2; ++j) {                // (rolled: code size)
+                        // where this lane's 16 bins of column chunk j go: base + step * i for i < count (no branch in the loop)
+                        //   j = 0 (k2 = i):        bin k1 + 32 i
+                        //   j = 1 (k2 = 16 + i):   mirror 1024 - (k1 + 32 k2) = 512 - k1 - 32 i  (k1 = 1..15);
+                        //                          k1 = 0: only k2 = 16, the Nyquist bin 512;  k1 = 16: nothing
+                        int base, step, count;
+                        if (j == 0) {
+                            base = k1; step = 32; count = 16;
+                        } else {
+                            base = 512 - k1; step = -32; count = k1 == 0 ? 1 : (k1 == 16 ? 0 : 16);
+                        }
+                        if (!valid) count = 0;
                         float v[32], u[32];
                         tmem_ld_32x32_pair(trow + 32 * j, trow + 64 + 32 * j, v, u);
-                        if (valid) {
+                        float* dst = Pf + base;
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float re = v[2 * i] + u[2 * i], im = v[2 * i + 1] + u[2 * i + 1];
-                                const float pw = fmaf(re, re, im * im);
-                                if (j == 0) {
-                                    Pf[k1 + 32 * i] = pw;                                   // k2 = i: bin k1 + 32 k2
-                                } else if (k1 == 0) {
-                                    if (i == 0) Pf[512] = pw;                               // k2 = 16: the Nyquist bin
-                                } else if (k1 != 16) {
-                                    Pf[512 - k1 - 32 * i] = pw;                             // mirror: 1024 - (k1 + 32 (16 + i))
-                                }
-                            }
+                        for (int i = 0; i < 16; ++i) {
+                            const float re = v[2 * i] + u[2 * i], im = v[2 * i + 1] + u[2 * i + 1];
+                            const float pw = fmaf(re, re, im * im);
+                            if (i < count) dst[step * i] = pw;
                         }
                     }
                 }
@@ -566,49 +586,49 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
             float* tile = s_tile + buf * kTileFloats;
             pipe_wait(&ctl->tile_empty[buf], ((it >> 1) & 1u) ^ 1u);   // the F warps have drained this tile
             group_barrier();                                     // P complete
-            // ---- sparse mel taps: units = (32 bands, 5 frames), most expensive bands first ----------------------------
+            // ---- sparse mel taps: lane = (band, frame).  The 16 lanes of a half-warp read the same four taps (broadcast)
+            // and their own frame's four bins (rows 532 floats apart: conflict-free LDS.128).  A warp takes QUADS of
+            // neighbouring bands (4q..4q+3; the host pads their tap runs to one length), two bands per lane, the loads of
+            // tap group i + 1 in flight while group i is accumulated; quads go round-robin over the four warps.
             if (nfr > 0) {
-                for (;;) {
-                    int u = 0;
-                    if (lane == 0) u = atomicAdd(&ctl->unit_counter, 1);
-                    u = __shfl_sync(0xffffffffu, u, 0);
-                    if (u >= n_units) break;
-                    const int bg = (n_units / 3) - 1 - u / 3, f_lo = 5 * (u % 3);
-                    if (f_lo >= nfr) continue;
-                    const int band = 32 * bg + lane;
-                    const bool active = band < p.n_mels;
-                    const int n4 = active ? s_mel_count[band] >> 2 : 0;
-                    const float4* __restrict__ w4 = reinterpret_cast<const float4*>(s_melw + (active ? s_mel_offset[band] : 0));
-                    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(s_P + f_lo * kPStride + (active ? s_mel_start[band] : 0));
-                    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-                    const int nf = min(5, nfr - f_lo);
-#pragma unroll 2
+                const int w = warp - kWarpD0, h = lane >> 4, f = lane & 15;
+                const int n_quads = (p.n_mels + 3) >> 2;
+                const float* Pf = s_P + (f < nfr ? f : 0) * kPStride;
+                const float i2 = sl.inv2[f < nfr ? f : 0];
+                for (int pq = w; pq < n_quads; pq += 4) {
+                    const int band0 = 4 * pq + h, band1 = band0 + 2;
+                    const int bq = min(band0, p.n_mels - 1), br = min(band1, p.n_mels - 1);
+                    const int n4 = s_mel_count[4 * pq] >> 2;     // the same for the whole quad
+                    const float4* __restrict__ wa = reinterpret_cast<const float4*>(s_melw + s_mel_offset[bq]);
+                    const float4* __restrict__ wb = reinterpret_cast<const float4*>(s_melw + s_mel_offset[br]);
+                    const float4* __restrict__ pa = reinterpret_cast<const float4*>(Pf + s_mel_start[bq]);
+                    const float4* __restrict__ pb = reinterpret_cast<const float4*>(Pf + s_mel_start[br]);
+                    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+                    float4 wva = wa[0], xa = pa[0], wvb = wb[0], xb = pb[0];
                     for (int i = 0; i < n4; ++i) {
-                        const float4 w = w4[i];
-                        float4 x[5];
-#pragma unroll
-                        for (int ff = 0; ff < 5; ++ff) x[ff] = p4[(ff < nf ? ff : 0) * (kPStride / 4) + i];
-#pragma unroll
-                        for (int ff = 0; ff < 5; ++ff)
-                            acc[ff] = fmaf(w.x, x[ff].x, fmaf(w.y, x[ff].y, fmaf(w.z, x[ff].z, fmaf(w.w, x[ff].w, acc[ff]))));
+                        const int nx = i + 1 < n4 ? i + 1 : i;
+                        const float4 nwa = wa[nx], nxa = pa[nx], nwb = wb[nx], nxb = pb[nx];
+                        a0 = fmaf(wva.x, xa.x, fmaf(wva.z, xa.z, a0));
+                        a1 = fmaf(wva.y, xa.y, fmaf(wva.w, xa.w, a1));
+                        b0 = fmaf(wvb.x, xb.x, fmaf(wvb.z, xb.z, b0));
+                        b1 = fmaf(wvb.y, xb.y, fmaf(wvb.w, xb.w, b1));
+                        wva = nwa; xa = nxa; wvb = nwb; xb = nxb;
                     }
-                    if (active) {
-#pragma unroll
-                        for (int ff = 0; ff < 5; ++ff) {
-                            if (ff < nf) {
-                                float v = acc[ff] * sl.inv2[f_lo + ff];
-                                // 10 log10(x) = (10 log10 2) lg2(x): lg2.approx is good to ~1e-7 relative here, i.e. ~1e-6 dB
-                                if (p.mode != SIR_OUT_MEL_POWER) v = 3.01029995663981195f * __log2f(fmaxf(v, 1e-10f));
-                                tile[band * 16 + f_lo + ff] = v;
-                            }
+                    if (f < nfr) {
+                        float va = (a0 + a1) * i2, vb = (b0 + b1) * i2;
+                        // 10 log10(x) = (10 log10 2) lg2(x): lg2.approx is good to ~1e-7 relative here, i.e. ~1e-6 dB
+                        if (p.mode != SIR_OUT_MEL_POWER) {
+                            va = 3.01029995663981195f * __log2f(fmaxf(va, 1e-10f));
+                            vb = 3.01029995663981195f * __log2f(fmaxf(vb, 1e-10f));
                         }
+                        if (band0 < p.n_mels) tile[band0 * 16 + f] = va;
+                        if (band1 < p.n_mels) tile[band1 * 16 + f] = vb;
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->tile_full[buf]);    // release: this warp's tile entries
-            group_barrier();                                     // every warp is done with P (and with the unit counter)
-            if (dt == 0) ctl->unit_counter = 0;                  // (next use is behind the next item's barrier)
+            group_barrier();                                     // every warp is done with P
             if (lane == 0) mbar_arrive(&ctl->ring_empty[rs]);
         }
     } else {
@@ -825,21 +845,44 @@ __global__ void __launch_bounds__(kFinThreads) frontend_finish_kernel(const Fron
 // ---- host side ------------------------------------------------------------------------------------------------------
 int frontend_tc_upload_tables(DeviceBuffer& buf, TcDeviceTables& dev, int sample_rate, int n_mels) {
     const fetc::HostTcTables t = fetc::build_tc_tables();
-    HostFrontendTables ft = build_frontend_tables(sample_rate, n_mels);
-    for (auto& w : ft.mel_weight) w *= 4.0f;                     // frontend_tables.h folds the CUDA-core post-pass's 0.25 in
+    const HostFrontendTables ft = build_frontend_tables(sample_rate, n_mels);
+    // The kernel walks the taps of a QUAD of neighbouring bands (4q .. 4q + 3) in lock step: their runs are padded with zero
+    // weights to the longest one (the extra taps multiply finite power bins, the rows of the power buffer are zero behind
+    // bin 512).  frontend_tables.h folds the CUDA-core post-pass's 0.25 into its weights: undone here.
+    std::vector<int32_t> m_start(n_mels), m_count(n_mels), m_offset(n_mels);
+    std::vector<float> m_weight;
+    for (int m = 0; m < n_mels; ++m) {
+        int n = 0;
+        for (int o = m & ~3; o < (m & ~3) + 4 && o < n_mels; ++o) n = ft.mel_count[o] > n ? ft.mel_count[o] : n;
+        if (ft.mel_start[m] + n > fetc::kPStride) return fail(SIR_ERR_UNSUPPORTED, "mel band %d: padded run leaves the power row", m);
+        m_start[m] = ft.mel_start[m];
+        m_count[m] = n;
+        m_offset[m] = (int32_t)m_weight.size();
+        for (int i = 0; i < n; ++i) m_weight.push_back(i < ft.mel_count[m] ? 4.0f * ft.mel_weight[ft.mel_offset[m] + i] : 0.f);
+    }
+    if ((int)m_weight.size() > fetc::kMelWeightCap)
+        return fail(SIR_ERR_UNSUPPORTED, "filterbank has %zu padded taps (cap %d)", m_weight.size(), fetc::kMelWeightCap);
     const size_t o_b1 = 0, o_b2 = o_b1 + t.b1_img.size() * 2, o_tw = o_b2 + t.b2_img.size() * 2,
-                 o_mw = o_tw + t.twiddle.size() * 4, total = o_mw + ft.mel_weight.size() * 4;
+                 o_mw = o_tw + t.twiddle.size() * 4, o_ms = o_mw + fetc::kMelWeightCap * 4, o_mc = o_ms + n_mels * 4,
+                 o_mo = o_mc + n_mels * 4, total = o_mo + n_mels * 4;
     int rc = buf.reserve(total);
     if (rc != SIR_OK) return rc;
     char* base = static_cast<char*>(buf.ptr);
     SIR_CUDA(cudaMemcpy(base + o_b1, t.b1_img.data(), t.b1_img.size() * 2, cudaMemcpyHostToDevice));
     SIR_CUDA(cudaMemcpy(base + o_b2, t.b2_img.data(), t.b2_img.size() * 2, cudaMemcpyHostToDevice));
     SIR_CUDA(cudaMemcpy(base + o_tw, t.twiddle.data(), t.twiddle.size() * 4, cudaMemcpyHostToDevice));
-    SIR_CUDA(cudaMemcpy(base + o_mw, ft.mel_weight.data(), ft.mel_weight.size() * 4, cudaMemcpyHostToDevice));
+    SIR_CUDA(cudaMemset(base + o_mw, 0, fetc::kMelWeightCap * 4));
+    SIR_CUDA(cudaMemcpy(base + o_mw, m_weight.data(), m_weight.size() * 4, cudaMemcpyHostToDevice));
+    SIR_CUDA(cudaMemcpy(base + o_ms, m_start.data(), n_mels * 4, cudaMemcpyHostToDevice));
+    SIR_CUDA(cudaMemcpy(base + o_mc, m_count.data(), n_mels * 4, cudaMemcpyHostToDevice));
+    SIR_CUDA(cudaMemcpy(base + o_mo, m_offset.data(), n_mels * 4, cudaMemcpyHostToDevice));
     dev.b1_img = reinterpret_cast<const uint16_t*>(base + o_b1);
     dev.b2_img = reinterpret_cast<const uint16_t*>(base + o_b2);
     dev.twiddle = reinterpret_cast<const float*>(base + o_tw);
     dev.mel_weight = reinterpret_cast<const float*>(base + o_mw);
+    dev.mel_start = reinterpret_cast<const int32_t*>(base + o_ms);
+    dev.mel_count = reinterpret_cast<const int32_t*>(base + o_mc);
+    dev.mel_offset = reinterpret_cast<const int32_t*>(base + o_mo);
     return SIR_OK;
 }
 

@@ -26,7 +26,8 @@ namespace sir {
 namespace fetc {
 
 constexpr int kTileFrames = 15;          // frames per work item: 15 x 17 = 255 stage-2 rows = two 128-row UMMA tiles
-constexpr int kPStride = 528;            // floats per frame of the power buffer (528 mod 32 = 16: conflict-free scatter)
+constexpr int kPStride = 532;            // floats per frame of the power buffer: 16-byte aligned rows whose 16-byte chunk index
+                                         // advances by 5 (mod 8) per frame - lanes = frames read LDS.128 without bank conflicts
 
 // fp32 -> fp16 bits, round to nearest even (host-side twin of cvt.rn.f16.f32)
 inline uint16_t half_bits(float f) {
