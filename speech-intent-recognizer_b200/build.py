@@ -39,7 +39,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     from concurrent.futures import ThreadPoolExecutor
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("SIR_NVCC_EXTRA", "").split()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers += [os.path.join(HERE, "..", "include", "sir_b200.h"), os.path.abspath(__file__)]
     newest_header = max(os.path.getmtime(h) for h in headers)

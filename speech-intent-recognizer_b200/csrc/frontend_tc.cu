@@ -44,6 +44,15 @@ namespace fetc {
 
 using namespace tc;
 
+#ifndef SIR_FE_SLEEP
+#define SIR_FE_SLEEP 32
+#endif
+#ifndef SIR_FE_PREFETCH
+#define SIR_FE_PREFETCH 1
+#endif
+#ifndef SIR_FE_S1_FIRST
+#define SIR_FE_S1_FIRST 1
+#endif
 constexpr int kNumWarps = 16;
 constexpr int kThreads = kNumWarps * 32;
 constexpr int kWarpMma = 4, kWarpD0 = 9, kWarpF0 = 13;       // warps 0-3: A, 4: MMA, 5-8: C, 9-12: D/E, 13-15: F
@@ -101,7 +110,7 @@ __device__ __forceinline__ void pipe_wait(uint64_t* bar, uint32_t parity) {
             : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
             : "memory");
         if (ok) return;
-        __nanosleep(32);                                         // (the hint alone still re-issued the probe every ~100 cycles)
+        __nanosleep(SIR_FE_SLEEP);                               // (the hint alone still re-issued the probe every ~100 cycles)
         if (spin > (1u << 22)) __trap();
     }
 }
@@ -285,7 +294,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
             uintptr_t hi = reinterpret_cast<uintptr_t>(base + (size_t)n_hi * sizeof(SampleT));
             lo = (lo + 15) & ~(uintptr_t)15;
             hi &= ~(uintptr_t)15;
+#if SIR_FE_PREFETCH == 1
             if (hi > lo) prefetch_l2_bulk(reinterpret_cast<const void*>(lo), (uint32_t)(hi - lo));
+#elif SIR_FE_PREFETCH == 2
+            for (uintptr_t a = lo; a < hi; a += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+#endif
         };
         if (warp == 0 && lane == 0) {
             i0 = draw();
@@ -394,6 +407,63 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
         bool have_slot = false, end1 = false;
         for (;;) {
             bool progressed = false;
+            // stage 1 first: its four MMAs are short and release an A warp; a stage 2 issued ahead of them (the tensor pipe
+            // executes in order) would keep that warp waiting for ~1,000 cycles
+#if SIR_FE_S1_FIRST
+            if (!end1) {
+                if (!have_slot) {
+                    const int rs = i1 % kRing;
+                    if (mbar_test_wait(&ctl->ring_full[rs], (i1 / kRing) & 1u)) {
+                        const bool more = ctl->slot[rs].item >= 0;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&ctl->ring_empty[rs]);
+                        if (more) have_slot = true;
+                        else end1 = true;
+                        progressed = true;
+                    }
+                }
+                if (have_slot && mbar_test_wait(&ctl->a1_full[s1], i1 & 1u) && mbar_test_wait(&ctl->d1_empty[s1], (i1 & 1u) ^ 1u)) {
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint64_t a = make_kmajor_desc<128>(sbase + kOffA1 + s1 * 16384u);
+                        const uint32_t d = tmem_base + s1 * 64u;
+                        umma_f16(d, desc_advance_k(a, 0), desc_advance_k(b1, 0), id1a, 0u);      // hi . [B_hi; B_lo]
+                        umma_f16(d, desc_advance_k(a, 16), desc_advance_k(b1, 16), id1a, 1u);
+                        umma_f16(d, desc_advance_k(a, 32), desc_advance_k(b1, 0), id1b, 1u);     // lo . B_hi
+                        umma_f16(d, desc_advance_k(a, 48), desc_advance_k(b1, 16), id1b, 1u);
+                        umma_commit(&ctl->a1_empty[s1]);
+                        umma_commit(&ctl->d1_full[s1]);
+                    }
+                    __syncwarp();
+                    if (++s1 == 4) {
+                        s1 = 0;
+                        ++i1;
+                        have_slot = false;
+                    }
+                    progressed = true;
+                }
+            }
+            if (i2 < i1 && mbar_test_wait(&ctl->a2_full[m2], i2 & 1u) && mbar_test_wait(&ctl->d2_empty[m2], (i2 & 1u) ^ 1u)) {
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint64_t ah = make_kmajor_desc<128>(sbase + kOffA2Hi + m2 * 16384u);
+                    const uint64_t al = make_kmajor_desc<128>(sbase + kOffA2Lo + m2 * 16384u);
+                    const uint32_t d = tmem_base + 256u + m2 * 128u;
+#pragma unroll
+                    for (int k = 0; k < 64; k += 16) umma_f16(d, desc_advance_k(ah, k), desc_advance_k(b2, k), id2a, k ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 64; k += 16) umma_f16(d, desc_advance_k(al, k), desc_advance_k(b2, k), id2b, 1u);
+                    umma_commit(&ctl->d2_full[m2]);
+                    if (m2 == 1) umma_commit(&ctl->a2_empty);
+                }
+                __syncwarp();
+                if (++m2 == 2) {
+                    m2 = 0;
+                    ++i2;
+                }
+                progressed = true;
+            }
+#else
             if (i2 < i1 && mbar_test_wait(&ctl->a2_full[m2], i2 & 1u) && mbar_test_wait(&ctl->d2_empty[m2], (i2 & 1u) ^ 1u)) {
                 tc_fence_after();
                 if (elect_one_sync()) {
@@ -447,6 +517,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                     progressed = true;
                 }
             }
+#endif
             if (end1 && i2 == i1) break;
             if (progressed) {
                 idle = 0;
