@@ -504,7 +504,7 @@ def measure_training(ctx, steps, warmup, batch=16, dataset_size=4096, cpu_ref=Tr
     model = ctx.models.CNNAudioGRU(NUM_CLASSES)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in ctx.synth.make_weights(1234).items()}, strict=False)
     model = model.cuda()
-    trainer = train.DataParallelTrainer(model, lr=5e-5, weight_decay=1e-4, use_amp=True, seed=1)
+    trainer = train.DataParallelTrainer(model, lr=5e-5, weight_decay=1e-4, use_amp=True, seed=1, use_graph=not ctx.args.no_graph)
     n = dataset_size
     feats, labels = train_features(100 + ctx.rank, n)
     feats, labels = feats.cuda(), labels.cuda()
@@ -535,6 +535,8 @@ def measure_training(ctx, steps, warmup, batch=16, dataset_size=4096, cpu_ref=Tr
     l0 = native.launch_count()
     ms, loss = ctx.timed(lambda: run(steps))
     launches = native.launch_count() - l0
+    if trainer._graph is not None:                                   # replayed launches are not seen by the library's counter
+        launches += trainer._graph["launches"] * steps
     coll = float(np.mean(trainer.collective_ms)) if trainer.collective_ms else 0.0
     trainer.time_collective = False
     # host-buffer variant: the batch (features + labels) comes from pinned host memory every step, the loss goes back
@@ -563,6 +565,9 @@ def measure_training(ctx, steps, warmup, batch=16, dataset_size=4096, cpu_ref=Tr
                        f"flag per step" if ctx.world > 1 else "none at world size 1 (the all-reduce is skipped)"),
         "all_reduce_ms": round(coll, 4), "all_reduce_share": round(coll / (ms / steps), 4) if ms > 0 else None,
         "skipped_steps": trainer.skipped_steps,
+        "cuda_graph": (f"two graphs per step (before / after the gradient all-reduce), {trainer._graph['launches']} kernels of "
+                       "libsir_b200 per replay; step count, bias corrections, loss scale and dropout offset live on the device"
+                       if trainer._graph is not None else "off (eager launches)"),
         "e2e": {"value": batch * ctx.world * steps / e2e_s, "unit": "utt/s", "h2d_bytes_per_step": batch * 64 * OUT_FRAMES * 4 + batch * 8,
                 "d2h_bytes_per_step": 8, "api": "DataParallelTrainer.step(features, labels) from pinned host buffers, loss read back"},
         "stages_ms": {k: round(v[0] / k_prof, 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][0])[:12]},
@@ -896,6 +901,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="utterances per GPU per step (config3: total utterances)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="config2: skip the `train` object")
+    ap.add_argument("--no-graph", action="store_true", help="training step: eager launches instead of CUDA-graph replays")
     ap.add_argument("--train-steps", type=int, default=50, help="config2: steps of the `train` object")
     ap.add_argument("--sub-batches", type=int, default=1, help="sub-batches of the host-buffer pipeline (e2e)")
     ap.add_argument("--depth", type=int, default=4, help="batches in flight in the host-buffer pipeline (e2e)")

@@ -240,6 +240,30 @@ int sir_gemm_nt_split_f16(const float* d_a, const float* d_w, const float* d_bia
 int sir_conv3x3_nhwc_split_f16(const float* d_in, const float* d_w, float* d_out, int B, int H, int W, int cin, int cout,
                                void* stream);
 
+/* ---- device-resident step state: the training step as a replayable CUDA graph ------------------------------------
+ * scripts/train.py:80-116 passes values that change every step through the host: the Adam step count (bias corrections),
+ * the GradScaler scale, the dropout stream position.  With them in a 32-byte DEVICE struct (d_state: any 8-byte aligned
+ * device allocation of SIR_TRAIN_STATE_BYTES) the whole step takes no per-step host argument and can be captured once
+ * with cudaStreamBeginCapture / torch.cuda.graph and replayed:
+ *     sir_train_state_begin      bias corrections of step + 1, inv_scale = 1 / (loss_scale * world)
+ *     sir_model_train_forward    (dropout offset read from the state once sir_model_set_train_state was called)
+ *     sir_cross_entropy_state    loss scale read from the state
+ *     sir_model_backward, sir_grad_nonfinite, [gradient all-reduce]
+ *     sir_adam_step_state        corrections / inv_scale read from the state; skipped when *d_found_inf != 0
+ *     sir_train_state_end        step += (*d_found_inf == 0); dropout offset += increment
+ * sir_train_state_set_scale is the host's GradScaler growth / back-off between replays (synchronises the stream). */
+#define SIR_TRAIN_STATE_BYTES 32
+int sir_train_state_init(void* d_state, float loss_scale, int step, uint64_t dropout_offset, void* stream);
+int sir_train_state_set_scale(void* d_state, float loss_scale, void* stream);
+int sir_train_state_begin(void* d_state, float beta1, float beta2, int world, void* stream);
+int sir_train_state_end(void* d_state, const float* d_found_inf, uint64_t dropout_offset_increment, void* stream);
+int sir_model_set_train_state(sir_model* m, const void* d_state);
+int sir_cross_entropy_state(const float* d_logits, const int64_t* d_labels, int batch, int num_classes, const void* d_state,
+                            float* d_loss, float* d_dlogits, void* stream);
+int sir_adam_step_state(float* d_params, const float* d_grads, float* d_exp_avg, float* d_exp_avg_sq, const int64_t* segments,
+                        int n_segments, float lr, float beta1, float beta2, float eps, float weight_decay, const void* d_state,
+                        const float* d_found_inf, void* stream);
+
 /* sir_pipeline_forward: frontend (SIR_OUT_LOGMEL_NORM, pad/trim to out_frames) + classifier in one call.
  * d_features [batch, n_mels, out_frames] is required (the classifier reads the features from it). */
 int sir_pipeline_forward(sir_frontend* fe, sir_model* m, const float* d_wave, int64_t wave_stride,

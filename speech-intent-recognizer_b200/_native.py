@@ -59,6 +59,14 @@ SIGNATURES = {
     "sir_grad_nonfinite": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "sir_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int, c_float, c_float, c_float,
                               c_float, c_float, c_int, c_float, c_void_p, c_void_p]),
+    "sir_train_state_init": (c_int, [c_void_p, c_float, c_int, c_uint64, c_void_p]),
+    "sir_train_state_set_scale": (c_int, [c_void_p, c_float, c_void_p]),
+    "sir_train_state_begin": (c_int, [c_void_p, c_float, c_float, c_int, c_void_p]),
+    "sir_train_state_end": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
+    "sir_model_set_train_state": (c_int, [c_void_p, c_void_p]),
+    "sir_cross_entropy_state": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sir_adam_step_state": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int, c_float, c_float, c_float,
+                                    c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "sir_gemm_nt_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "sir_conv3x3_nhwc_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sir_pipeline_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
@@ -301,8 +309,14 @@ class Model:
         return logits
 
     # -- training step pieces (flat fp32 parameter / gradient buffers owned by the caller) ---------------------
+    def set_train_state(self, state: "TrainState" = None):
+        """Read the dropout stream position from a device-resident ``TrainState`` (None: from the ``offset`` argument)."""
+        self._train_state = state                                     # keeps the device buffer alive
+        check(load_library().sir_model_set_train_state(self._h, ptr(state.buf) if state is not None else None),
+              "sir_model_set_train_state")
+
     def train_forward(self, flat_params: torch.Tensor, feat: torch.Tensor, dropout_keep: torch.Tensor = None, seed: int = 0,
-                      offset: int = 0, bn_momentum: float = 0.1, bn_eps: float = 1e-5) -> torch.Tensor:
+                      offset: int = 0, bn_momentum: float = 0.1, bn_eps: float = 1e-5, logits: torch.Tensor = None) -> torch.Tensor:
         """Train-mode forward; ``feat`` (contiguous, CUDA) must stay alive until ``backward``."""
         require_cuda(flat_params, "flat_params")
         require_cuda(feat, "features")
@@ -311,7 +325,8 @@ class Model:
         if dropout_keep is not None:
             require_cuda(dropout_keep, "dropout_keep", torch.uint8)
             assert dropout_keep.is_contiguous() and dropout_keep.numel() == B * (T // 8) * 512
-        logits = torch.empty((B, self.num_classes), device=feat.device, dtype=torch.float32)
+        if logits is None:
+            logits = torch.empty((B, self.num_classes), device=feat.device, dtype=torch.float32)
         check(load_library().sir_model_train_forward(self._h, ptr(flat_params), ptr(feat), B, T, ptr(dropout_keep), int(seed),
                                                      int(offset), float(bn_momentum), float(bn_eps), ptr(logits),
                                                      stream_ptr()), "sir_model_train_forward")
@@ -369,6 +384,51 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, segments, lr, betas=(0.9, 0.99
     check(load_library().sir_adam_step(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), seg, len(segments), float(lr),
                                        float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
                                        float(inv_scale), ptr(found_inf), stream_ptr()), "sir_adam_step")
+
+
+TRAIN_STATE_BYTES = 32
+
+
+class TrainState:
+    """Device-resident per-step scalars of the training step (include/sir_b200.h "device-resident step state"): Adam step
+    count and bias corrections, GradScaler scale, dropout stream position.  With it the step takes no per-step host
+    argument, i.e. it can be captured in a CUDA graph once and replayed."""
+
+    def __init__(self, loss_scale: float = 65536.0, step: int = 0, dropout_offset: int = 0):
+        self.buf = torch.zeros(TRAIN_STATE_BYTES // 4, dtype=torch.int32, device="cuda")
+        check(load_library().sir_train_state_init(ptr(self.buf), float(loss_scale), int(step), int(dropout_offset), stream_ptr()),
+              "sir_train_state_init")
+
+    def set_scale(self, loss_scale: float):
+        check(load_library().sir_train_state_set_scale(ptr(self.buf), float(loss_scale), stream_ptr()), "sir_train_state_set_scale")
+
+    def begin(self, betas, world: int):
+        check(load_library().sir_train_state_begin(ptr(self.buf), float(betas[0]), float(betas[1]), int(world), stream_ptr()),
+              "sir_train_state_begin")
+
+    def end(self, found_inf: torch.Tensor, dropout_offset_increment: int):
+        check(load_library().sir_train_state_end(ptr(self.buf), ptr(found_inf), int(dropout_offset_increment), stream_ptr()),
+              "sir_train_state_end")
+
+    def read(self):
+        """(step, loss_scale, dropout_offset) - synchronises; for tests and checkpoints."""
+        raw = self.buf.cpu().numpy()
+        return int(raw[2]), float(raw[4:5].view("float32")[0]), int(raw[0:2].view("uint64")[0])
+
+
+def cross_entropy_state(logits: torch.Tensor, labels: torch.Tensor, state: TrainState, loss_out: torch.Tensor, dlogits: torch.Tensor):
+    require_cuda(logits, "logits")
+    require_cuda(labels, "labels", torch.int64)
+    B, C = logits.shape
+    check(load_library().sir_cross_entropy_state(ptr(logits), ptr(labels), B, C, ptr(state.buf), ptr(loss_out), ptr(dlogits),
+                                                 stream_ptr()), "sir_cross_entropy_state")
+
+
+def adam_step_state(params, grads, exp_avg, exp_avg_sq, segments, lr, betas, eps, weight_decay, state: TrainState, found_inf):
+    seg = (c_int64 * (2 * len(segments)))(*[int(v) for pair in segments for v in pair])
+    check(load_library().sir_adam_step_state(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), seg, len(segments), float(lr),
+                                             float(betas[0]), float(betas[1]), float(eps), float(weight_decay), ptr(state.buf),
+                                             ptr(found_inf), stream_ptr()), "sir_adam_step_state")
 
 
 def conv3x3_nhwc_split_f16(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:

@@ -453,18 +453,33 @@ __global__ void __cluster_dims__(kGtCluster, 1, 1) __launch_bounds__(PpLayout<NC
             const int k = j0 + 8 * ug, kb = k >> 6, chunk = (k & 63) >> 3;
             chunk_off = (uint32_t)(kb * (NB * 128) + (ui >> 3) * 1024 + (ui & 7) * 128 + ((chunk ^ (ui & 7)) << 4));
         }
+        // gate pre-activations of the input projection, requested ONE STEP AHEAD: the loads of step s + 1 fly during the whole
+        // of step s (issued at the top of the step they belong to, they were still in flight when the MMAs had finished)
+        const float* gbase = gi + (int64_t)(uvalid ? ubb : B - 1) * T * 1536 + dir * 768 + j0 + 8 * ug;
+        float4 gnext[3][2];
+        {
+            const float4* gp = reinterpret_cast<const float4*>(gbase + (int64_t)(dir == 0 ? 0 : T - 1) * 1536);
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                gnext[g][0] = __ldg(gp + g * 64);
+                gnext[g][1] = __ldg(gp + g * 64 + 1);
+            }
+        }
         for (int s = 0; s < T; ++s) {
             const int t = dir == 0 ? s : T - 1 - s;
             const int nxt = (s & 1) ^ 1;
-            // gate pre-activations of the input projection (consumed after the MMA: the loads overlap it)
             float4 gin[3][2];
-            {
-                const float4* gp = reinterpret_cast<const float4*>(
-                    gi + ((int64_t)(uvalid ? ubb : B - 1) * T + t) * 1536 + dir * 768 + j0 + 8 * ug);
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                gin[g][0] = gnext[g][0];
+                gin[g][1] = gnext[g][1];
+            }
+            if (s + 1 < T) {
+                const float4* gp = reinterpret_cast<const float4*>(gbase + (int64_t)(dir == 0 ? s + 1 : T - 2 - s) * 1536);
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
-                    gin[g][0] = __ldg(gp + g * 64);
-                    gin[g][1] = __ldg(gp + g * 64 + 1);
+                    gnext[g][0] = __ldg(gp + g * 64);
+                    gnext[g][1] = __ldg(gp + g * 64 + 1);
                 }
             }
             if (s > 0) {

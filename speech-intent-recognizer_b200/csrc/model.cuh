@@ -109,6 +109,7 @@ struct sir_model {
     __half *whh_hi[2] = {nullptr, nullptr}, *whh_lo[2] = {nullptr, nullptr};
     sir::TrainSaved ts;
     bool have_saved = false;
+    const void* train_state = nullptr;       // device TrainState (train.cu): the dropout offset comes from it when set
     int num_sms = 148;
 };
 

@@ -158,11 +158,37 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const float* __re
     }
 }
 
+// Per-step scalars of the training step, DEVICE resident (sir_train_state_*): with them the whole step - forward, loss,
+// backward, inf/nan flag, Adam - takes no host value that changes from step to step, so it can be captured ONCE in a CUDA
+// graph and replayed (the 62 launches of a batch-16 step cost more host time than device time otherwise).
+struct TrainState {
+    unsigned long long dropout_offset;         // Philox offset of the GRU dropout (advances every step)
+    int step;                                  // successful Adam steps so far (a skipped step does not count, as in torch)
+    int pad;
+    float loss_scale;                          // GradScaler scale (the host changes it on growth / back-off)
+    float inv_scale;                           // 1 / (loss_scale * world)
+    float bc1, bc2_sqrt;                       // Adam bias corrections of step + 1
+};
+static_assert(sizeof(TrainState) == 32, "sir_b200.h documents 32 bytes");
+
+__global__ void train_state_begin_kernel(TrainState* st, float beta1, float beta2, float inv_world) {
+    const double n = (double)(st->step + 1);
+    st->bc1 = (float)(1.0 - pow((double)beta1, n));
+    st->bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, n));
+    st->inv_scale = inv_world / st->loss_scale;
+}
+__global__ void train_state_end_kernel(TrainState* st, const float* __restrict__ found_inf, unsigned long long offset_inc) {
+    if (!found_inf || *found_inf == 0.f) st->step += 1;
+    st->dropout_offset += offset_inc;
+}
+
 // Inter-layer GRU dropout (train mode): y * keep / (1 - p); keep comes from the caller's mask or from Philox.
 __global__ void gru_dropout_kernel(const float* __restrict__ y, int64_t n, const uint8_t* __restrict__ keep_in,
-                                   uint64_t seed, uint64_t offset, uint8_t* __restrict__ keep_out, float* __restrict__ yd,
+                                   uint64_t seed, uint64_t offset, const TrainState* __restrict__ state,
+                                   uint8_t* __restrict__ keep_out, float* __restrict__ yd,
                                    __half* __restrict__ yd_hi, __half* __restrict__ yd_lo) {
     const float scale = 1.f / (1.f - kDropoutP);
+    if (state) offset = state->dropout_offset;
     for (int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i4 < n; i4 += (int64_t)gridDim.x * blockDim.x * 4) {
         uint32_t r[4] = {0, 0, 0, 0};
         if (!keep_in) philox4x32_10(seed, offset + (uint64_t)(i4 >> 2), 0x44524F50u, r);
@@ -191,9 +217,10 @@ __global__ void gru_dropout_kernel(const float* __restrict__ y, int64_t n, const
 // denominator; any other label outside [0, C) is an error - torch raises a device assert, here the row is masked and the
 // loss comes back NaN so that the caller's per-step loss read-back (scripts/train.py:112-116) sees it.
 __global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
-                                                            int B, int C, float scale, float* __restrict__ loss,
-                                                            float* __restrict__ dlogits) {
+                                                            int B, int C, float scale, const TrainState* __restrict__ state,
+                                                            float* __restrict__ loss, float* __restrict__ dlogits) {
     __shared__ float s_part[8];
+    if (state) scale = state->loss_scale;
     __shared__ int s_valid, s_bad;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) s_valid = s_bad = 0;
@@ -879,8 +906,13 @@ struct AdamSegments {
 // inf/nan skip: g = grad * inv_scale + wd * p.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             AdamSegments seg, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
-                            float inv_scale, const float* __restrict__ found_inf) {
+                            float inv_scale, const float* __restrict__ found_inf, const TrainState* __restrict__ state) {
     if (found_inf && *found_inf != 0.f) return;
+    if (state) {
+        bc1 = state->bc1;
+        bc2_sqrt = state->bc2_sqrt;
+        inv_scale = state->inv_scale;
+    }
     int64_t total = 0;
     for (int s = 0; s < seg.n; ++s) total += seg.count[s];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1152,7 +1184,8 @@ extern "C" int sir_model_train_forward(sir_model* m, float* d_params, const floa
     if ((rc = tc::gru_layer_tc(m->whh_hi[0], m->whh_lo[0], t.gi[0], m->bhh[0], t.y[0], t.ytmp_hi, t.ytmp_lo, B, T, st)))
         return rc;
     gru_dropout_kernel<<<blocks_for((int64_t)BT * 512 / 4), 256, 0, st>>>(t.y[0], (int64_t)BT * 512, d_dropout_keep, seed, offset,
-                                                                         t.keep, t.y0d, t.y0d_hi, t.y0d_lo);
+                                                                         (const TrainState*)m->train_state, t.keep, t.y0d,
+                                                                         t.y0d_hi, t.y0d_lo);
     SIR_CHECK_LAUNCH("gru_dropout_kernel");
     // layer 1
     if ((rc = tc::tc_gemm_nt(t.y0d_hi, t.y0d_lo, m->wih_hi[1], m->wih_lo[1], m->bih[1], t.gi[1], BT, 1536, 512, st,
@@ -1233,8 +1266,59 @@ extern "C" int sir_cross_entropy(const float* d_logits, const int64_t* d_labels,
                                  float* d_loss, float* d_dlogits, void* stream) {
     if (!d_logits || !d_labels || !d_loss || batch < 1 || num_classes < 1)
         return fail(SIR_ERR_INVALID, "sir_cross_entropy: bad arguments");
-    cross_entropy_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_logits, d_labels, batch, num_classes, scale, d_loss, d_dlogits);
+    cross_entropy_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_logits, d_labels, batch, num_classes, scale, nullptr, d_loss, d_dlogits);
     SIR_CHECK_LAUNCH("cross_entropy_kernel");
+    return SIR_OK;
+}
+
+extern "C" int sir_cross_entropy_state(const float* d_logits, const int64_t* d_labels, int batch, int num_classes,
+                                       const void* d_state, float* d_loss, float* d_dlogits, void* stream) {
+    if (!d_logits || !d_labels || !d_loss || !d_state || batch < 1 || num_classes < 1)
+        return fail(SIR_ERR_INVALID, "sir_cross_entropy_state: bad arguments");
+    cross_entropy_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_logits, d_labels, batch, num_classes, 1.f, (const TrainState*)d_state,
+                                                              d_loss, d_dlogits);
+    SIR_CHECK_LAUNCH("cross_entropy_kernel");
+    return SIR_OK;
+}
+
+extern "C" int sir_train_state_init(void* d_state, float loss_scale, int step, uint64_t dropout_offset, void* stream) {
+    if (!d_state || !(loss_scale > 0.f) || step < 0) return fail(SIR_ERR_INVALID, "sir_train_state_init: bad arguments");
+    TrainState h{};
+    h.dropout_offset = dropout_offset;
+    h.step = step;
+    h.loss_scale = loss_scale;
+    h.inv_scale = 1.f / loss_scale;
+    h.bc1 = h.bc2_sqrt = 1.f;
+    SIR_CUDA(cudaMemcpyAsync(d_state, &h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    SIR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));     // h goes out of scope
+    return SIR_OK;
+}
+
+extern "C" int sir_train_state_set_scale(void* d_state, float loss_scale, void* stream) {
+    if (!d_state || !(loss_scale > 0.f)) return fail(SIR_ERR_INVALID, "sir_train_state_set_scale: bad arguments");
+    SIR_CUDA(cudaMemcpyAsync((char*)d_state + offsetof(TrainState, loss_scale), &loss_scale, sizeof(float), cudaMemcpyHostToDevice,
+                             (cudaStream_t)stream));
+    SIR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return SIR_OK;
+}
+
+extern "C" int sir_train_state_begin(void* d_state, float beta1, float beta2, int world, void* stream) {
+    if (!d_state || world < 1) return fail(SIR_ERR_INVALID, "sir_train_state_begin: bad arguments");
+    train_state_begin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((TrainState*)d_state, beta1, beta2, 1.f / (float)world);
+    SIR_CHECK_LAUNCH("train_state_begin_kernel");
+    return SIR_OK;
+}
+
+extern "C" int sir_train_state_end(void* d_state, const float* d_found_inf, uint64_t dropout_offset_increment, void* stream) {
+    if (!d_state) return fail(SIR_ERR_INVALID, "sir_train_state_end: bad arguments");
+    train_state_end_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((TrainState*)d_state, d_found_inf, dropout_offset_increment);
+    SIR_CHECK_LAUNCH("train_state_end_kernel");
+    return SIR_OK;
+}
+
+extern "C" int sir_model_set_train_state(sir_model* m, const void* d_state) {
+    if (!m) return fail(SIR_ERR_INVALID, "sir_model_set_train_state: NULL handle");
+    m->train_state = d_state;
     return SIR_OK;
 }
 
@@ -1246,10 +1330,10 @@ extern "C" int sir_grad_nonfinite(const float* d_grads, int64_t count, float* d_
     return SIR_OK;
 }
 
-extern "C" int sir_adam_step(float* d_params, const float* d_grads, float* d_exp_avg, float* d_exp_avg_sq,
+static int adam_launch(float* d_params, const float* d_grads, float* d_exp_avg, float* d_exp_avg_sq,
                              const int64_t* segments, int n_segments, float lr, float beta1, float beta2, float eps,
-                             float weight_decay, int step, float inv_scale, const float* d_found_inf, void* stream) {
-    if (!d_params || !d_grads || !d_exp_avg || !d_exp_avg_sq || !segments || n_segments < 1 || n_segments > 4 || step < 1)
+                             float weight_decay, int step, float inv_scale, const float* d_found_inf, const void* d_state, void* stream) {
+    if (!d_params || !d_grads || !d_exp_avg || !d_exp_avg_sq || !segments || n_segments < 1 || n_segments > 4 || (step < 1 && !d_state))
         return fail(SIR_ERR_INVALID, "sir_adam_step: bad arguments");
     AdamSegments seg{};
     seg.n = n_segments;
@@ -1265,7 +1349,22 @@ extern "C" int sir_adam_step(float* d_params, const float* d_grads, float* d_exp
     const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
     const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     adam_kernel<<<blocks_for(total, 256 * 4, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
-        d_params, d_grads, d_exp_avg, d_exp_avg_sq, seg, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, inv_scale, d_found_inf);
+        d_params, d_grads, d_exp_avg, d_exp_avg_sq, seg, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, inv_scale, d_found_inf, (const TrainState*)d_state);
     SIR_CHECK_LAUNCH("adam_kernel");
     return SIR_OK;
+}
+
+extern "C" int sir_adam_step(float* d_params, const float* d_grads, float* d_exp_avg, float* d_exp_avg_sq,
+                             const int64_t* segments, int n_segments, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, int step, float inv_scale, const float* d_found_inf, void* stream) {
+    return adam_launch(d_params, d_grads, d_exp_avg, d_exp_avg_sq, segments, n_segments, lr, beta1, beta2, eps, weight_decay, step,
+                       inv_scale, d_found_inf, nullptr, stream);
+}
+
+extern "C" int sir_adam_step_state(float* d_params, const float* d_grads, float* d_exp_avg, float* d_exp_avg_sq,
+                                   const int64_t* segments, int n_segments, float lr, float beta1, float beta2, float eps,
+                                   float weight_decay, const void* d_state, const float* d_found_inf, void* stream) {
+    if (!d_state) return fail(SIR_ERR_INVALID, "sir_adam_step_state: NULL state");
+    return adam_launch(d_params, d_grads, d_exp_avg, d_exp_avg_sq, segments, n_segments, lr, beta1, beta2, eps, weight_decay, 1, 1.f,
+                       d_found_inf, d_state, stream);
 }

@@ -150,7 +150,7 @@ class DataParallelTrainer:
     """
 
     def __init__(self, model, lr=5e-5, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, use_amp=True, process_group=None,
-                 seed=0):
+                 seed=0, use_graph=False):
         import torch.distributed as dist
         self.model = model
         self.group = process_group
@@ -174,16 +174,114 @@ class DataParallelTrainer:
         self.skipped_steps = 0
         self._scalars = torch.zeros(2, device="cuda", dtype=torch.float32)        # [loss, found_inf]
         self._host_scalars = torch.zeros(2, dtype=torch.float32).pin_memory()
+        # use_graph: the step's per-step scalars live on the device (``_native.TrainState``) and the launches before / after
+        # the all-reduce are captured ONCE as two CUDA graphs and replayed - at batch 16 the ~60 launches of a step cost more
+        # host time than device time.  Built lazily for the first (batch, frames) shape; other shapes run eagerly.
+        self.use_graph = bool(use_graph)
+        self._graph = None
         # optional device timing of the collective (bench.py): CUDA events around the all-reduce of every step
         self.time_collective = False
         self.collective_ms = []
         self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+
+    # -- CUDA-graph path ------------------------------------------------------------------------------------------------
+    def _graph_body_pre(self, g):
+        m = self.model
+        g["state"].begin(self.betas, self.world)
+        m._flat_grad[self.n:].zero_()
+        m._native_model.train_forward(m._flat, g["feats"], seed=m.dropout_seed, bn_momentum=m.bn1.momentum, bn_eps=m.bn1.eps,
+                                      logits=g["logits"])
+        _native.cross_entropy_state(g["logits"], g["labels"], g["state"], self._scalars[0:1], g["dlogits"])
+        m._native_model.backward(m._flat, g["dlogits"], m._flat_grad)
+        _native.grad_nonfinite(m._flat_grad, self.n, m._flat_grad[self.n:])
+
+    def _graph_body_post(self, g):
+        m = self.model
+        _native.adam_step_state(m._flat, m._flat_grad, self.exp_avg, self.exp_avg_sq, self.segments, self.lr, self.betas, self.eps,
+                                self.weight_decay, g["state"], m._flat_grad[self.n:])
+        g["state"].end(m._flat_grad[self.n:], g["offset_inc"])
+        self._scalars[1:2].copy_(m._flat_grad[self.n:])
+        self._host_scalars.copy_(self._scalars, non_blocking=True)
+
+    def _build_graph(self, B, n_mels, T):
+        import torch.distributed as dist
+        m = self.model
+        self.world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        g = {"key": (B, T), "offset_inc": (B * (T // 8) * 512 + 3) // 4,
+             "state": _native.TrainState(self.scaler.scale, self.adam_steps, m._dropout_offset),
+             "feats": torch.zeros((B, n_mels, T), device="cuda"), "labels": torch.zeros(B, device="cuda", dtype=torch.int64),
+             "logits": torch.zeros((B, m.num_classes), device="cuda"), "dlogits": torch.zeros((B, m.num_classes), device="cuda")}
+        m._native_model.set_train_state(g["state"])
+        # a warm-up pass outside capture sizes every workspace and opts the kernels in; it must not change the training state:
+        # parameters, moments, running statistics and the step state are restored afterwards
+        saved = (m._flat.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), g["state"].buf.clone())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._graph_body_pre(g)
+            self._graph_body_post(g)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        m._flat.copy_(saved[0]); self.exp_avg.copy_(saved[1]); self.exp_avg_sq.copy_(saved[2]); g["state"].buf.copy_(saved[3])
+        before = _native.launch_count()
+        g["pre"], g["post"] = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g["pre"]):
+            self._graph_body_pre(g)
+        with torch.cuda.graph(g["post"], pool=g["pre"].pool()):
+            self._graph_body_post(g)
+        g["launches"] = _native.launch_count() - before          # kernels of libsir_b200 inside one replay of both graphs
+        self._graph = g
+
+    def _step_graph(self, feats, label) -> float:
+        m, g = self.model, self._graph
+        g["feats"].copy_(feats, non_blocking=True)
+        g["labels"].copy_(label, non_blocking=True)
+        g["pre"].replay()
+        if self.time_collective:
+            self._ev[0].record()
+        sync_flat_gradients(m._flat_grad, self.group)
+        if self.time_collective:
+            self._ev[1].record()
+        g["post"].replay()
+        torch.cuda.current_stream().synchronize()                 # the reference reads loss.item() every step
+        m._dropout_offset += g["offset_inc"]
+        m._native_dirty = True
+        m._train_generation += 1
+        self.graph_replays = getattr(self, "graph_replays", 0) + 1
+        return self._finish_step()
+
+    def _finish_step(self) -> float:
+        loss, found_inf = float(self._host_scalars[0]), bool(self._host_scalars[1] != 0)
+        if self.time_collective:
+            self.collective_ms.append(self._ev[0].elapsed_time(self._ev[1]))
+        if found_inf:
+            self.skipped_steps += 1
+        else:
+            self.adam_steps += 1
+        old_scale = self.scaler.scale
+        self.scaler.update(found_inf)
+        if self._graph is not None and self.scaler.scale != old_scale:
+            self._graph["state"].set_scale(self.scaler.scale)     # GradScaler growth / back-off between replays
+        with torch.no_grad():
+            for bn in (self.model.bn1, self.model.bn2, self.model.bn3):
+                bn.num_batches_tracked += 1
+        return loss
 
     def step(self, mel: torch.Tensor, label: torch.Tensor, dropout_keep: torch.Tensor = None) -> float:
         m = self.model
         m.train()
         feats = m._check_input(mel).to(device="cuda", dtype=torch.float32).contiguous()
         label = label.to(device="cuda", dtype=torch.int64)
+        if self.use_graph and dropout_keep is None:
+            if self._graph is None:
+                self._build_graph(feats.shape[0], feats.shape[1], feats.shape[2])
+            if self._graph["key"] == (feats.shape[0], feats.shape[2]):
+                return self._step_graph(feats, label)
+        if self._graph is not None:
+            # an eager step between replays: move the device state's counters over to the host arguments and back afterwards
+            step_d, _, off_d = self._graph["state"].read()
+            m._dropout_offset = off_d
+            m._native_model.set_train_state(None)
         flat, grads = m.flatten_parameters_(), m._flat_grad
         B, _, T = feats.shape
         logits = m._native_model.train_forward(flat, feats, dropout_keep=dropout_keep, seed=m.dropout_seed,
@@ -206,15 +304,9 @@ class DataParallelTrainer:
         self._scalars[1:2].copy_(grads[self.n:])
         self._host_scalars.copy_(self._scalars, non_blocking=True)
         torch.cuda.current_stream().synchronize()                 # the reference reads loss.item() every step
-        loss, found_inf = float(self._host_scalars[0]), bool(self._host_scalars[1] != 0)
-        if self.time_collective:
-            self.collective_ms.append(self._ev[0].elapsed_time(self._ev[1]))
-        if found_inf:
-            self.skipped_steps += 1
-        else:
-            self.adam_steps += 1
-        self.scaler.update(found_inf)
-        with torch.no_grad():
-            for bn in (m.bn1, m.bn2, m.bn3):
-                bn.num_batches_tracked += 1
+        loss = self._finish_step()
+        if self._graph is not None:                               # hand the counters back to the device state
+            g = self._graph
+            g["state"] = _native.TrainState(self.scaler.scale, self.adam_steps, m._dropout_offset)
+            self._graph = None                                    # (the graphs captured the old state buffer: rebuild lazily)
         return loss

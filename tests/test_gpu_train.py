@@ -207,3 +207,37 @@ def test_data_parallel_two_gpus_equals_one_big_batch_of_gradients():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "dp_check ok" in out.stdout
+
+
+def test_graph_replayed_step_equals_eager_step():
+    """``DataParallelTrainer(use_graph=True)``: the step captured once as two CUDA graphs (device-resident step state: Adam
+    step count / bias corrections, loss scale, dropout stream position) and replayed == the eager step over several batches,
+    through a skipped (non-finite) step and a loss-scale back-off."""
+    x, labels = train_inputs(seed=21, batch=16 * 5)
+    xs = [torch.from_numpy(x[16 * i:16 * (i + 1)]).cuda() for i in range(5)]
+    ys = [torch.from_numpy(labels[16 * i:16 * (i + 1)]).cuda() for i in range(5)]
+    results = []
+    for use_graph in (False, True):
+        model, _ = make_model(1234)
+        tr = train.DataParallelTrainer(model, lr=1e-3, weight_decay=1e-4, use_amp=True, seed=3, use_graph=use_graph)
+        losses = [tr.step(xs[i], ys[i]) for i in range(3)]
+        bad = xs[3].clone()
+        bad[0, 0, 0] = float("inf")
+        before = model._flat.clone()
+        losses.append(tr.step(bad, ys[3]))                                  # every rank skips; the scale backs off
+        for o, k in model.param_segments():
+            assert torch.equal(model._flat[o:o + k], before[o:o + k]), "a skipped step changed parameters"
+        assert tr.skipped_steps == 1 and tr.adam_steps == 3 and tr.scaler.scale == 32768.0
+        losses.append(tr.step(xs[4], ys[4]))
+        if use_graph:
+            assert tr._graph is not None and tr.graph_replays == 5 and tr._graph["launches"] > 20
+            step_d, scale_d, off_d = tr._graph["state"].read()
+            assert step_d == 4 and scale_d == 32768.0 and off_d == model._dropout_offset
+        results.append((losses, model._flat.clone(), tr.exp_avg.clone(), tr.exp_avg_sq.clone()))
+    (l0, p0, m0, v0), (l1, p1, m1, v1) = results
+    # same kernels in the same order; the only difference is WHERE the Adam bias corrections are evaluated (host libm pow vs
+    # device pow, both in double): the last bit of 1 - beta^step may differ, i.e. ~1e-7 relative on the update
+    assert np.allclose(l0[:3], l1[:3], rtol=1e-5) and np.isfinite(l0[4]) and abs(l0[4] - l1[4]) < 1e-4 * abs(l0[4])
+    assert torch.equal(m0, m1) or torch.allclose(m0, m1, rtol=1e-5, atol=1e-9)
+    assert torch.allclose(v0, v1, rtol=1e-5, atol=1e-12)
+    assert float((p0 - p1).abs().max()) < 1e-6
