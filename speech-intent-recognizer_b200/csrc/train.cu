@@ -879,19 +879,33 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
 }
 
 // dW[(co * CIN + ci) * 9 + tap] = sum_chunk partial[chunk][tap][co][ci]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int cin, int cout, float* __restrict__ dw) {
+// A block owns 32 consecutive elements; its 8 warps split the chunks (warp w: chunks w, w + 8, ... with four independent
+// accumulators, so ~32 loads are in flight per thread instead of a dependent chain over up to 592 chunks), then the eight
+// partial sums are added in warp order: the summation order is fixed, the result deterministic.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int cin, int cout,
+                                                           float* __restrict__ dw) {
+    __shared__ float s_part[8][33];
     const int n = 9 * cin * cout;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float a0 = 0.f, a1 = 0.f;
-    int c = 0;
-    for (; c + 1 < chunks; c += 2) {
-        a0 += partial[(int64_t)c * n + i];
-        a1 += partial[(int64_t)(c + 1) * n + i];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    if (i < n) {
+        int c = w;
+        for (; c + 24 < chunks; c += 32) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] += partial[(int64_t)(c + 8 * u) * n + i];
+        }
+        for (int u = 0; c < chunks; c += 8, ++u) a[u & 3] += partial[(int64_t)c * n + i];
     }
-    if (c < chunks) a0 += partial[(int64_t)c * n + i];
-    const int ci = i % cin, co = (i / cin) % cout, tap = i / (cin * cout);
-    dw[((int64_t)co * cin + ci) * 9 + tap] = a0 + a1;
+    s_part[w][lane] = (a[0] + a[1]) + (a[2] + a[3]);
+    __syncthreads();
+    if (w == 0 && i < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += s_part[k][lane];
+        const int ci = i % cin, co = (i / cin) % cout, tap = i / (cin * cout);
+        dw[((int64_t)co * cin + ci) * 9 + tap] = t;
+    }
 }
 
 // =========================================================================================================
@@ -1073,7 +1087,7 @@ static int conv_wgrad(const float* dz, const float* a, int B, int H, int W, floa
     const int chunks = (int)((rows + rpc - 1) / rpc);
     conv_wgrad_kernel<CIN, COUT><<<dim3(9, (unsigned)chunks), 256, 0, st>>>(dz, a, B, H, W, rpc, partial);
     SIR_CHECK_LAUNCH("conv_wgrad_kernel");
-    wgrad_reduce_kernel<<<(9 * CIN * COUT + 255) / 256, 256, 0, st>>>(partial, chunks, CIN, COUT, dw);
+    wgrad_reduce_kernel<<<(9 * CIN * COUT + 31) / 32, 256, 0, st>>>(partial, chunks, CIN, COUT, dw);
     SIR_CHECK_LAUNCH("wgrad_reduce_kernel");
     return SIR_OK;
 }
@@ -1254,7 +1268,7 @@ extern "C" int sir_model_backward(sir_model* m, const float* d_params, const flo
         const int nblk = (int)((int64_t)B * H < 592 ? (int64_t)B * H : 592);
         conv1_wgrad_kernel<<<nblk, 256, 0, st>>>(t.dz, t.feat, B, H, W, t.wg_partial);
         SIR_CHECK_LAUNCH("conv1_wgrad_kernel");
-        wgrad_reduce_kernel<<<2, 256, 0, st>>>(t.wg_partial, nblk, 1, 32, d_grads + o.conv_w[0]);
+        wgrad_reduce_kernel<<<(9 * 32 + 31) / 32, 256, 0, st>>>(t.wg_partial, nblk, 1, 32, d_grads + o.conv_w[0]);
         SIR_CHECK_LAUNCH("wgrad_reduce_kernel");
     }
     // the backward reduce/apply pair leaves its accumulators dirty (apply reads them): clear for the next step
