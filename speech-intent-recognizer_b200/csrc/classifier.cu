@@ -15,6 +15,7 @@
 // fp16 (hi, lo) pair - the same 4 bytes per value as fp32.  conv1 (K = 9), the GRU recurrence and the
 // attention/fc head stay on the fp32 CUDA cores.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -483,11 +484,17 @@ int model_forward_convs(sir_model* m, const Workspace& ws, const float* feat, in
     const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2, Tg = W4 / 2;
     const size_t o1 = (size_t)first * H2 * W2 * 32, o2 = (size_t)first * H4 * W4 * 64, o3 = (size_t)first * Tg * m->gru_in;
     int rc;
-    {
+    static const bool conv1_cuda_cores = [] {                // SIR_CONV1_KERNEL=cuda: round 1's fp32 kernel (A/B measurements)
+        const char* v = getenv("SIR_CONV1_KERNEL");
+        return v && (v[0] == 'c' || v[0] == 'C');
+    }();
+    if (conv1_cuda_cores) {
         dim3 grid((unsigned)((H2 * W2 + 127) / 128), (unsigned)count);
         ProfScope ps("conv1_bn_relu_pool", st);
         conv1_bn_relu_pool_kernel<<<grid, 128, 0, st>>>(feat, m->w1, m->sh1, ws.act1_hi + o1, ws.act1_lo + o1, H, W);
         SIR_CHECK_LAUNCH("conv1_bn_relu_pool_kernel");
+    } else if ((rc = tc::conv1_tc(feat, m->w1, m->sh1, ws.act1_hi + o1, ws.act1_lo + o1, count, H, W, m->num_sms, st))) {
+        return rc;
     }
     if ((rc = tc::tc_conv3x3_persistent<32, 64>(ws.act1_hi + o1, ws.act1_lo + o1, m->w2_hi, m->w2_lo, m->sh2, ws.act2_hi + o2,
                                                 ws.act2_lo + o2, count, H2, W2, m->num_sms, st, "conv2_bn_relu_pool", ws.tickets)))

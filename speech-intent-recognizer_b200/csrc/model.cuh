@@ -131,6 +131,9 @@ int tc_conv3x3_stream(const __half* in_hi, const __half* in_lo, const __half* w_
                       __half* out_hi, __half* out_lo, int B, int H, int W, int out_whc, int num_sms, cudaStream_t st,
                       const char* name, TicketSource* tickets = nullptr);
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint32_t* box);
+// conv1 (C_in = 1) + folded BN + ReLU + 2x2 max-pool on tcgen05 (conv1_tc.cu): feat [B,H,W] fp32 -> [B,H/2,W/2,32] fp16 (hi, lo)
+int conv1_tc(const float* feat, const float* w1, const float* shift1, __half* out_hi, __half* out_lo, int B, int H, int W,
+             int num_sms, cudaStream_t st);
 int gru_layer_tc(const __half* w_hi, const __half* w_lo, const float* gi, const float* bhh, float* y,
                  __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st);
 }  // namespace tc
