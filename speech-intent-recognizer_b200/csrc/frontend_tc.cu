@@ -803,7 +803,9 @@ constexpr int kFinThreads = 128;
 __global__ void __launch_bounds__(kFinThreads) frontend_finish_kernel(const FrontendParams p) {
     __shared__ float red[8];
     extern __shared__ float s_dct[];
+    // gridDim.y CTAs share an utterance (each merges the partials itself - a few dozen flops - and takes a slice of the rows)
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int part = blockIdx.y, parts = gridDim.y;
     int L = p.lengths ? min(p.lengths[b], p.n_samples) : p.n_samples;
     if (p.max_samples > 0) L = min(L, p.max_samples);
     if (L <= kNfft / 2) return;                                  // invalid utterance: zero-filled by the main kernel
@@ -851,14 +853,14 @@ __global__ void __launch_bounds__(kFinThreads) frontend_finish_kernel(const Fron
     if (mfcc) {
         const float floor_db = p.top_db > 0.f ? red[2] - p.top_db : -INFINITY;
         const int Tn = min(T, p.out_frames);
-        for (int idx = tid; idx < p.n_mfcc * Tn; idx += kFinThreads) {
+        for (int idx = part * kFinThreads + tid; idx < p.n_mfcc * Tn; idx += parts * kFinThreads) {
             const int c = idx / Tn, tt = idx - c * Tn;
             float acc = 0.f;
             for (int mrow = 0; mrow < p.n_mels; ++mrow)
                 acc = fmaf(fmaxf(out[(int64_t)mrow * row_stride + tt], floor_db), s_dct[mrow * p.n_mfcc + c], acc);
             final_out[(int64_t)c * p.out_frames + tt] = acc;
         }
-        for (int c = 0; c < p.n_mfcc; ++c)
+        for (int c = part; c < p.n_mfcc; c += parts)
             for (int tt = T + tid; tt < p.out_frames; tt += kFinThreads) final_out[(int64_t)c * p.out_frames + tt] = 0.f;
         return;
     }
@@ -872,9 +874,10 @@ __global__ void __launch_bounds__(kFinThreads) frontend_finish_kernel(const Fron
     }
     const bool out_vec = (p.out_frames % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
     if (out_vec) {
-        const int cols = p.out_frames >> 2, total = p.n_mels * cols;
+        const int cols = p.out_frames >> 2, all = p.n_mels * cols;
+        const int per = (all + parts - 1) / parts, total = min(all, (part + 1) * per);
         constexpr int kU = 4;
-        for (int i0 = tid; i0 < total; i0 += kU * kFinThreads) {
+        for (int i0 = part * per + tid; i0 < total; i0 += kU * kFinThreads) {
             float4 x[kU];
 #pragma unroll
             for (int u = 0; u < kU; ++u) {                      // the loads of a batch are issued before its first store
@@ -902,7 +905,7 @@ __global__ void __launch_bounds__(kFinThreads) frontend_finish_kernel(const Fron
         }
     } else {
         const int total = p.n_mels * p.out_frames;
-        for (int i = tid; i < total; i += kFinThreads) {
+        for (int i = part * kFinThreads + tid; i < total; i += parts * kFinThreads) {
             const int mrow = i / p.out_frames, tt = i - mrow * p.out_frames;
             const bool masked = (tt >= mt0 && tt < mt1) || (mrow >= mf0 && mrow < mf1);
             const float x = tt < T ? out[(int64_t)mrow * p.out_frames + tt] : 0.f;
@@ -974,7 +977,9 @@ int frontend_tc_launch(const FrontendParams& p, bool pcm16, int num_sms, cudaStr
         if (e != cudaSuccess) return fail(SIR_ERR_CUDA, "launch of logmel_frontend_tc_kernel failed: %s", cudaGetErrorString(e));
         count_launch();
         const size_t dct_bytes = p.mode == SIR_OUT_MFCC ? (size_t)p.n_mels * p.n_mfcc * sizeof(float) : 0;
-        fetc::frontend_finish_kernel<<<p.batch, fetc::kFinThreads, dct_bytes, stream>>>(p);
+        // small batches: several CTAs per utterance, so that the pass is not one wave of under-occupied SMs
+        const int parts = p.batch >= 2048 ? 1 : (p.batch >= 512 ? 2 : 4);
+        fetc::frontend_finish_kernel<<<dim3((unsigned)p.batch, (unsigned)parts), fetc::kFinThreads, dct_bytes, stream>>>(p);
     }
     return SIR_OK;
 }
