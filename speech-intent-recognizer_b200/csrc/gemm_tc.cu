@@ -35,8 +35,11 @@ struct TcParams {
     int num_kblocks;
     // GEMM
     int M, N;
-    const float* bias;
+    const float* bias;      // nullable
     float* C;
+    float* C2;              // rows >= m_split go to C2 + (m - m_split) * N (two parameter blocks out of one launch)
+    int m_split;
+    const float* out_scale; // nullable: ONE device float the product is multiplied by (inverse of an operand's split scale)
     // CONV (input dims H x W, output pooled H/2 x W/2)
     int H, W, tiles_x;
     const float* shift;
@@ -156,18 +159,26 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
         if constexpr (MODE == kModeGemm) {
             const int m = m0 + q * 32 + lane;
+            const float os = p.out_scale ? __ldg(p.out_scale) : 1.f;
+            float* row = m < p.m_split ? p.C + (int64_t)m * p.N : p.C2 + (int64_t)(m - p.m_split) * p.N;
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N; c += 32) {
                 float v[32];
                 tmem_ld_32x32(trow + c, v);
                 if (m < p.M) {
-                    float4* dst = reinterpret_cast<float4*>(p.C + (int64_t)m * p.N + n0 + c);
-                    const float4* bs = reinterpret_cast<const float4*>(p.bias + n0 + c);
+                    float4* dst = reinterpret_cast<float4*>(row + n0 + c);
+                    if (p.bias) {
+                        const float4* bs = reinterpret_cast<const float4*>(p.bias + n0 + c);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 b4 = __ldg(bs + i);
-                        dst[i] = make_float4(v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z,
-                                             v[4 * i + 3] + b4.w);
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 b4 = __ldg(bs + i);
+                            dst[i] = make_float4(fmaf(v[4 * i], os, b4.x), fmaf(v[4 * i + 1], os, b4.y),
+                                                 fmaf(v[4 * i + 2], os, b4.z), fmaf(v[4 * i + 3], os, b4.w));
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            dst[i] = make_float4(v[4 * i] * os, v[4 * i + 1] * os, v[4 * i + 2] * os, v[4 * i + 3] * os);
                     }
                 }
             }
@@ -304,6 +315,9 @@ struct GpParams {
     int M, N, num_kblocks, tiles_w, tiles_x, num_tiles;   // tiles_w: weight-row tiles (N / 128), tiles_x: activation-row tiles
     const float* bias;
     float* C;
+    float* C2;
+    int m_split;
+    const float* out_scale;
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -404,8 +418,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             tc_fence_after();
             const uint32_t trow = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
             const int n = w0 + q * 32 + lane;
-            const float bias = __ldg(p.bias + n);
-            float* __restrict__ dst = p.C + n;
+            const float bias = p.bias ? __ldg(p.bias + n) : 0.f;
+            const float os = p.out_scale ? __ldg(p.out_scale) : 1.f;
 #pragma unroll 1
             for (int c = 0; c < L::kBN; c += 16) {
                 uint32_t r[16];
@@ -420,7 +434,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int m = x0 + c + i;
-                    if (m < p.M) dst[(int64_t)m * p.N] = __uint_as_float(r[i]) + bias;     // 32 lanes -> 128 contiguous bytes
+                    if (m < p.M) {                                                         // 32 lanes -> 128 contiguous bytes
+                        float* dst = m < p.m_split ? p.C + (int64_t)m * p.N : p.C2 + (int64_t)(m - p.m_split) * p.N;
+                        dst[n] = fmaf(__uint_as_float(r[i]), os, bias);
+                    }
                 }
             }
             tc_fence_before();
@@ -437,7 +454,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 }
 
 static int tc_gemm_nt_persistent(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo, const float* bias,
-                                 float* C, int M, int N, int K, cudaStream_t st, const char* name, TicketSource* tickets) {
+                                 float* C, int M, int N, int K, cudaStream_t st, const char* name, TicketSource* tickets,
+                                 const GemmOutput* out) {
     using L = GpLayout;
     CUtensorMap tw_hi, tw_lo, tx_hi, tx_lo;
     const uint64_t xdims[2] = {(uint64_t)K, (uint64_t)M}, wdims[2] = {(uint64_t)K, (uint64_t)N};
@@ -455,6 +473,9 @@ static int tc_gemm_nt_persistent(const __half* a_hi, const __half* a_lo, const _
     p.num_tiles = p.tiles_w * p.tiles_x;
     p.bias = bias;
     p.C = C;
+    p.C2 = out && out->C2 ? out->C2 : C;
+    p.m_split = out && out->C2 ? out->m_split : M;
+    p.out_scale = out ? out->out_scale : nullptr;
     SIR_SMEM_OPTIN(gemm_persistent_kernel, L::kSmemBytes);
     const int num_sms = device_sm_count();
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
@@ -468,12 +489,12 @@ static int tc_gemm_nt_persistent(const __half* a_hi, const __half* a_lo, const _
     return SIR_OK;
 }
 
-// C[M,N] = A[M,K] W[N,K]^T + bias ; operands as fp16 hi/lo pairs.  N % 128 == 0, K % 64 == 0.
+// C[M,N] = out_scale * A[M,K] W[N,K]^T + bias ; operands as fp16 hi/lo pairs.  N % 128 == 0, K % 64 == 0.
 int tc_gemm_nt(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo, const float* bias,
-               float* C, int M, int N, int K, cudaStream_t st, const char* name, TicketSource* tickets) {
+               float* C, int M, int N, int K, cudaStream_t st, const char* name, TicketSource* tickets, const GemmOutput* out) {
     if (N % 128 || K % 64) return fail(SIR_ERR_INVALID, "tc_gemm_nt: N %% 128 and K %% 64 required (N %d, K %d)", N, K);
     if ((int64_t)((M + 175) / 176) * (N / 128) >= 32)   // enough tiles to be worth a persistent launch
-        return tc_gemm_nt_persistent(a_hi, a_lo, w_hi, w_lo, bias, C, M, N, K, st, name, tickets);
+        return tc_gemm_nt_persistent(a_hi, a_lo, w_hi, w_lo, bias, C, M, N, K, st, name, tickets, out);
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     const uint64_t adims[2] = {(uint64_t)K, (uint64_t)M}, bdims[2] = {(uint64_t)K, (uint64_t)N};
     const uint32_t abox[2] = {64, 128}, bbox[2] = {64, 128};
@@ -487,6 +508,9 @@ int tc_gemm_nt(const __half* a_hi, const __half* a_lo, const __half* w_hi, const
     p.N = N;
     p.bias = bias;
     p.C = C;
+    p.C2 = out && out->C2 ? out->C2 : C;
+    p.m_split = out && out->C2 ? out->m_split : M;
+    p.out_scale = out ? out->out_scale : nullptr;
     dim3 grid((unsigned)(N / 128), (unsigned)((M + 127) / 128));
     return launch_tc<kModeGemm, 128, 64, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, st, name);
 }
@@ -568,7 +592,7 @@ extern "C" int sir_gemm_nt_split_f16(const float* d_a, const float* d_w, const f
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = tc::split_f16_async(d_a, a_hi, a_lo, (int64_t)na, st))) return rc;
     if ((rc = tc::split_f16_async(d_w, w_hi, w_lo, (int64_t)nw, st))) return rc;
-    return tc::tc_gemm_nt(a_hi, a_lo, w_hi, w_lo, d_bias, d_c, M, N, K, st, "gemm_nt_split_f16", nullptr);
+    return tc::tc_gemm_nt(a_hi, a_lo, w_hi, w_lo, d_bias, d_c, M, N, K, st, "gemm_nt_split_f16", nullptr, nullptr);
 }
 
 // 3x3 convolution (stride 1, zero padding 1, no bias) on channels-last fp32 tensors through the same implicit-GEMM

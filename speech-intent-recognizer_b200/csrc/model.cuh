@@ -74,6 +74,8 @@ struct TrainSaved {
     // backward scratch
     float *dy, *dx, *ds, *ctx, *dgi, *dgh, *gh, *hprevf, *dz, *dact, *wg_partial;
     __half *hprev_hi, *hprev_lo, *dz_hi, *dz_lo;
+    // K-major fp16 (hi, lo) operands of the GRU gradient GEMMs (train.cu: operand_prep_kernel)
+    __half *gT_hi, *gT_lo, *gs_hi, *gs_lo, *ghT_hi, *ghT_lo, *xT_hi, *xT_lo, *hT_hi, *hT_lo, *wT_hi, *wT_lo;
     double* bn_acc;                     // [3 layers][2 (fwd, bwd)][2*128] accumulators, zero between uses
     float* amax;                        // max |dz| per data-gradient convolution + the inverse split scales
 };
@@ -117,7 +119,8 @@ namespace sir {
 
 namespace tc {
 int tc_gemm_nt(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo, const float* bias,
-               float* C, int M, int N, int K, cudaStream_t st, const char* name, TicketSource* tickets = nullptr);
+               float* C, int M, int N, int K, cudaStream_t st, const char* name, TicketSource* tickets = nullptr,
+               const GemmOutput* out = nullptr);
 template <int CIN, int COUT>
 int tc_conv3x3(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
                __half* out_hi, __half* out_lo, float* raw_out, int B, int H, int W, int out_whc, cudaStream_t st,

@@ -117,6 +117,14 @@ struct TileTickets {
 // Host view of a ticket counter: launches that share one must be stream-ordered.  first() is the launch's first
 // ticket; consumed() is called once the launch has been accepted (a failed launch draws nothing, so the host's
 // idea of the counter must not move either).
+// Optional output routing of tc_gemm_nt: rows >= m_split are written to C2 (two parameter blocks from one launch) and the
+// product is multiplied by *out_scale (a device float: the inverse of the power-of-two scale of a gradient operand).
+struct GemmOutput {
+    float* C2 = nullptr;
+    int m_split = 0;
+    const float* out_scale = nullptr;
+};
+
 struct TicketSource {
     unsigned long long* dev = nullptr;
     unsigned long long next = 0;

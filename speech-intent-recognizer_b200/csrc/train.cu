@@ -409,22 +409,51 @@ __global__ void gru_hprev_kernel(const float* __restrict__ y, int B, int T, floa
     }
 }
 
-// BPTT of one layer, both directions, ONE launch.  An 8-CTA cluster owns (direction, 16 utterances); CTA r keeps
-// W_hh[:, 32r .. 32r+32) resident in shared memory; per step every CTA turns dh of its 32 units into the gate
-// gradients, pushes them into all 8 peers through distributed shared memory, and after one cluster barrier
-// computes its slice of W_hh^T dgh for the next (earlier) time step.
-constexpr int kGbNB = 16, kGbThreads = 256, kGbCluster = 8, kGbWStride = 772;
-constexpr int kGbSmemBytes = (32 * kGbWStride + 2 * kGbNB * 768 + kGbNB * 33) * 4;
+// BPTT of one layer, both directions, ONE launch.  An 8-CTA cluster owns (direction, 16 utterances); CTA r owns the hidden
+// units [32r, 32r + 32).  Per step every CTA turns dh of its units into gate gradients (phase A), pushes them - scaled,
+// split into fp16 (hi, lo) - into all 8 peers through distributed shared memory, and after one cluster barrier computes
+// its slice of dh_prev = dgh W_hh (phase B) for the next (earlier) time step.
+// Phase B is a [16 utterances] x [768 gates] x [32 units] product per step whose W_hh operand never changes: it lives in
+// REGISTERS for the whole launch as mma.sync m16n8k16 B-fragments - warp w holds gates [96w, 96w + 96) x 32 units as fp16
+// (hi, lo): 6 k-steps x 4 n-tiles x 4 registers = 96 per thread.  (The previous version kept W_hh in shared memory and
+// every warp re-read all 98 KB of it per step: 9.7 us per step, bound by shared-memory bandwidth.)  Per step a warp loads
+// the A fragments (gate gradients of the 16 utterances) with 24 conflict-free LDS.64 and issues 72 MMAs - hi.hi, hi.lo,
+// lo.hi with fp32 accumulation, the classifier's three-pass split - and the 8 per-warp partial sums are added in a fixed
+// order by the thread that owns (utterance, unit pair) in phase A, whose dh carry never leaves its registers.
+// The pushed gradients are multiplied by a power of two that takes max |dy| of the layer to [32, 64): gate gradients are
+// bounded by |dh|, which leaves a factor 1000 of growth through the recurrence before fp16 overflows (the step is then
+// skipped like any other overflow), and keeps 22 significant bits down to 2^-9 of that maximum.
+constexpr int kGbNB = 16, kGbThreads = 256, kGbCluster = 8;
+constexpr int kGbRS = 388;      // uint2 {hi pair, lo pair} per utterance row: 384 gate pairs + 4, rows 32 bytes apart mod 128
+constexpr int kGbPS = 40;       // floats per utterance row of a warp's partial sums (same trick)
+constexpr int kGbSmemBytes = 2 * kGbNB * kGbRS * 8 + 8 * kGbNB * kGbPS * 4;
 
 __device__ __forceinline__ uint32_t gb_map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
     return r;
 }
-__device__ __forceinline__ void gb_st_cluster_v2(uint32_t addr, float a, float b) {
-    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+__device__ __forceinline__ void gb_st_cluster_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ float gb_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+// {lo 16 bits: split(a), hi 16 bits: split(b)} for the hi parts and for the lo parts
+__device__ __forceinline__ uint2 gb_split_pair(float a, float b) {
+    __half ah, al, bh, bl;
+    tc::split_f16(a, ah, al);
+    tc::split_f16(b, bh, bl);
+    return make_uint2((uint32_t)__half_as_ushort(ah) | ((uint32_t)__half_as_ushort(bh) << 16),
+                      (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16));
+}
+__device__ __forceinline__ void gb_mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+struct GbStepInputs {
+    float2 gir, giz, gin, ghr, ghz, ghn, hp, dy;
+};
 
 __global__ void __cluster_dims__(kGbCluster, 1, 1) __launch_bounds__(kGbThreads, 1)
     gru_layer_bwd_kernel(const float* __restrict__ whh_f,     // W_hh forward direction [768][256] (flat parameters)
@@ -433,60 +462,100 @@ __global__ void __cluster_dims__(kGbCluster, 1, 1) __launch_bounds__(kGbThreads,
                          const float* __restrict__ gh,        // [2][B*T, 768] recurrent projection (+ b_hh), tile order
                          const float* __restrict__ y,         // [B, T, 512] layer output
                          const float* __restrict__ dy,        // [B, T, 512] gradient w.r.t. the layer output
+                         const float* __restrict__ dy_amax,   // max |dy| (one device float)
                          float* __restrict__ dgi,             // [B*T, 1536]
                          float* __restrict__ dgh,             // [2][B*T, 768] natural gate order
                          float* __restrict__ dbih_f, float* __restrict__ dbih_r,   // [768] bias gradients (pre-zeroed)
                          float* __restrict__ dbhh_f, float* __restrict__ dbhh_r, int B, int T) {
-    extern __shared__ __align__(16) float gsm[];
-    float* s_w = gsm;                                    // [32 units][772]
-    float* s_dgh = gsm + 32 * kGbWStride;                // [2][16][768]
-    float* s_dh = s_dgh + 2 * kGbNB * 768;               // [16][33]
-    const int tid = threadIdx.x;
+    extern __shared__ __align__(16) uint8_t gsm_raw[];
+    uint2* s_g = reinterpret_cast<uint2*>(gsm_raw);                                       // [2][16][kGbRS] pushed gate gradients
+    float* s_part = reinterpret_cast<float*>(gsm_raw + 2 * kGbNB * kGbRS * 8);            // [8 warps][16][kGbPS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
     const int rank = blockIdx.x % kGbCluster, slice = blockIdx.x / kGbCluster, dir = blockIdx.y;
     const int j0 = rank * 32, b0 = slice * kGbNB;
     const float* __restrict__ whh = dir == 0 ? whh_f : whh_r;
-    for (int i = tid; i < 768 * 32; i += kGbThreads) {
-        const int u = i & 31, g = i >> 5;
-        s_w[u * kGbWStride + g] = __ldg(whh + (int64_t)g * 256 + j0 + u);
+
+    float scale = 1.f, inv_scale = 1.f;
+    {
+        const float a = __ldg(dy_amax);
+        if (a > 0.f) {
+            int e;
+            frexpf(a, &e);
+            e = 6 - e;                                   // a * 2^e in [32, 64)
+            e = e > 100 ? 100 : (e < -100 ? -100 : e);
+            scale = ldexpf(1.f, e);
+            inv_scale = ldexpf(1.f, -e);
+        }
     }
-    for (int i = tid; i < kGbNB * 33; i += kGbThreads) s_dh[i] = 0.f;
-    // phase-A role: utterance ab, units j0 + 2*aug, +1
+    // W_hh fragments: B[k = gate][n = unit], k-step ks covers gates 96 warp + 16 ks .. + 16, n-tile nt units j0 + 8 nt .. + 8;
+    // register h of a fragment holds k = 2 tig + 8 h, + 1 for n = gid
+    uint32_t w_hi[6][4][2], w_lo[6][4][2];
+#pragma unroll
+    for (int ks = 0; ks < 6; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int g = 96 * warp + 16 * ks + 2 * tig + 8 * h, u = j0 + 8 * nt + gid;
+                const uint2 p = gb_split_pair(__ldg(whh + (int64_t)g * 256 + u), __ldg(whh + (int64_t)(g + 1) * 256 + u));
+                w_hi[ks][nt][h] = p.x;
+                w_lo[ks][nt][h] = p.y;
+            }
+    // phase-A role: utterance ab, units j0 + 2 aug, + 1
     const int ab = tid >> 4, aug = tid & 15;
     const int abb = b0 + ab;
     const bool avalid = abb < B;
     const int abc = avalid ? abb : B - 1;
-    // phase-B role: unit bu, utterances bq and bq + 8
-    const int bu = tid & 31, bq = tid >> 5;
-    const uint32_t s_dgh_addr = (uint32_t)__cvta_generic_to_shared(s_dgh);
+    const uint32_t s_g_addr = (uint32_t)__cvta_generic_to_shared(s_g);
     const int64_t BT = (int64_t)B * T;
     float sum_r[2] = {0.f, 0.f}, sum_z[2] = {0.f, 0.f}, sum_n[2] = {0.f, 0.f}, sum_hn[2] = {0.f, 0.f};
-    __syncthreads();
+    float carry[2] = {0.f, 0.f};                         // z * dh of the previous step: the direct path of dh through h_prev
+
+    auto load_inputs = [&](int s, GbStepInputs& in) {
+        const int t = dir == 0 ? T - 1 - s : s;          // reverse of the forward processing order
+        const int tp = dir == 0 ? t - 1 : t + 1;         // where h_prev lives
+        const int64_t row = (int64_t)abc * T + t;
+        const float* gip = gi + row * 1536 + dir * 768 + j0 + 2 * aug;
+        const float* ghp = gh + ((int64_t)dir * BT + row) * 768 + rank * 96 + 2 * aug;
+        in.gir = *reinterpret_cast<const float2*>(gip);
+        in.giz = *reinterpret_cast<const float2*>(gip + 256);
+        in.gin = *reinterpret_cast<const float2*>(gip + 512);
+        in.ghr = *reinterpret_cast<const float2*>(ghp);
+        in.ghz = *reinterpret_cast<const float2*>(ghp + 32);
+        in.ghn = *reinterpret_cast<const float2*>(ghp + 64);
+        in.hp = make_float2(0.f, 0.f);
+        if (tp >= 0 && tp < T) in.hp = *reinterpret_cast<const float2*>(y + ((int64_t)abc * T + tp) * 512 + dir * 256 + j0 + 2 * aug);
+        in.dy = *reinterpret_cast<const float2*>(dy + row * 512 + dir * 256 + j0 + 2 * aug);
+    };
+    GbStepInputs cur, nxt;
+    load_inputs(0, nxt);
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 
     for (int s = 0; s < T; ++s) {
-        const int t = dir == 0 ? T - 1 - s : s;          // reverse of the forward processing order
-        const int tp = dir == 0 ? t - 1 : t + 1;         // where h_{prev} lives
+        const int t = dir == 0 ? T - 1 - s : s;
         const int buf = s & 1;
         const int64_t row = (int64_t)abc * T + t;
+        cur = nxt;
+        if (s + 1 < T) load_inputs(s + 1, nxt);          // the next step's operands do not depend on the recurrence
         // ---- phase A: gate gradients of this CTA's units ------------------------------------------------------
         {
-            const float* gip = gi + row * 1536 + dir * 768 + j0 + 2 * aug;
-            const float* ghp = gh + ((int64_t)dir * BT + row) * 768 + rank * 96 + 2 * aug;
-            const float2 gir = *reinterpret_cast<const float2*>(gip), giz = *reinterpret_cast<const float2*>(gip + 256),
-                         gin = *reinterpret_cast<const float2*>(gip + 512);
-            const float2 ghr = *reinterpret_cast<const float2*>(ghp), ghz = *reinterpret_cast<const float2*>(ghp + 32),
-                         ghn = *reinterpret_cast<const float2*>(ghp + 64);
-            float2 hp = make_float2(0.f, 0.f);
-            if (tp >= 0 && tp < T) hp = *reinterpret_cast<const float2*>(y + ((int64_t)abc * T + tp) * 512 + dir * 256 + j0 + 2 * aug);
-            const float2 dyv = *reinterpret_cast<const float2*>(dy + row * 512 + dir * 256 + j0 + 2 * aug);
+            float back[2] = {0.f, 0.f};                  // dh arriving through the gates: sum of the 8 warps' partial products
+            if (s > 0) {
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                    const float2 p = *reinterpret_cast<const float2*>(s_part + (w * kGbNB + ab) * kGbPS + 2 * aug);
+                    back[0] += p.x;
+                    back[1] += p.y;
+                }
+            }
             float o_r[2], o_z[2], o_n[2], o_hn[2];
-            const float a_gir[2] = {gir.x, gir.y}, a_giz[2] = {giz.x, giz.y}, a_gin[2] = {gin.x, gin.y};
-            const float a_ghr[2] = {ghr.x, ghr.y}, a_ghz[2] = {ghz.x, ghz.y}, a_ghn[2] = {ghn.x, ghn.y};
-            const float a_hp[2] = {hp.x, hp.y}, a_dy[2] = {dyv.x, dyv.y};
+            const float a_gir[2] = {cur.gir.x, cur.gir.y}, a_giz[2] = {cur.giz.x, cur.giz.y}, a_gin[2] = {cur.gin.x, cur.gin.y};
+            const float a_ghr[2] = {cur.ghr.x, cur.ghr.y}, a_ghz[2] = {cur.ghz.x, cur.ghz.y}, a_ghn[2] = {cur.ghn.x, cur.ghn.y};
+            const float a_hp[2] = {cur.hp.x, cur.hp.y}, a_dy[2] = {cur.dy.x, cur.dy.y};
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const float dh = avalid ? a_dy[e] + s_dh[ab * 33 + 2 * aug + e] : 0.f;
+                const float dh = avalid ? a_dy[e] + (carry[e] + back[e] * inv_scale) : 0.f;
                 const float r = gb_sigmoid(a_gir[e] + a_ghr[e]);
                 const float z = gb_sigmoid(a_giz[e] + a_ghz[e]);
                 const float n = tanhf(a_gin[e] + r * a_ghn[e]);
@@ -498,7 +567,7 @@ __global__ void __cluster_dims__(kGbCluster, 1, 1) __launch_bounds__(kGbThreads,
                 o_z[e] = dz * z * (1.f - z);
                 o_n[e] = dpn;
                 o_hn[e] = dpn * r;
-                s_dh[ab * 33 + 2 * aug + e] = z * dh;
+                carry[e] = z * dh;
                 sum_r[e] += o_r[e];
                 sum_z[e] += o_z[e];
                 sum_n[e] += o_n[e];
@@ -515,39 +584,42 @@ __global__ void __cluster_dims__(kGbCluster, 1, 1) __launch_bounds__(kGbThreads,
                 *reinterpret_cast<float2*>(dghp + 512) = make_float2(o_hn[0], o_hn[1]);
             }
             if (s + 1 < T) {
-                const uint32_t local = s_dgh_addr + (uint32_t)(((buf * kGbNB + ab) * 768 + j0 + 2 * aug) * 4);
+                const uint2 pr = gb_split_pair(o_r[0] * scale, o_r[1] * scale), pz = gb_split_pair(o_z[0] * scale, o_z[1] * scale),
+                            ph = gb_split_pair(o_hn[0] * scale, o_hn[1] * scale);
+                const uint32_t local = s_g_addr + (uint32_t)(((buf * kGbNB + ab) * kGbRS + (j0 >> 1) + aug) * 8);
 #pragma unroll
                 for (int c = 0; c < kGbCluster; ++c) {
                     const uint32_t ra = gb_map_to_cta(local, (uint32_t)c);
-                    gb_st_cluster_v2(ra, o_r[0], o_r[1]);
-                    gb_st_cluster_v2(ra + 256 * 4, o_z[0], o_z[1]);
-                    gb_st_cluster_v2(ra + 512 * 4, o_hn[0], o_hn[1]);
+                    gb_st_cluster_v2(ra, pr.x, pr.y);
+                    gb_st_cluster_v2(ra + 128 * 8, pz.x, pz.y);
+                    gb_st_cluster_v2(ra + 256 * 8, ph.x, ph.y);
                 }
             }
         }
         if (s + 1 == T) break;
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-        // ---- phase B: dh_prev[b][u] += sum_g W_hh[g][j0+u] * dgh[b][g] ----------------------------------------
+        // ---- phase B: partial[warp][b][u] = sum over the warp's 96 gates of dgh[b][g] * W_hh[g][j0 + u] -----------
         {
-            const float4* w4 = reinterpret_cast<const float4*>(s_w + bu * kGbWStride);
-            const float4* d0 = reinterpret_cast<const float4*>(s_dgh + (buf * kGbNB + bq) * 768);
-            const float4* d1 = reinterpret_cast<const float4*>(s_dgh + (buf * kGbNB + bq + 8) * 768);
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll 4
-            for (int g4 = 0; g4 < 192; ++g4) {
-                const float4 w = w4[g4], x0 = d0[g4], x1 = d1[g4];
-                a0 = fmaf(w.x, x0.x, a0);
-                a0 = fmaf(w.y, x0.y, a0);
-                a0 = fmaf(w.z, x0.z, a0);
-                a0 = fmaf(w.w, x0.w, a0);
-                a1 = fmaf(w.x, x1.x, a1);
-                a1 = fmaf(w.y, x1.y, a1);
-                a1 = fmaf(w.z, x1.z, a1);
-                a1 = fmaf(w.w, x1.w, a1);
+            float acc0[4][4] = {}, acc1[4][4] = {};
+            const uint2* a_lo_row = s_g + (buf * kGbNB + gid) * kGbRS + 48 * warp + tig;     // gate pair (96 warp + 2 tig) / 2
+            const uint2* a_hi_row = a_lo_row + 8 * kGbRS;                                    // utterance gid + 8
+#pragma unroll
+            for (int ks = 0; ks < 6; ++ks) {
+                const uint2 p0 = a_lo_row[8 * ks], p1 = a_hi_row[8 * ks], p2 = a_lo_row[8 * ks + 4], p3 = a_hi_row[8 * ks + 4];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) gb_mma(acc0[nt], p0.x, p1.x, p2.x, p3.x, w_hi[ks][nt][0], w_hi[ks][nt][1]);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) gb_mma(acc1[nt], p0.x, p1.x, p2.x, p3.x, w_lo[ks][nt][0], w_lo[ks][nt][1]);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) gb_mma(acc1[nt], p0.y, p1.y, p2.y, p3.y, w_hi[ks][nt][0], w_hi[ks][nt][1]);
             }
-            s_dh[bq * 33 + bu] += a0;
-            s_dh[(bq + 8) * 33 + bu] += a1;
+            float* prow = s_part + (warp * kGbNB + gid) * kGbPS + 2 * tig;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                *reinterpret_cast<float2*>(prow + 8 * nt) = make_float2(acc0[nt][0] + acc1[nt][0], acc0[nt][1] + acc1[nt][1]);
+                *reinterpret_cast<float2*>(prow + 8 * kGbPS + 8 * nt) = make_float2(acc0[nt][2] + acc1[nt][2], acc0[nt][3] + acc1[nt][3]);
+            }
         }
         __syncthreads();
     }
@@ -555,7 +627,7 @@ __global__ void __cluster_dims__(kGbCluster, 1, 1) __launch_bounds__(kGbThreads,
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     // bias gradients: column sums of dgi / dgh over (utterance, step); reduce the 16 utterances through shared memory
-    float* s_b = s_dgh;                                  // [4 kinds][16 utterances][32 units], free after the last barrier
+    float* s_b = s_part;                                 // [4 kinds][16 utterances][32 units], free after the last barrier
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
         s_b[(0 * kGbNB + ab) * 32 + 2 * aug + e] = sum_r[e];
@@ -586,57 +658,105 @@ __global__ void __cluster_dims__(kGbCluster, 1, 1) __launch_bounds__(kGbThreads,
     }
 }
 
-// C[M,N] = op(A) B + beta C on the fp32 CUDA cores; B stored [K][N]; TA: A stored [K][M], else [M][K].
-template <bool TA>
-__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
-                                                    float* __restrict__ Cm, int ldc, int M, int N, int K, float beta) {
-    __shared__ __align__(16) float As[16][68], Bs[16][68];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-    float acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        if (TA) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int e = tid + i * 256, kk = e >> 6, mm = e & 63;
-                As[kk][mm] = (k0 + kk < K && m0 + mm < M) ? A[(int64_t)(k0 + kk) * lda + m0 + mm] : 0.f;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int e = tid + i * 256, mm = e >> 4, kk = e & 15;
-                As[kk][mm] = (k0 + kk < K && m0 + mm < M) ? A[(int64_t)(m0 + mm) * lda + k0 + kk] : 0.f;
-            }
-        }
+// ---- operands of the GRU parameter / input gradients on the tensor cores -------------------------------------------
+// dW_ih = dgi^T x, dW_hh = dgh^T h_prev and dx = dgi [W_ih fwd; W_ih rev] are tc_gemm_nt contractions (fp16 hi/lo, three
+// passes).  The kernel wants both operands K-major; for the weight gradients K is the (utterance, step) index, i.e. the
+// TRANSPOSES of what the recurrence leaves in memory.  One launch of operand_prep_kernel runs a table of jobs, each
+//     dst[c][col0 + r] = split(scale * src[r][c])   (transpose)   or   dst[r][c] = split(scale * src[r][c])
+// over 32 x 32 tiles, rows beyond `rows` zero-filled up to rows_pad (K padded to the GEMM's 64-wide k-blocks).
+// Gate gradients carry the loss scale and span many orders of magnitude: they are multiplied by a power of two that puts
+// their largest magnitude in [8192, 16384) (gate_absmax_kernel), undone in the GEMM's epilogue.
+struct PrepJob {
+    const float* src;
+    __half* hi;
+    __half* lo;
+    const float* amax;      // nullable: operand is used as it is
+    float* inv_scale;       // where 1 / scale goes (nullable)
+    int rows, rows_pad, cols, ld_src, ld_dst, col0, transpose, tile0;
+};
+constexpr int kMaxPrepJobs = 10;
+struct PrepJobs {
+    PrepJob j[kMaxPrepJobs];
+    int n, tiles;
+};
+
+__device__ __forceinline__ float split_scale_from_amax(float a, float* inv_scale) {
+    int e = 0;
+    if (a > 0.f) {
+        frexpf(a, &e);                             // a = f * 2^e, f in [0.5, 1)
+        e = 14 - e;                                // a * 2^e in [8192, 16384)
+        e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    }
+    if (inv_scale) *inv_scale = ldexpf(1.f, -e);
+    return ldexpf(1.f, e);
+}
+
+__global__ void __launch_bounds__(256) operand_prep_kernel(const __grid_constant__ PrepJobs jobs) {
+    __shared__ float tile[32][33];
+    int ji = 0;
+#pragma unroll 1
+    while (ji + 1 < jobs.n && (int)blockIdx.x >= jobs.j[ji + 1].tile0) ++ji;
+    const PrepJob& jb = jobs.j[ji];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int local = (int)blockIdx.x - jb.tile0, tiles_c = jb.cols / 32;
+    const int r0 = (local / tiles_c) * 32, c0 = (local % tiles_c) * 32;
+    float inv_dummy;
+    const bool writer = local == 0 && threadIdx.x == 0;
+    const float scale = jb.amax ? split_scale_from_amax(__ldg(jb.amax), writer && jb.inv_scale ? jb.inv_scale : &inv_dummy) : 1.f;
+    if (jb.transpose) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int e = tid + i * 256, kk = e >> 6, nn = e & 63;
-            Bs[kk][nn] = (k0 + kk < K && n0 + nn < N) ? Bm[(int64_t)(k0 + kk) * ldb + n0 + nn] : 0.f;
+            const int r = r0 + ty + 8 * i;
+            tile[ty + 8 * i][tx] = r < jb.rows ? jb.src[(int64_t)r * jb.ld_src + c0 + tx] * scale : 0.f;
         }
         __syncthreads();
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int i = 0; i < 4; ++i) {
+            const int c = c0 + ty + 8 * i;
+            __half h, l;
+            tc::split_f16(tile[tx][ty + 8 * i], h, l);
+            const int64_t o = (int64_t)c * jb.ld_dst + jb.col0 + r0 + tx;
+            jb.hi[o] = h;
+            jb.lo[o] = l;
         }
-        __syncthreads();
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = r0 + ty + 8 * i;
+            if (r >= jb.rows) continue;
+            __half h, l;
+            tc::split_f16(jb.src[(int64_t)r * jb.ld_src + c0 + tx] * scale, h, l);
+            const int64_t o = (int64_t)r * jb.ld_dst + jb.col0 + c0 + tx;
+            jb.hi[o] = h;
+            jb.lo[o] = l;
+        }
+    }
+}
+
+// out[0] = max |a|, out[1] = max |b| over the finite elements (non-finite ones stay what they are through the split and
+// poison the products, which is what the found-inf check needs to see).  out is pre-zeroed.
+__global__ void __launch_bounds__(256) gate_absmax_kernel(const float* __restrict__ a, int64_t na, const float* __restrict__ b,
+                                                          int64_t nb, float* __restrict__ out) {
+    float ma = 0.f, mb = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4, i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    for (int64_t i = i0; i < na; i += stride) {
+        const float4 v = *reinterpret_cast<const float4*>(a + i);
+        const float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+        if (isfinite(m)) ma = fmaxf(ma, m);
+    }
+    for (int64_t i = i0; i < nb; i += stride) {
+        const float4 v = *reinterpret_cast<const float4*>(b + i);
+        const float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+        if (isfinite(m)) mb = fmaxf(mb, m);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
-        if (m >= M) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
-            if (n >= N) continue;
-            float* c = Cm + (int64_t)m * ldc + n;
-            *c = beta != 0.f ? acc[i][j] + beta * *c : acc[i][j];
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+        ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+        mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (ma > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(ma));
+        if (mb > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out + 1), __float_as_uint(mb));
     }
 }
 
@@ -971,15 +1091,6 @@ static void debug_dump(const char* name, const float* d, size_t n, cudaStream_t 
     }
 }
 
-template <bool TA>
-static int sgemm(const float* A, int lda, const float* Bm, int ldb, float* Cm, int ldc, int M, int N, int K, float beta,
-                 cudaStream_t st) {
-    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
-    sgemm_kernel<TA><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, Cm, ldc, M, N, K, beta);
-    SIR_CHECK_LAUNCH("sgemm_kernel");
-    return SIR_OK;
-}
-
 static inline unsigned blocks_for(int64_t n, int per_block = 256, int cap = 148 * 16) {
     const int64_t b = (n + per_block - 1) / per_block;
     return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
@@ -999,7 +1110,9 @@ static size_t carve_train(TrainSaved& t, uint8_t* base, int B, int H, int W, int
     const size_t n_a1 = (size_t)B * H2 * W2 * 32, n_a2 = (size_t)B * H4 * W4 * 64, n_g = (size_t)B * T * gin;
     const size_t BT = (size_t)B * T, n_y = BT * 512;
     t.bn_acc = (double*)next(3 * 2 * 256 * 8);     // first: fixed offset, so it stays zeroed when the batch size changes
-    t.amax = (float*)next(8 * 4);                  // [layer 3, layer 2] max |dz|, then their inverse split scales
+    t.amax = (float*)next(24 * 4);                 // [layer 3, layer 2] max |dz|, then their inverse split scales;
+                                                   // [8 + 4 l ..]: GRU layer l max |dgi|, max |dgh|, inverse split scales;
+                                                   // [16 + l]: max |dy| of GRU layer l
     t.z1 = (float*)next(n_z1 * 4);
     t.z2 = (float*)next(n_z2 * 4);
     t.z3 = (float*)next(n_z3 * 4);
@@ -1034,6 +1147,21 @@ static size_t carve_train(TrainSaved& t, uint8_t* base, int B, int H, int W, int
     t.hprevf = (float*)next(2 * BT * 256 * 4);
     t.hprev_hi = (__half*)next(2 * BT * 256 * 2);
     t.hprev_lo = (__half*)next(2 * BT * 256 * 2);
+    {
+        const size_t Kp = (BT + 63) & ~(size_t)63, gmax = (size_t)(gin > 512 ? gin : 512);
+        t.gT_hi = (__half*)next(1536 * Kp * 2);
+        t.gT_lo = (__half*)next(1536 * Kp * 2);
+        t.gs_hi = (__half*)next(BT * 1536 * 2);
+        t.gs_lo = (__half*)next(BT * 1536 * 2);
+        t.ghT_hi = (__half*)next(2 * 768 * Kp * 2);
+        t.ghT_lo = (__half*)next(2 * 768 * Kp * 2);
+        t.xT_hi = (__half*)next(gmax * Kp * 2);
+        t.xT_lo = (__half*)next(gmax * Kp * 2);
+        t.hT_hi = (__half*)next(2 * 256 * Kp * 2);
+        t.hT_lo = (__half*)next(2 * 256 * Kp * 2);
+        t.wT_hi = (__half*)next(gmax * 1536 * 2);
+        t.wT_lo = (__half*)next(gmax * 1536 * 2);
+    }
     t.dz = (float*)next(n_z1 * 4);                 // largest raw conv output (layer 1); reused by layers 2, 3
     t.dz_hi = (__half*)next(n_z2 * 2);
     t.dz_lo = (__half*)next(n_z2 * 2);
@@ -1109,27 +1237,70 @@ static int gru_layer_backward(sir_model* m, int layer, const float* params, cons
                                  "gru_bwd_recurrent_gemm")))
             return rc;
     }
+    float* dy_amax = t.amax + 16 + layer;
+    gate_absmax_kernel<<<blocks_for((int64_t)BT * 512 / 4, 256, 148), 256, 0, st>>>(t.dy, (int64_t)BT * 512, nullptr, 0, dy_amax);
+    SIR_CHECK_LAUNCH("gate_absmax_kernel");
     {
         SIR_SMEM_OPTIN(gru_layer_bwd_kernel, kGbSmemBytes);
         dim3 grid((unsigned)(kGbCluster * ((B + kGbNB - 1) / kGbNB)), 2);
         ProfScope ps(layer == 0 ? "gru_l0_bptt" : "gru_l1_bptt", st);
         gru_layer_bwd_kernel<<<grid, kGbThreads, kGbSmemBytes, st>>>(params + m->off.whh[layer][0], params + m->off.whh[layer][1],
-                                                                     t.gi[layer], t.gh, t.y[layer], t.dy, t.dgi, t.dgh,
+                                                                     t.gi[layer], t.gh, t.y[layer], t.dy, dy_amax, t.dgi, t.dgh,
                                                                      grads + m->off.bih[layer][0], grads + m->off.bih[layer][1],
                                                                      grads + m->off.bhh[layer][0], grads + m->off.bhh[layer][1], B, T);
         SIR_CHECK_LAUNCH("gru_layer_bwd_kernel");
     }
-    for (int d = 0; d < 2; ++d) {
-        const float* dgi_d = t.dgi + d * 768;
-        const float* dgh_d = t.dgh + (size_t)d * BT * 768;
-        // dW_ih = dgi^T x ; dW_hh = dgh^T h_prev ; db = column sums
-        if ((rc = sgemm<true>(dgi_d, 1536, x, in_sz, grads + m->off.wih[layer][d], in_sz, 768, in_sz, BT, 0.f, st))) return rc;
-        if ((rc = sgemm<true>(dgh_d, 768, t.hprevf + (size_t)d * BT * 256, 256, grads + m->off.whh[layer][d], 256, 768, 256, BT,
-                              0.f, st)))
+    // parameter and input gradients: dW_ih = dgi^T x, dW_hh = dgh^T h_prev, dx = dgi [W_ih fwd; W_ih rev]
+    const int Kp = (BT + 63) & ~63;
+    float* amax = t.amax + 8 + 4 * layer;          // max |dgi|, max |dgh|, 1 / scale(dgi), 1 / scale(dgh)
+    gate_absmax_kernel<<<blocks_for((int64_t)BT * 1536 / 4, 256, 148 * 2), 256, 0, st>>>(t.dgi, (int64_t)BT * 1536, t.dgh,
+                                                                                        (int64_t)2 * BT * 768, amax);
+    SIR_CHECK_LAUNCH("gate_absmax_kernel");
+    {
+        PrepJobs jobs{};
+        int n = 0, tiles = 0;
+        auto add = [&](const float* src, __half* hi, __half* lo, const float* am, float* inv, int rows, int rows_pad, int cols,
+                       int ld_src, int ld_dst, int col0, int transpose) {
+            PrepJob& j = jobs.j[n++];
+            j = PrepJob{src, hi, lo, am, inv, rows, rows_pad, cols, ld_src, ld_dst, col0, transpose, tiles};
+            tiles += (rows_pad / 32) * (cols / 32);
+        };
+        const int BTp = (BT + 31) & ~31;
+        add(t.dgi, t.gT_hi, t.gT_lo, amax, amax + 2, BT, Kp, 1536, 1536, Kp, 0, 1);                        // dgi^T [1536][Kp]
+        for (int d = 0; d < 2; ++d)                                                                        // dgh^T [2][768][Kp]
+            add(t.dgh + (size_t)d * BT * 768, t.ghT_hi + (size_t)d * 768 * Kp, t.ghT_lo + (size_t)d * 768 * Kp, amax + 1, amax + 3,
+                BT, Kp, 768, 768, Kp, 0, 1);
+        add(x, t.xT_hi, t.xT_lo, nullptr, nullptr, BT, Kp, in_sz, in_sz, Kp, 0, 1);                        // x^T [in_sz][Kp]
+        for (int d = 0; d < 2; ++d)                                                                        // h_prev^T [2][256][Kp]
+            add(t.hprevf + (size_t)d * BT * 256, t.hT_hi + (size_t)d * 256 * Kp, t.hT_lo + (size_t)d * 256 * Kp, nullptr, nullptr,
+                BT, Kp, 256, 256, Kp, 0, 1);
+        if (dx) {
+            add(t.dgi, t.gs_hi, t.gs_lo, amax, nullptr, BT, BTp, 1536, 1536, 1536, 0, 0);                  // dgi [BT][1536]
+            for (int d = 0; d < 2; ++d)                                                                    // [W_ih fwd; W_ih rev]^T
+                add(params + m->off.wih[layer][d], t.wT_hi, t.wT_lo, nullptr, nullptr, 768, 768, in_sz, in_sz, 1536, d * 768, 1);
+        }
+        jobs.n = n;
+        jobs.tiles = tiles;
+        operand_prep_kernel<<<(unsigned)tiles, 256, 0, st>>>(jobs);
+        SIR_CHECK_LAUNCH("operand_prep_kernel");
+    }
+    {
+        tc::GemmOutput out{grads + m->off.wih[layer][1], 768, amax + 2};
+        if ((rc = tc::tc_gemm_nt(t.gT_hi, t.gT_lo, t.xT_hi, t.xT_lo, nullptr, grads + m->off.wih[layer][0], 1536, in_sz, Kp, st,
+                                 "gru_bwd_wih_gemm", nullptr, &out)))
             return rc;
-        // dx (+)= dgi W_ih
-        if (dx && (rc = sgemm<false>(dgi_d, 1536, params + m->off.wih[layer][d], in_sz, dx, in_sz, BT, in_sz, 768,
-                                     d == 0 ? 0.f : 1.f, st)))
+    }
+    for (int d = 0; d < 2; ++d) {
+        tc::GemmOutput out{nullptr, 0, amax + 3};
+        if ((rc = tc::tc_gemm_nt(t.ghT_hi + (size_t)d * 768 * Kp, t.ghT_lo + (size_t)d * 768 * Kp, t.hT_hi + (size_t)d * 256 * Kp,
+                                 t.hT_lo + (size_t)d * 256 * Kp, nullptr, grads + m->off.whh[layer][d], 768, 256, Kp, st,
+                                 "gru_bwd_whh_gemm", nullptr, &out)))
+            return rc;
+    }
+    if (dx) {
+        tc::GemmOutput out{nullptr, 0, amax + 2};
+        if ((rc = tc::tc_gemm_nt(t.gs_hi, t.gs_lo, t.wT_hi, t.wT_lo, nullptr, dx, BT, in_sz, 1536, st, "gru_bwd_dx_gemm", nullptr,
+                                 &out)))
             return rc;
     }
     return SIR_OK;
@@ -1221,7 +1392,7 @@ extern "C" int sir_model_backward(sir_model* m, const float* d_params, const flo
     const int B = t.B, H = t.H, W = t.W, T = W / 8, C = m->num_classes, BT = B * T;
     int rc;
     SIR_CUDA(cudaMemsetAsync(d_grads, 0, (size_t)o.total * sizeof(float), st));
-    SIR_CUDA(cudaMemsetAsync(t.amax, 0, 8 * sizeof(float), st));
+    SIR_CUDA(cudaMemsetAsync(t.amax, 0, 24 * sizeof(float), st));
     // head
     {
         const size_t smem = (size_t)(2 * T + 512 + C) * sizeof(float);
