@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsir_b200.so")
-SOURCES = ["frontend.cu", "frontend_tc.cu", "classifier.cu", "conv1_tc.cu", "gemm_tc.cu", "gru_tc.cu", "train.cu", "conv_persist.cu"]
+SOURCES = ["frontend.cu", "frontend_tc.cu", "classifier.cu", "conv1_tc.cu", "gemm_tc.cu", "gru_tc.cu", "train.cu", "conv_persist.cu", "conv_wgrad_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -122,6 +122,9 @@ int tc_gemm_nt(const __half* a_hi, const __half* a_lo, const __half* w_hi, const
                float* C, int M, int N, int K, cudaStream_t st, const char* name, TicketSource* tickets = nullptr,
                const GemmOutput* out = nullptr);
 template <int CIN, int COUT>
+int tc_conv_wgrad(const __half* dz_hi, const __half* dz_lo, const __half* a_hi, const __half* a_lo, float* partial, int B, int H,
+                  int W, int max_chunks, int* chunks_out, cudaStream_t st, const char* name);
+template <int CIN, int COUT>
 int tc_conv3x3(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
                __half* out_hi, __half* out_lo, float* raw_out, int B, int H, int W, int out_whc, cudaStream_t st,
                const char* name);

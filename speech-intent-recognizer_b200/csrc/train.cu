@@ -909,62 +909,6 @@ __global__ void scaled_split_kernel(const float* __restrict__ x, int64_t n, cons
     }
 }
 
-// Weight gradient of a 3x3 convolution: partial[chunk][tap][co][ci] = sum over the chunk's pixels of
-// dz[pix][co] * a[pix shifted by the tap][ci].  grid (9, chunks); a chunk is `rows_per_chunk` image rows.
-template <int CIN, int COUT>
-__global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ a, int B, int H,
-                                                         int W, int rows_per_chunk, float* __restrict__ partial) {
-    constexpr int P = 16, TCO = COUT / 16, TCI = CIN / 16;
-    __shared__ __align__(16) float s_dz[P][COUT];
-    __shared__ __align__(16) float s_a[P][CIN];
-    const int tap = blockIdx.x, kh = tap / 3, kw = tap - kh * 3;
-    const int tid = threadIdx.x, tco = tid >> 4, tci = tid & 15;
-    float acc[TCO][TCI] = {};
-    const int64_t rows = (int64_t)B * H;
-    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
-    const int64_t r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
-    for (int64_t row = r0; row < r1; ++row) {
-        const int b = (int)(row / H), y = (int)(row % H);
-        const int ya = y + kh - 1;
-        const bool row_ok = ya >= 0 && ya < H;
-        for (int x0 = 0; x0 < W; x0 += P) {
-            for (int e = tid; e < P * COUT / 4; e += 256) {
-                const int p = e / (COUT / 4), c4 = e % (COUT / 4);
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (x0 + p < W) v = *reinterpret_cast<const float4*>(dz + ((row * W) + x0 + p) * COUT + c4 * 4);
-                *reinterpret_cast<float4*>(&s_dz[p][c4 * 4]) = v;
-            }
-            for (int e = tid; e < P * CIN / 4; e += 256) {
-                const int p = e / (CIN / 4), c4 = e % (CIN / 4);
-                const int xa = x0 + p + kw - 1;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row_ok && x0 + p < W && xa >= 0 && xa < W)
-                    v = *reinterpret_cast<const float4*>(a + (((int64_t)b * H + ya) * W + xa) * CIN + c4 * 4);
-                *reinterpret_cast<float4*>(&s_a[p][c4 * 4]) = v;
-            }
-            __syncthreads();
-#pragma unroll 4
-            for (int p = 0; p < P; ++p) {
-                float dv[TCO], av[TCI];
-#pragma unroll
-                for (int i = 0; i < TCO; ++i) dv[i] = s_dz[p][tco * TCO + i];
-#pragma unroll
-                for (int j = 0; j < TCI; ++j) av[j] = s_a[p][tci * TCI + j];
-#pragma unroll
-                for (int i = 0; i < TCO; ++i)
-#pragma unroll
-                    for (int j = 0; j < TCI; ++j) acc[i][j] = fmaf(dv[i], av[j], acc[i][j]);
-            }
-            __syncthreads();
-        }
-    }
-    float* out = partial + ((int64_t)blockIdx.y * 9 + tap) * COUT * CIN;
-#pragma unroll
-    for (int i = 0; i < TCO; ++i)
-#pragma unroll
-        for (int j = 0; j < TCI; ++j) out[(tco * TCO + i) * CIN + tci * TCI + j] = acc[i][j];
-}
-
 // conv1 (C_in = 1): partial[block][tap][co]; lane = output channel, warps stride over pixels.
 __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ feat, int B,
                                                           int H, int W, float* __restrict__ partial) {
@@ -1003,7 +947,7 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
 // accumulators, so ~32 loads are in flight per thread instead of a dependent chain over up to 592 chunks), then the eight
 // partial sums are added in warp order: the summation order is fixed, the result deterministic.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int cin, int cout,
-                                                           float* __restrict__ dw) {
+                                                           const float* __restrict__ out_scale, float* __restrict__ dw) {
     __shared__ float s_part[8][33];
     const int n = 9 * cin * cout;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1024,7 +968,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += s_part[k][lane];
         const int ci = i % cin, co = (i / cin) % cout, tap = i / (cin * cout);
-        dw[((int64_t)co * cin + ci) * 9 + tap] = t;
+        dw[((int64_t)co * cin + ci) * 9 + tap] = out_scale ? t * __ldg(out_scale) : t;
     }
 }
 
@@ -1209,13 +1153,13 @@ static int bn_stage_backward(const float* z, const float* dpool, int B, int H, i
 }
 
 template <int CIN, int COUT>
-static int conv_wgrad(const float* dz, const float* a, int B, int H, int W, float* partial, float* dw, cudaStream_t st) {
-    const int64_t rows = (int64_t)B * H;
-    const int rpc = (int)((rows + kWgradMaxChunks - 1) / kWgradMaxChunks);
-    const int chunks = (int)((rows + rpc - 1) / rpc);
-    conv_wgrad_kernel<CIN, COUT><<<dim3(9, (unsigned)chunks), 256, 0, st>>>(dz, a, B, H, W, rpc, partial);
-    SIR_CHECK_LAUNCH("conv_wgrad_kernel");
-    wgrad_reduce_kernel<<<(9 * CIN * COUT + 31) / 32, 256, 0, st>>>(partial, chunks, CIN, COUT, dw);
+static int conv_wgrad(const __half* dz_hi, const __half* dz_lo, const float* inv_scale, const __half* a_hi, const __half* a_lo,
+                      int B, int H, int W, float* partial, float* dw, cudaStream_t st) {
+    int chunks = 0, rc;
+    if ((rc = tc::tc_conv_wgrad<CIN, COUT>(dz_hi, dz_lo, a_hi, a_lo, partial, B, H, W, kWgradMaxChunks, &chunks, st,
+                                           CIN == 32 ? "conv2_wgrad" : "conv3_wgrad")))
+        return rc;
+    wgrad_reduce_kernel<<<(9 * CIN * COUT + 31) / 32, 256, 0, st>>>(partial, chunks, CIN, COUT, inv_scale, dw);
     SIR_CHECK_LAUNCH("wgrad_reduce_kernel");
     return SIR_OK;
 }
@@ -1415,7 +1359,9 @@ extern "C" int sir_model_backward(sir_model* m, const float* d_params, const flo
     if ((rc = bn_stage_backward<128, 1>(t.z3, t.dx, B, H / 4, W / 4, acc + 1024, t.stats[2], d_params, o, 2, t.dz, t.dz_hi, t.dz_lo,
                                         t.amax, d_grads, st)))
         return rc;
-    if ((rc = conv_wgrad<64, 128>(t.dz, t.a2f, B, H / 4, W / 4, t.wg_partial, d_grads + o.conv_w[2], st))) return rc;
+    if ((rc = conv_wgrad<64, 128>(t.dz_hi, t.dz_lo, t.amax + 2, t.a2_hi, t.a2_lo, B, H / 4, W / 4, t.wg_partial,
+                                  d_grads + o.conv_w[2], st)))
+        return rc;
     if ((rc = tc::tc_conv3x3<128, 64>(t.dz_hi, t.dz_lo, m->w3t_hi, m->w3t_lo, t.amax + 2, nullptr, nullptr, t.dact, B, H / 4,
                                       W / 4, 0, st, "conv3_dgrad")))
         return rc;
@@ -1425,7 +1371,9 @@ extern "C" int sir_model_backward(sir_model* m, const float* d_params, const flo
     if ((rc = bn_stage_backward<64, 0>(t.z2, t.dact, B, H / 2, W / 2, acc + 512, t.stats[1], d_params, o, 1, t.dz, t.dz_hi, t.dz_lo,
                                        t.amax + 1, d_grads, st)))
         return rc;
-    if ((rc = conv_wgrad<32, 64>(t.dz, t.a1f, B, H / 2, W / 2, t.wg_partial, d_grads + o.conv_w[1], st))) return rc;
+    if ((rc = conv_wgrad<32, 64>(t.dz_hi, t.dz_lo, t.amax + 3, t.a1_hi, t.a1_lo, B, H / 2, W / 2, t.wg_partial,
+                                 d_grads + o.conv_w[1], st)))
+        return rc;
     if ((rc = tc::tc_conv3x3<64, 32>(t.dz_hi, t.dz_lo, m->w2t_hi, m->w2t_lo, t.amax + 3, nullptr, nullptr, t.dact, B, H / 2,
                                      W / 2, 0, st, "conv2_dgrad")))
         return rc;
@@ -1439,7 +1387,7 @@ extern "C" int sir_model_backward(sir_model* m, const float* d_params, const flo
         const int nblk = (int)((int64_t)B * H < 592 ? (int64_t)B * H : 592);
         conv1_wgrad_kernel<<<nblk, 256, 0, st>>>(t.dz, t.feat, B, H, W, t.wg_partial);
         SIR_CHECK_LAUNCH("conv1_wgrad_kernel");
-        wgrad_reduce_kernel<<<(9 * 32 + 31) / 32, 256, 0, st>>>(t.wg_partial, nblk, 1, 32, d_grads + o.conv_w[0]);
+        wgrad_reduce_kernel<<<(9 * 32 + 31) / 32, 256, 0, st>>>(t.wg_partial, nblk, 1, 32, nullptr, d_grads + o.conv_w[0]);
         SIR_CHECK_LAUNCH("wgrad_reduce_kernel");
     }
     // the backward reduce/apply pair leaves its accumulators dirty (apply reads them): clear for the next step
