@@ -562,10 +562,14 @@ def measure_training(ctx, steps, warmup, batch=16, dataset_size=4096, cpu_ref=Tr
         "ms_per_step": ms / steps, "value": batch * ctx.world * steps / (ms * 1e-3), "unit": "utt/s",
         "batch_per_gpu": batch, "steps": steps, "final_loss": loss, "gpu_launches_per_step": launches / steps,
         "collective": (f"nccl all_reduce(SUM) of {(model.weight_count() + 1) * 4 / 1e6:.2f} MB flat fp32 gradients + found-inf "
-                       f"flag per step" if ctx.world > 1 else "none at world size 1 (the all-reduce is skipped)"),
+                       f"flag per step, two buckets: {(model.weight_count() + 1 - trainer.bucket) * 4 / 1e6:.2f} MB (GRU + head, "
+                       f"side stream, under the conv backward) then {trainer.bucket * 4 / 1e6:.2f} MB (conv); all_reduce_ms = what "
+                       "the step still waits for after the conv backward" if ctx.world > 1 and trainer._graph is not None else
+                       (f"nccl all_reduce(SUM) of {(model.weight_count() + 1) * 4 / 1e6:.2f} MB flat fp32 gradients + found-inf flag"
+                        if ctx.world > 1 else "none at world size 1 (the all-reduce is skipped)")),
         "all_reduce_ms": round(coll, 4), "all_reduce_share": round(coll / (ms / steps), 4) if ms > 0 else None,
         "skipped_steps": trainer.skipped_steps,
-        "cuda_graph": (f"two graphs per step (before / after the gradient all-reduce), {trainer._graph['launches']} kernels of "
+        "cuda_graph": (f"{'three' if ctx.world > 1 else 'two'} graphs per step (split at the gradient all-reduces), {trainer._graph['launches']} kernels of "
                        "libsir_b200 per replay; step count, bias corrections, loss scale and dropout offset live on the device"
                        if trainer._graph is not None else "off (eager launches)"),
         "e2e": {"value": batch * ctx.world * steps / e2e_s, "unit": "utt/s", "h2d_bytes_per_step": batch * 64 * OUT_FRAMES * 4 + batch * 8,

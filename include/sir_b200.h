@@ -195,6 +195,15 @@ int sir_model_train_forward(sir_model* m, float* d_params, const float* d_featur
  *   d_dlogits [batch, num_classes] -> d_grads [sir_model_weight_count] (overwritten, not accumulated). */
 int sir_model_backward(sir_model* m, const float* d_params, const float* d_dlogits, float* d_grads, void* stream);
 
+/* The same backward in two launches, so that a data-parallel job can all-reduce the first bucket of gradients while
+ * the second is still being computed (what DistributedDataParallel's gradient buckets do behind scripts/train.py:107):
+ *   part 1: attention + fc + both GRU layers.  Zeroes d_grads, then writes every gradient at or behind
+ *           sir_model_gru_grad_offset() (96 % of the bytes); d_dlogits required.
+ *   part 2: the three conv blocks.  Writes the gradients in front of that offset; d_dlogits may be NULL.
+ * part 1 followed by part 2 on one stream is sir_model_backward. */
+int sir_model_backward_part(sir_model* m, const float* d_params, const float* d_dlogits, float* d_grads, int part, void* stream);
+int sir_model_gru_grad_offset(const sir_model* m, int64_t* offset);
+
 /* sir_cross_entropy  <->  nn.CrossEntropyLoss()(output, label) + its backward    scripts/train.py:96,106,243
  *   d_loss[0] = mean_b( logsumexp(logits_b) - logits_b[label_b] );
  *   d_dlogits (may be NULL) = scale * (softmax(logits) - onehot(label)) / n_valid (scale = the GradScaler loss scale).

@@ -55,6 +55,8 @@ SIGNATURES = {
     "sir_model_train_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_uint64, c_uint64, c_float,
                                         c_float, c_void_p, c_void_p]),
     "sir_model_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sir_model_backward_part": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "sir_model_gru_grad_offset": (c_int, [c_void_p, POINTER(c_int64)]),
     "sir_cross_entropy": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "sir_grad_nonfinite": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "sir_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int, c_float, c_float, c_float,
@@ -340,6 +342,20 @@ class Model:
         check(load_library().sir_model_backward(self._h, ptr(flat_params), ptr(dlogits), ptr(flat_grads), stream_ptr()),
               "sir_model_backward")
         return flat_grads
+
+    def backward_part(self, flat_params: torch.Tensor, dlogits, flat_grads: torch.Tensor, part: int):
+        """Half of :meth:`backward`: part 1 = head + GRU layers (zeroes ``flat_grads`` first), part 2 = conv stack."""
+        require_cuda(flat_grads, "flat_grads")
+        assert flat_grads.is_contiguous() and flat_grads.numel() >= self.weight_count()
+        check(load_library().sir_model_backward_part(self._h, ptr(flat_params), ptr(dlogits) if dlogits is not None else None,
+                                                     ptr(flat_grads), int(part), stream_ptr()), "sir_model_backward_part")
+        return flat_grads
+
+    def gru_grad_offset(self) -> int:
+        """Index of the first GRU parameter in the flat buffer: conv / BatchNorm gradients lie in front of it."""
+        out = c_int64(0)
+        check(load_library().sir_model_gru_grad_offset(self._h, ctypes.byref(out)), "sir_model_gru_grad_offset")
+        return int(out.value)
 
     def pipeline(self, fe: Frontend, wave, lengths=None, max_samples=0, out_frames=200, features=None):
         require_cuda(wave, "wave")

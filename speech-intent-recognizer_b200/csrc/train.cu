@@ -1327,14 +1327,15 @@ extern "C" int sir_model_train_forward(sir_model* m, float* d_params, const floa
     return SIR_OK;
 }
 
-extern "C" int sir_model_backward(sir_model* m, const float* d_params, const float* d_dlogits, float* d_grads, void* stream) {
-    if (!m || !d_params || !d_dlogits || !d_grads) return fail(SIR_ERR_INVALID, "sir_model_backward: NULL argument");
-    if (!m->have_saved) return fail(SIR_ERR_INVALID, "sir_model_backward: no training forward to differentiate");
+// part 1: head + both GRU layers (leaves the gradient w.r.t. the GRU input in the workspace); part 2: the conv stack.
+// Every gradient of part 1 lies behind o.wih[0][0] in the flat buffer, every gradient of part 2 in front of it.
+static int model_backward_part(sir_model* m, const float* d_params, const float* d_dlogits, float* d_grads, int part, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     TrainSaved& t = m->ts;
     const FlatOffsets& o = m->off;
     const int B = t.B, H = t.H, W = t.W, T = W / 8, C = m->num_classes, BT = B * T;
     int rc;
+    if (part == 1) {
     SIR_CUDA(cudaMemsetAsync(d_grads, 0, (size_t)o.total * sizeof(float), st));
     SIR_CUDA(cudaMemsetAsync(t.amax, 0, 24 * sizeof(float), st));
     // head
@@ -1354,6 +1355,8 @@ extern "C" int sir_model_backward(sir_model* m, const float* d_params, const flo
     SIR_CUDA(cudaMemcpyAsync(t.dy, t.dx, (size_t)BT * 512 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if ((rc = gru_layer_backward(m, 0, d_params, t.ginf, m->gru_in, t.dx, d_grads, st))) return rc;
     debug_dump("dgin", t.dx, (size_t)BT * m->gru_in, st);
+    return SIR_OK;
+    }
     // conv3 stage: dx is the gradient w.r.t. the GRU input in the reference's feature order
     double* acc = t.bn_acc + 256;
     if ((rc = bn_stage_backward<128, 1>(t.z3, t.dx, B, H / 4, W / 4, acc + 1024, t.stats[2], d_params, o, 2, t.dz, t.dz_hi, t.dz_lo,
@@ -1393,6 +1396,28 @@ extern "C" int sir_model_backward(sir_model* m, const float* d_params, const flo
     // the backward reduce/apply pair leaves its accumulators dirty (apply reads them): clear for the next step
     SIR_CUDA(cudaMemsetAsync(t.bn_acc + 256, 0, (size_t)(3 * 2 * 256 - 256) * sizeof(double), st));
     return SIR_OK;
+}
+
+extern "C" int sir_model_backward_part(sir_model* m, const float* d_params, const float* d_dlogits, float* d_grads, int part,
+                                       void* stream) {
+    if (!m || !d_params || !d_grads || (part != 2 && !d_dlogits)) return fail(SIR_ERR_INVALID, "sir_model_backward_part: NULL argument");
+    if (part != 1 && part != 2) return fail(SIR_ERR_INVALID, "sir_model_backward_part: part must be 1 (head + GRU) or 2 (conv stack)");
+    if (!m->have_saved) return fail(SIR_ERR_INVALID, "sir_model_backward_part: no training forward to differentiate");
+    return model_backward_part(m, d_params, d_dlogits, d_grads, part, stream);
+}
+
+extern "C" int sir_model_gru_grad_offset(const sir_model* m, int64_t* offset) {
+    if (!m || !offset) return fail(SIR_ERR_INVALID, "sir_model_gru_grad_offset: NULL argument");
+    *offset = m->off.wih[0][0];
+    return SIR_OK;
+}
+
+extern "C" int sir_model_backward(sir_model* m, const float* d_params, const float* d_dlogits, float* d_grads, void* stream) {
+    if (!m || !d_params || !d_dlogits || !d_grads) return fail(SIR_ERR_INVALID, "sir_model_backward: NULL argument");
+    if (!m->have_saved) return fail(SIR_ERR_INVALID, "sir_model_backward: no training forward to differentiate");
+    int rc;
+    if ((rc = model_backward_part(m, d_params, d_dlogits, d_grads, 1, stream))) return rc;
+    return model_backward_part(m, d_params, d_dlogits, d_grads, 2, stream);
 }
 
 extern "C" int sir_cross_entropy(const float* d_logits, const int64_t* d_labels, int batch, int num_classes, float scale,

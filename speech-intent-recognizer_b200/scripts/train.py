@@ -167,6 +167,9 @@ class DataParallelTrainer:
             model._native_dirty = True
         model.dropout_seed = (int(seed) << 8) + self.rank         # distinct dropout streams per rank
         self.n = model.weight_count()
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.bucket = model._native_model.gru_grad_offset()        # conv / BatchNorm gradients lie in front of it
+        self._side = torch.cuda.Stream() if self.world > 1 else None
         self.exp_avg = torch.zeros_like(flat)
         self.exp_avg_sq = torch.zeros_like(flat)
         self.segments = model.param_segments()
@@ -186,17 +189,32 @@ class DataParallelTrainer:
 
     # -- CUDA-graph path ------------------------------------------------------------------------------------------------
     def _graph_body_pre(self, g):
+        """begin -> forward -> loss -> backward.  With more than one rank the backward stops after its first part (head + GRU
+        layers: every gradient behind ``self.bucket`` = 96 % of the bytes) and checks that bucket for inf/nan, so that its
+        all-reduce can run while ``_graph_body_mid`` computes the conv gradients in front of it."""
         m = self.model
         g["state"].begin(self.betas, self.world)
         m._flat_grad[self.n:].zero_()
         m._native_model.train_forward(m._flat, g["feats"], seed=m.dropout_seed, bn_momentum=m.bn1.momentum, bn_eps=m.bn1.eps,
                                       logits=g["logits"])
         _native.cross_entropy_state(g["logits"], g["labels"], g["state"], self._scalars[0:1], g["dlogits"])
-        m._native_model.backward(m._flat, g["dlogits"], m._flat_grad)
-        _native.grad_nonfinite(m._flat_grad, self.n, m._flat_grad[self.n:])
+        if self.world > 1:
+            m._native_model.backward_part(m._flat, g["dlogits"], m._flat_grad, 1)
+            _native.grad_nonfinite(m._flat_grad[self.bucket:], self.n - self.bucket, m._flat_grad[self.n:])
+        else:
+            m._native_model.backward(m._flat, g["dlogits"], m._flat_grad)
+            _native.grad_nonfinite(m._flat_grad, self.n, m._flat_grad[self.n:])
+
+    def _graph_body_mid(self, g):
+        m = self.model
+        m._native_model.backward_part(m._flat, None, m._flat_grad, 2)
 
     def _graph_body_post(self, g):
         m = self.model
+        if self.world > 1:
+            # the conv bucket is checked AFTER its all-reduce: the reduced values are the same bits on every rank, an inf / nan
+            # of any rank survives the sum, and the flag needs no collective of its own
+            _native.grad_nonfinite(m._flat_grad, self.bucket, m._flat_grad[self.n:])
         _native.adam_step_state(m._flat, m._flat_grad, self.exp_avg, self.exp_avg_sq, self.segments, self.lr, self.betas, self.eps,
                                 self.weight_decay, g["state"], m._flat_grad[self.n:])
         g["state"].end(m._flat_grad[self.n:], g["offset_inc"])
@@ -219,6 +237,8 @@ class DataParallelTrainer:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             self._graph_body_pre(g)
+            if self.world > 1:
+                self._graph_body_mid(g)
             self._graph_body_post(g)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -227,6 +247,10 @@ class DataParallelTrainer:
         g["pre"], g["post"] = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(g["pre"]):
             self._graph_body_pre(g)
+        if self.world > 1:
+            g["mid"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g["mid"], pool=g["pre"].pool()):
+                self._graph_body_mid(g)
         with torch.cuda.graph(g["post"], pool=g["pre"].pool()):
             self._graph_body_post(g)
         g["launches"] = _native.launch_count() - before          # kernels of libsir_b200 inside one replay of both graphs
@@ -237,10 +261,22 @@ class DataParallelTrainer:
         g["feats"].copy_(feats, non_blocking=True)
         g["labels"].copy_(label, non_blocking=True)
         g["pre"].replay()
-        if self.time_collective:
+        if self.world > 1:
+            # two gradient buckets (what DistributedDataParallel does behind scripts/train.py:107): the GRU / head bucket +
+            # found-inf flag is reduced on a side stream while the conv backward runs, the small conv bucket follows it
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                sync_flat_gradients(m._flat_grad[self.bucket:self.n + 1], self.group)
+            g["mid"].replay()
+            if self.time_collective:
+                self._ev[0].record()                                # from here on the step only waits for the collectives
+            sync_flat_gradients(m._flat_grad[:self.bucket], self.group)
+            main.wait_stream(self._side)
+            if self.time_collective:
+                self._ev[1].record()
+        elif self.time_collective:
             self._ev[0].record()
-        sync_flat_gradients(m._flat_grad, self.group)
-        if self.time_collective:
             self._ev[1].record()
         g["post"].replay()
         torch.cuda.current_stream().synchronize()                 # the reference reads loss.item() every step

@@ -86,6 +86,25 @@ def main():
         else:
             for o, k in m2.param_segments():
                 assert torch.equal(mine[o:o + k], other[o:o + k]), "differently seeded replicas diverged"
+    # (e) the graph-replayed step (backward split in two, the GRU / head bucket all-reduced on a side stream under the conv
+    # backward, the conv bucket after it) against the eager step with its single all-reduce: same losses, same parameters,
+    # same collective skip
+    me, mg = build(), build()
+    te = train.DataParallelTrainer(me, lr=1e-3, weight_decay=1e-4, use_amp=True, seed=3)
+    tg = train.DataParallelTrainer(mg, lr=1e-3, weight_decay=1e-4, use_amp=True, seed=3, use_graph=True)
+    for i in range(4):
+        inp = bad if i == 2 else xs
+        le, lg = te.step(inp, ls), tg.step(inp, ls)
+        assert tg._graph is not None and "mid" in tg._graph, "the bucketed graph path did not run"
+        assert (le == lg) or (le != le and lg != lg), (i, le, lg)
+        for o, k in me.param_segments():
+            assert torch.equal(me._flat[o:o + k], mg._flat[o:o + k]), f"graph step {i} differs from the eager step"
+    assert te.skipped_steps == 1 and tg.skipped_steps == 1 and tg.adam_steps == 3
+    mine = mg._flat.clone()
+    other = mine.clone()
+    dist.broadcast(other, src=0)
+    for o, k in mg.param_segments():
+        assert torch.equal(mine[o:o + k], other[o:o + k]), "graph-replayed replicas diverged"
     dist.barrier()
     if rank == 0:
         print("dp_check ok")

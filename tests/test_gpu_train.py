@@ -243,3 +243,34 @@ def test_graph_replayed_step_equals_eager_step():
     assert torch.equal(m0, m1) or torch.allclose(m0, m1, rtol=1e-5, atol=1e-9)
     assert torch.allclose(v0, v1, rtol=1e-5, atol=1e-12)
     assert float((p0 - p1).abs().max()) < 1e-6
+
+
+def test_backward_in_two_parts_equals_one_call():
+    """``sir_model_backward_part`` 1 (head + GRU layers) then 2 (conv stack) writes the same bits as ``sir_model_backward``;
+    part 1 alone leaves the conv gradients zero and already holds every gradient behind ``sir_model_gru_grad_offset``."""
+    x, labels = train_inputs(seed=TRAIN_SEED_B16, batch=16)
+    model, _ = make_model(1234)
+    model._ensure_native()
+    flat, nm, n = model.flatten_parameters_(), model._native_model, model.weight_count()
+    off = nm.gru_grad_offset()
+    assert 0 < off < n
+    feats = torch.from_numpy(x).cuda()
+    grads = []
+    for split in (False, True):
+        p = flat.clone()                                               # (the forward updates the running statistics in place)
+        logits = nm.train_forward(p, feats, seed=7, offset=0, bn_momentum=0.1, bn_eps=1e-5)
+        _, dlogits = native.cross_entropy(logits, torch.from_numpy(labels).cuda(), scale=1024.0)
+        g = torch.full((n + 4,), 3.0, device="cuda")
+        if split:
+            nm.backward_part(p, dlogits, g, 1)
+            assert float(g[:off].abs().max()) == 0.0 and float(g[off:n].abs().max()) > 0.0
+            tail = g[off:n].clone()
+            nm.backward_part(p, None, g, 2)
+            assert torch.equal(g[off:n], tail), "part 2 touched the first bucket"
+        else:
+            nm.backward(p, dlogits, g)
+        grads.append(g[:n].clone())
+    assert torch.equal(grads[0], grads[1])
+    assert float(grads[0][:off].abs().max()) > 0.0
+    with pytest.raises(native.NativeError):
+        nm.backward_part(p, dlogits, g, 3)
