@@ -9,8 +9,9 @@ namespace sir {
 
 // Device tables of the tensor-core DFT kernel (frontend_tc_tables.h builds them on the host).
 struct TcDeviceTables {
-    const uint16_t* b1_img;      // 8 KB   stage-1 operand image (fp16, swizzled, hi rows then lo rows)
-    const uint16_t* b2_img;      // 16 KB  stage-2 operand image
+    const float* b1_img;         // 8 KB   stage-1 operand image (tf32 pieces, swizzled: hi tile then lo tile)
+    const float* b2_img;         // 32 KB  stage-2 operand image (hi K 0..31, hi K 32..63, lo K 0..31, lo K 32..63)
+    const float* win_img;        // 4 KB   Hann window as [8][32 lanes][4]: lane's w[32 n1 + lane], n1 = 4c .. 4c + 3
     const float* twiddle;        // [32][16][2] (cos, -sin)(2 pi n2 k1 / 1024), k1 = 1..16
     const float* mel_weight;     // the sparse filterbank taps WITHOUT the 0.25 of the CUDA-core post-pass, the runs of a band
                                  // quad (4q .. 4q+3) zero-padded to the same length; 1536 floats, zero behind the taps

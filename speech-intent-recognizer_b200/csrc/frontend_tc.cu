@@ -1,35 +1,33 @@
 // Fused log-mel frontend on the sm_100a TENSOR CORES: the 1024-point real DFT of every frame is two matrix stages on
-// tcgen05 (32 x 32 Cooley-Tukey, fp16 (hi, lo) split operands, fp32 accumulators in tensor memory); CUDA cores only
-// window / scale / split the samples, apply the inter-stage twiddles, square, and run the sparse mel projection.
+// tcgen05 (32 x 32 Cooley-Tukey, TF32 (hi, lo) split operands, fp32 accumulators in tensor memory); CUDA cores only
+// window / split the samples, apply the inter-stage twiddles, square, and run the sparse mel projection.
 //
 // Replaces (per utterance) scripts/precompute_features.py:59-73, scripts/dataset.py:105-113,160-176 of the reference and
 // the torchaudio calls behind them, like frontend.cu, whose CUDA-core FFT it supersedes: that kernel
 // needs ~1,360 warp instructions per frame and is issue / latency bound at 8-11 % of the HBM roofline; here the butterflies
-// are MMAs and ~550 warp instructions per frame remain.  Numerics: frontend_tc_tables.h, tests/host/tc_dft_host_check.cpp
-// (within ~2x of an fp32 FFT's own rounding error).
+// are MMAs.  Numerics: frontend_tc_tables.h, tests/host/tc_dft_host_check.cpp (within ~2x of an fp32 FFT's own rounding
+// error).  TF32 pieces need no scaling (fp32 exponent range) and the split is a mask and a subtraction; the first version
+// of this kernel used fp16 pieces, which cost a maximum over every windowed frame, a power-of-two rescale and three
+// conversions per value on the CUDA cores - the resource this kernel is bound by.
 //
 // One persistent CTA per SM, 16 warps, work item = 15 consecutive frames of one utterance (15 x 17 stage-2 rows = 255 = two
 // 128-row UMMA tiles), drawn from a ticket counter:
 //   warps 0-3   "A": load samples (lane = n2, one coalesced 128-byte request per 32 samples; a 512-sample block is loaded
-//                once and serves the two frames that overlap it), per-frame power-of-two scale to max|x| in [1, 2), Hann
-//                window, fp16 (hi, lo) split, write the stage-1 operand rows (frame, n2) x K = n1 (hi | lo in one 128-byte
-//                swizzled row).  Warp w fills sub-tile w = frames 4w..4w+3.
-//   warp 4      issues the MMAs: stage 1 per sub-tile: D1 = A_hi [B1_hi; B1_lo] (N = 64) + A_lo B1_hi (N = 32);
-//                stage 2 per 128-row tile: D2 = A2_hi [B2_hi; B2_lo] (N = 128) + A2_lo B2_hi (N = 64).  The warp polls the
-//                barriers of both stages and issues whichever is ready, so stage 1 of later items never queues behind a
-//                stage 2 that waits for its consumers.
+//                once and serves the two frames that overlap it), Hann window, TF32 (hi, lo) split, and write the stage-1
+//                operand rows (frame, n2) x K = n1 STRAIGHT INTO TENSOR MEMORY (tcgen05.st: lane = row, 32 columns hi,
+//                32 columns lo).  Warp w takes frames 4w..4w+3 and owns lane quadrant w of every sub-tile: frame 4w + s is
+//                quadrant w of sub-tile s, so sub-tile s is complete after every warp's s-th frame.
+//   warp 4      issues the MMAs: stage 1 per sub-tile, A from tensor memory: D1 = A_hi B1_hi + A_hi B1_lo + A_lo B1_hi (12
+//                instructions of K = 8, N = 32); stage 2 per 128-row tile, A from shared memory: 24 instructions of K = 8,
+//                N = 64.  The warp polls the barriers of both stages and issues whichever is ready.
 //   warps 5-8   "C": read D1 (lane = n2, 32 real numbers = Y[0..16]), multiply by the twiddles W1024^(n2 k1), split, and
-//                write the stage-2 operand rows (frame, k1) x K = (n2, re/im): for a fixed k1 the 32 lanes write 32
-//                consecutive words of one row - the transposition between the stages costs no bank conflict.
+//                write the stage-2 operand rows (frame, k1) x K = (n2, re/im): for a fixed k1 the 32 lanes write 256
+//                consecutive bytes - the transposition between the stages costs no bank conflict.
 //   warps 9-12  "D/E": read D2 (lane = (frame, k1), 32 complex bins k1 + 32 k2), |X|^2 into the one-sided power spectrum
 //                (the bins with k mod 32 > 16 are mirrors), sparse mel taps, dB -> one of two [n_mels][16] tiles in shared
 //                memory.  These warps never touch global memory.
-//   warps 13-15 "F": tile -> global, the item's partial statistics, the counting atomic and - for the item that completes
-//                an utterance - the normalisation pass (as in frontend.cu).  The fence / atomic / L2 round trips of this
-//                group (~2 us per item) run beside the next item's arithmetic instead of in front of it.
+//   warps 13-15 "F": tile -> global and the item's partial statistics (frontend_finish_kernel merges them).
 // Every hand-off is an mbarrier; every wait is bounded and traps.
-#include <cuda_fp16.h>
-
 #include <vector>
 
 #include "frontend_params.cuh"
@@ -50,51 +48,65 @@ using namespace tc;
 #ifndef SIR_FE_PREFETCH
 #define SIR_FE_PREFETCH 1
 #endif
-#ifndef SIR_FE_S1_FIRST
-#define SIR_FE_S1_FIRST 1
+#ifndef SIR_FE_CHUNK
+#define SIR_FE_CHUNK 2                          // (pass, column block) chunks of stage 2 issued between looks at stage 1: 1, 2, 3 or 6
+#endif
+// Optional timeline of the first CTAs' first items (build with -DSIR_FE_TRACE; tools/fe_trace.py reads it): clock64 at the
+// hand-offs of every role, to see which dependency the pipeline waits for.  Not compiled into the product library.
+#ifdef SIR_FE_TRACE
+constexpr int kTraceCtas = 4, kTraceItems = 96, kTraceEvents = 32;
+__device__ long long g_fe_trace[kTraceCtas][kTraceItems][kTraceEvents];
+#define FE_TRACE(EV, IT)                                                                                    \
+    do {                                                                                                     \
+        if (blockIdx.x < kTraceCtas && (IT) < (uint32_t)kTraceItems && lane == 0) g_fe_trace[blockIdx.x][IT][EV] = clock64(); \
+    } while (0)
+#else
+#define FE_TRACE(EV, IT) do { } while (0)
 #endif
 constexpr int kNumWarps = 16;
 constexpr int kThreads = kNumWarps * 32;
-constexpr int kWarpMma = 4, kWarpD0 = 9, kWarpF0 = 13;       // warps 0-3: A, 4: MMA, 5-8: C, 9-12: D/E, 13-15: F
-constexpr int kFThreads = 96;
+constexpr int kWarpMma = 4, kWarpD0 = 9, kWarpF0 = 13, kWarpPub = 15;   // warps 0-3: A, 4: MMA, 5-8: C, 9-12: D/E, 13-14: F, 15: items
+constexpr int kFThreads = 64;
 constexpr int kRing = 8;                       // item slots between the ticket drawer and the other warps
 constexpr int kMelWeightCap = 1536;
 
 struct ItemSlot {
     long long item;                            // < 0: no more work
     int b, t0, nfr, T, L, n_groups;
-    float inv2[16];                            // per frame: 1 / scale^2 (undoes the power-of-two scaling on the power)
 };
 struct Control {
-    uint64_t ring_full[kRing], ring_empty[kRing], sc_full[kRing];
+    uint64_t ring_full[kRing], ring_empty[kRing];
     uint64_t a1_full[4], a1_empty[4], d1_full[4], d1_empty[4];
-    uint64_t a2_full[2], a2_empty, d2_full[2], d2_empty[2];
+    uint64_t a2_full[2], a2_empty[2], d2_full[2], d2_empty[2];
     uint64_t tile_full[2], tile_empty[2];
     ItemSlot slot[kRing];
     uint32_t tmem_base;
     int unit_counter;
+    volatile uint32_t a_progress;              // the item A warp 0 works on (the publisher stays at most three ahead of it)
     int flag;
     int pad;
     float red[48];
 };
 
-// shared-memory carve-up (bytes from the 1024-aligned base)
-constexpr uint32_t kOffA1 = 0;                                   // 4 sub-tiles x 128 rows x 128 B (hi | lo halves of K)
-constexpr uint32_t kOffA2Hi = 65536, kOffA2Lo = 98304;           // 256 rows x 128 B each
-constexpr uint32_t kOffB1 = 131072;                              // 64 rows x 128 B
-constexpr uint32_t kOffB2 = 139264;                              // 128 rows x 128 B
-constexpr uint32_t kOffP = 155648;                               // 15 x 528 floats
-constexpr uint32_t kPBytes = 32256;
+// shared-memory carve-up (bytes from the 1024-aligned base).  The stage-1 data operand lives in tensor memory.
+constexpr uint32_t kOffA2Hi = 0, kOffA2Lo = 65536;               // each: K 0..31 then K 32..63 (32 KB apart), 256 rows x 128 B
+constexpr uint32_t kA2KBlock = 32768;
+constexpr uint32_t kOffB1 = 131072;                              // hi tile, lo tile: 32 rows x 128 B each
+constexpr uint32_t kOffB2 = 139264;                              // hi K 0..31, hi K 32..63, lo K 0..31, lo K 32..63: 64 rows x 128 B each
+constexpr uint32_t kOffP = 172032;                               // 14 x 532 floats
+constexpr uint32_t kPBytes = 29824;
 constexpr uint32_t kOffMelW = kOffP + kPBytes;                   // 1536 floats
 constexpr uint32_t kOffMelIdx = kOffMelW + kMelWeightCap * 4;    // start / count / offset: 3 x 128 ints
 constexpr uint32_t kOffTile = kOffMelIdx + 3 * kMaxMels * 4;     // two [n_mels][16] float tiles (D/E -> F)
 constexpr uint32_t kTileFloats = kMaxMels * 16;
-constexpr uint32_t kOffWin = kOffTile + 2 * kTileFloats * 4;       // Hann window as [8][32 lanes][4]: lane's w[32 n1 + lane], n1 = 4c..4c+3
+constexpr uint32_t kOffWin = kOffTile + 2 * kTileFloats * 4;     // Hann window as [8][32 lanes][4]: lane's w[32 n1 + lane], n1 = 4c..4c+3
 constexpr uint32_t kOffCtl = kOffWin + 4096;
 constexpr uint32_t kSmemBytes = kOffCtl + ((sizeof(Control) + 127) & ~127u) + 1024;   // + slack for the 1024-byte alignment
 static_assert(kTileFrames * kPStride * 4 <= kPBytes, "power buffer");
 static_assert(kSmemBytes <= 232448, "shared memory per CTA");
-static_assert(kOffA2Hi % 1024 == 0 && kOffA2Lo % 1024 == 0 && kOffB1 % 1024 == 0 && kOffB2 % 1024 == 0, "swizzle atoms");
+static_assert(kOffA2Lo % 1024 == 0 && kOffB1 % 1024 == 0 && kOffB2 % 1024 == 0, "swizzle atoms");
+// tensor-memory columns (512): stage-1 accumulators, stage-1 data operand (hi | lo per sub-tile), stage-2 accumulators
+constexpr uint32_t kColD1 = 0, kColA1 = 128, kColD2 = 384;
 
 // mbarrier wait for the pipeline hand-offs: try_wait with a suspend-time hint, so a waiting warp sleeps in hardware until the
 // phase completes (or 20 us pass) instead of re-issuing the probe - with 16 warps of 5 roles on one SM the plain spin loops
@@ -119,21 +131,19 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t byte
 }
 
 __device__ __forceinline__ void group_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the four D/E warps
-__device__ __forceinline__ void f_barrier() { asm volatile("bar.sync 2, 96;" ::: "memory"); }        // the three F warps
+__device__ __forceinline__ void f_barrier() { asm volatile("bar.sync 2, 64;" ::: "memory"); }        // the two F warps
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t a) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
 }
-__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
-
-// (a, b) -> fp16 pair of the values and fp16 pair of what the rounding dropped
-__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(a, b);
-    const float2 f = __half22float2(h);
-    hi = h2_bits(h);
-    lo = h2_bits(__floats2half2_rn(a - f.x, b - f.y));
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+// what the tensor core does not read of an fp32 operand: x minus x with its 13 low mantissa bits cleared (exact)
+__device__ __forceinline__ uint32_t tf32_lo_bits(uint32_t x_bits) {
+    return __float_as_uint(__uint_as_float(x_bits) - __uint_as_float(x_bits & 0xFFFFE000u));
 }
 
 // One 512-sample block (samples [512 jb, 512 jb + 512) of the reflect-padded utterance, jb >= -1): lane takes the samples
@@ -157,42 +167,32 @@ __device__ __forceinline__ void load_block(const SampleT* __restrict__ row, int 
     }
 }
 
-// One frame = blocks (first: n1 0..15, second: n1 16..31): Hann window, power-of-two scale that puts the frame's largest
-// WINDOWED value in [1, 2) (the window can take a loud frame edge down by 100 dB: scaling by the raw maximum would leave the
-// operand in the fp16 subnormals there), fp16 (hi, lo) split, store row `r` of the stage-1 operand sub-tile.
-// Returns 1 / scale^2.
-__device__ __forceinline__ float store_frame(const float (&first)[16], const float (&second)[16], const float4* __restrict__ s_win,
-                                             uint32_t tile_addr, int r) {
-    float t[32];
-    float m = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float4 w = s_win[c * 32];                          // (this lane's) w[32 n1 + lane], n1 = 4c .. 4c+3
-        const float wv[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int n1 = 4 * c + e;
-            t[n1] = (n1 < 16 ? first[n1] : second[n1 - 16]) * wv[e];
-            m = fmaxf(m, fabsf(t[n1]));
-        }
-    }
-    uint32_t eb = __reduce_max_sync(0xffffffffu, __float_as_uint(m)) >> 23;
-    eb = eb < 65u ? 65u : (eb > 187u ? 187u : eb);
-    const float scale = __uint_as_float((254u - eb) << 23), inv = __uint_as_float(eb << 23);
-    const uint32_t row_addr = tile_addr + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
-    const int sw = r & 7;
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+// Half a frame = one 512-sample block in its role as n1 = 16 h .. 16 h + 15 of the frame: Hann window, then columns
+// [16 h, 16 h + 16) of the row (frame, n2 = lane) of the stage-1 operand in tensor memory get the windowed values themselves
+// (the tensor core reads their 19 leading bits) and columns 32 + [16 h, 16 h + 16) what it does not read of them.
+template <int H>
+__device__ __forceinline__ void store_half_frame(const float (&x)[16], const float4* __restrict__ g_win, uint32_t taddr) {
+    uint32_t t[16];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int n1 = 8 * c + 2 * e;
-            split_pair(t[n1] * scale, t[n1 + 1] * scale, hi[e], lo[e]);         // the scaling is exact
-        }
-        st_shared_v4(row_addr + (uint32_t)((c ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);       // K = n1        (hi half)
-        st_shared_v4(row_addr + (uint32_t)(((4 + c) ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]); // K = 32 + n1   (lo half)
+        const float4 w = g_win[(4 * H + c) * 32];                // (this lane's) w[32 n1 + lane], n1 = 16 H + 4c .. + 3
+        t[4 * c + 0] = __float_as_uint(x[4 * c + 0] * w.x);
+        t[4 * c + 1] = __float_as_uint(x[4 * c + 1] * w.y);
+        t[4 * c + 2] = __float_as_uint(x[4 * c + 2] * w.z);
+        t[4 * c + 3] = __float_as_uint(x[4 * c + 3] * w.w);
     }
-    return inv * inv;
+    tmem_st_32x16(taddr + 16u * H, t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = tf32_lo_bits(t[i]);
+    tmem_st_32x16(taddr + 32u + 16u * H, t);
 }
 
 template <typename SampleT>
@@ -215,25 +215,24 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
     if (tid == 0) {
         for (int i = 0; i < kRing; ++i) {
             mbar_init(&ctl->ring_full[i], 1);
-            mbar_init(&ctl->ring_empty[i], 15);                  // A warps 1-3, MMA warp, 4 C warps, 4 D/E warps, 3 F warps
-            mbar_init(&ctl->sc_full[i], 4);
+            mbar_init(&ctl->ring_empty[i], 15);                  // 4 A warps, MMA warp, 4 C warps, 4 D/E warps, 2 F warps
         }
         for (int i = 0; i < 4; ++i) {
-            mbar_init(&ctl->a1_full[i], 1);
+            mbar_init(&ctl->a1_full[i], 4);                      // every A warp owns one lane quadrant of every sub-tile
             mbar_init(&ctl->a1_empty[i], 1);
             mbar_init(&ctl->d1_full[i], 1);
             mbar_init(&ctl->d1_empty[i], 4);
         }
-        mbar_init(&ctl->a2_full[0], 8);                          // frames 0..7: two sub-tiles x four C warps
-        mbar_init(&ctl->a2_full[1], 16);                         // every frame has its k1 = 16 row in the second tile
-        mbar_init(&ctl->a2_empty, 1);
         for (int i = 0; i < 2; ++i) {
+            mbar_init(&ctl->a2_full[i], 7);                      // seven frames per stage-2 tile (one arrival per C warp and frame)
+            mbar_init(&ctl->a2_empty[i], 1);
             mbar_init(&ctl->d2_full[i], 1);
             mbar_init(&ctl->d2_empty[i], 4);
             mbar_init(&ctl->tile_full[i], 4);
-            mbar_init(&ctl->tile_empty[i], 3);
+            mbar_init(&ctl->tile_empty[i], 2);
         }
         ctl->unit_counter = 0;
+        ctl->a_progress = 0;
         fence_barrier_init();
     }
     if (warp == kWarpMma) tmem_alloc<512>(&ctl->tmem_base);
@@ -243,17 +242,15 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
         uint4* s1 = reinterpret_cast<uint4*>(smem + kOffB1);
         uint4* s2 = reinterpret_cast<uint4*>(smem + kOffB2);
         for (int i = tid; i < 512; i += kThreads) s1[i] = __ldg(g1 + i);
-        for (int i = tid; i < 1024; i += kThreads) s2[i] = __ldg(g2 + i);
+        for (int i = tid; i < 2048; i += kThreads) s2[i] = __ldg(g2 + i);
         for (int i = tid; i < kMelWeightCap; i += kThreads) s_melw[i] = __ldg(p.tc.mel_weight + i);   // (zero behind the taps)
         for (int i = tid; i < p.n_mels; i += kThreads) {
             s_mel_start[i] = __ldg(p.tc.mel_start + i);
             s_mel_count[i] = __ldg(p.tc.mel_count + i);
             s_mel_offset[i] = __ldg(p.tc.mel_offset + i);
         }
-        for (int i = tid; i < 1024; i += kThreads) {               // window[32 n1 + l] -> [n1 / 4][l][n1 % 4]
-            const int n1 = i >> 5, l = i & 31;
-            reinterpret_cast<float*>(smem + kOffWin)[((n1 >> 2) * 32 + l) * 4 + (n1 & 3)] = __ldg(p.tables.window + i);
-        }
+        for (int i = tid; i < 256; i += kThreads)
+            reinterpret_cast<uint4*>(smem + kOffWin)[i] = __ldg(reinterpret_cast<const uint4*>(p.tc.win_img) + i);
         for (int i = tid; i < (int)(kPBytes / 4); i += kThreads) s_P[i] = 0.f;       // bins 513..527 stay zero for good
         fence_proxy_async();                                     // the operand images are read by the tensor core
     }
@@ -265,151 +262,90 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
 
     if (warp < 4) {
         // =============================== A: samples -> stage-1 operand ===============================================
-        const float4* s_win = reinterpret_cast<const float4*>(smem + kOffWin) + lane;
-        // ticket pipeline of the drawing lane: i0 / L0 = this iteration's item and its length, i1 = the next item
-        // (32-bit item indices: one launch has fewer than 2^31 items; a ticket outside [0, total) means "no more work")
-        const int total_i = (int)total_items;
-        int i0 = -1, i1 = -1;
-        int L0 = 0;
-        auto length_of = [&](int item) -> int {
-            if (item < 0) return 0;
-            const int b = item / p.groups_max;
-            int L = p.lengths ? min(__ldg(p.lengths + b), p.n_samples) : p.n_samples;
-            if (p.max_samples > 0) L = min(L, p.max_samples);
-            return L;
+        const float4* g_win = reinterpret_cast<const float4*>(smem + kOffWin) + lane;
+        struct WarpItem {                                        // what an A warp needs of an item: its row, length, first block, frames
+            const SampleT* row;
+            int L, jb, nf;
+            __device__ __forceinline__ void read(const ItemSlot& sl, const FrontendParams& p, int warp) {
+                const bool more = sl.item >= 0;
+                row = static_cast<const SampleT*>(p.wave) + (int64_t)(more ? sl.b : 0) * p.wave_stride;
+                L = sl.L;
+                jb = sl.t0 + 4 * warp - 1;
+                nf = more ? min(4, max(sl.nfr - 4 * warp, 0)) : 0;
+            }
         };
-        auto draw = [&]() -> int {
-            const unsigned long long t = atomicAdd(p.work_counter, 1ULL) - p.work_base;      // wraps to huge if the base is ahead
-            return t < (unsigned long long)total_i ? (int)t : -1;
-        };
-        // Request the samples of a coming item into L2 (one bulk-prefetch instruction for its 16 blocks): the A warps hold
-        // only 8 KB of loads in flight per SM, which at HBM latency is ~1 TB/s for the whole chip; at L2 latency it is enough.
-        auto prefetch_item = [&](int item, int Li) {
-            if (item < 0 || Li <= kNfft / 2) return;
-            const int b = item / p.groups_max, g = item - b * p.groups_max;
-            const int n_lo = max(0, (g * kTileFrames - 1) * kHop), n_hi = min(Li, (g * kTileFrames + kTileFrames) * kHop);
-            if (n_hi <= n_lo) return;
-            const char* base = reinterpret_cast<const char*>(static_cast<const SampleT*>(p.wave) + (int64_t)b * p.wave_stride);
-            uintptr_t lo = reinterpret_cast<uintptr_t>(base + (size_t)n_lo * sizeof(SampleT));
-            uintptr_t hi = reinterpret_cast<uintptr_t>(base + (size_t)n_hi * sizeof(SampleT));
-            lo = (lo + 15) & ~(uintptr_t)15;
-            hi &= ~(uintptr_t)15;
-#if SIR_FE_PREFETCH == 1
-            if (hi > lo) prefetch_l2_bulk(reinterpret_cast<const void*>(lo), (uint32_t)(hi - lo));
-#elif SIR_FE_PREFETCH == 2
-            for (uintptr_t a = lo; a < hi; a += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-#endif
-        };
-        if (warp == 0 && lane == 0) {
-            i0 = draw();
-            i1 = draw();
-            L0 = length_of(i0);
-            prefetch_item(i0, L0);
-        }
-        uint32_t pub = 0;                                        // slots published so far (drawing lane)
-        bool pub_end = false;
+        WarpItem cur{nullptr, 0, 0, 0}, nxt{nullptr, 0, 0, 0};
+        float x0[16], x1[16], x2[16], x3[16], x4[16];
         for (uint32_t it = 0;; ++it) {
             const int rs = it % kRing;
             const uint32_t rph = (it / kRing) & 1u;
-            if (warp == 0) {
-                if (lane == 0) {
-                    // publish ONE ITEM AHEAD: the other warps never wait for this warp to finish its own frames first
-                    while (!pub_end && pub <= it + 1) {
-                        const int ps = pub % kRing;
-                        pipe_wait(&ctl->ring_empty[ps], ((pub / kRing) & 1u) ^ 1u);
-                        ItemSlot& sl = ctl->slot[ps];
-                        for (;;) {                               // skip tickets beyond an utterance's last group (ragged batches)
-                            if (i0 < 0) {
-                                sl.item = -1;
-                                pub_end = true;
-                                break;
-                            }
-                            const int b = i0 / p.groups_max, g = i0 - b * p.groups_max;
-                            const bool valid = L0 > kNfft / 2;
-                            const int T = valid ? 1 + L0 / kHop : 0;
-                            const int n_groups = valid ? (T + kTileFrames - 1) / kTileFrames : 1;
-                            if (g < n_groups) {
-                                sl.item = i0;
-                                sl.b = b;
-                                sl.t0 = g * kTileFrames;
-                                sl.nfr = valid ? min(kTileFrames, T - g * kTileFrames) : 0;
-                                sl.T = T;
-                                sl.L = L0;
-                                sl.n_groups = n_groups;
-                                break;
-                            }
-                            const int L1 = length_of(i1);
-                            i0 = i1;
-                            L0 = L1;
-                            i1 = draw();
-                        }
-                        mbar_arrive(&ctl->ring_full[ps]);
-                        ++pub;
-                        if (!pub_end) {                          // advance: the next item's samples are requested into L2, the
-                            const int L1 = length_of(i1);        // draw after it is in flight while this item is processed
-                            prefetch_item(i1, L1);
-                            i0 = i1;
-                            L0 = L1;
-                            i1 = draw();
-                        }
-                    }
-                }
-                __syncwarp();
-            }
+            if (warp == 0 && lane == 0) ctl->a_progress = it;
             pipe_wait(&ctl->ring_full[rs], rph);
-            ItemSlot& sl = ctl->slot[rs];
-            if (sl.item < 0) break;
-            const int L = sl.L, t0 = sl.t0, nfr = sl.nfr;
-            const SampleT* __restrict__ row = static_cast<const SampleT*>(p.wave) + (int64_t)sl.b * p.wave_stride;
-            const int f0 = 4 * warp;
-            if (f0 < nfr) {
-                const uint32_t tile_addr = sbase + kOffA1 + (uint32_t)warp * 16384u;
-                // blocks t0 + f0 - 1 .. t0 + f0 + 3: frame j = (block j, block j + 1); block j + 2 is requested before frame j
-                // is processed
-                float xa[16], xb[16], xc[16];
-                const int jb = t0 + f0 - 1, nf = min(4, nfr - f0);
-                // step s requests block jb + s and - from s = 2 on - turns blocks (s - 2, s - 1) into frame s - 2: one copy of
-                // the load code and one of the frame code (rolled: the inlined copies thrashed the instruction cache), and
-                // every block is requested two frames before it is needed
-#pragma unroll 1
-                for (int step = 0; step < nf + 2; ++step) {
-                    if (step <= nf) load_block(row, L, jb + step, lane, xc);
-                    if (step == 2) pipe_wait(&ctl->a1_empty[warp], (it & 1u) ^ 1u);   // stage 1 of the previous item has read this sub-tile
-                    if (step >= 2) {
-                        const float i2 = store_frame(xa, xb, s_win, tile_addr, 32 * (step - 2) + lane);
-                        if (lane == 0) sl.inv2[f0 + step - 2] = i2;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        xa[i] = xb[i];
-                        xb[i] = xc[i];
-                    }
+            if (ctl->slot[rs].item < 0) break;
+            if (warp == 0) FE_TRACE(0, it);
+            // This warp's frames 4 warp .. 4 warp + 3 need blocks b0..b4 (frame j = blocks j, j + 1).  The work is BLOCK by block:
+            // block k is the upper half (n1 = 16..31) of frame k - 1 and the lower half of frame k, so only the block in hand
+            // and the blocks in flight hold registers.  Five buffers with static roles (buffer k = block k of every item); after
+            // block k the block TWO positions further in the warp's stream (b2, b3, b4, then b0, b1 of the NEXT item, which is
+            // published two ahead) is requested: every load is in flight during two blocks of arithmetic, also across item
+            // boundaries.  (A rolled three-buffer rotation - the first version - waited a fifth of the warp's time for the block
+            // requested one frame earlier and spent more MOVs rotating buffers than FMULs on the window.)
+            if (it == 0) {
+                cur.read(ctl->slot[rs], p, warp);
+                if (cur.nf > 0) {
+                    load_block(cur.row, cur.L, cur.jb + 0, lane, x0);
+                    load_block(cur.row, cur.L, cur.jb + 1, lane, x1);
                 }
-                fence_proxy_async();                             // generic-proxy stores -> visible to the tensor core
-            } else {
-                pipe_wait(&ctl->a1_empty[warp], (it & 1u) ^ 1u); // (keeps the barrier phases in step)
             }
+            {                                                    // the item after this one (published two ahead)
+                const int ns = (it + 1) % kRing;
+                pipe_wait(&ctl->ring_full[ns], ((it + 1) / kRing) & 1u);
+                nxt.read(ctl->slot[ns], p, warp);
+            }
+            if (warp == 0) FE_TRACE(1, it);
+            const uint32_t lane_addr = tmem_base + kColA1 + ((uint32_t)(warp * 32) << 16);
+            const uint32_t ph = (it & 1u) ^ 1u;
+            // block K in buffer XK: closes frame K - 1 (sub-tile K - 1), opens frame K; then the request two positions ahead
+#define SIR_FE_BLOCK(K, XK, REQ)                                                                                          \
+            if (K >= 1) {                                                                                                \
+                if (K - 1 < cur.nf) {                                                                                    \
+                    store_half_frame<1>(XK, g_win, lane_addr + (K >= 1 ? K - 1 : 0) * 64u);                                           \
+                    tmem_st_wait();                                                                                      \
+                }                                                                                                        \
+                tc_fence_before();                                                                                       \
+                __syncwarp();                                                                                            \
+                if (lane == 0) mbar_arrive(&ctl->a1_full[K >= 1 ? K - 1 : 0]);                                                      \
+                if (warp == 0) FE_TRACE(3 + 2 * (K - 1), it);                                                            \
+            }                                                                                                            \
+            if (K <= 3) {                                                                                                \
+                pipe_wait(&ctl->a1_empty[K], ph);            /* stage 1 of the previous item has read this sub-tile */   \
+                if (warp == 0) FE_TRACE(2 + 2 * K, it);                                                                  \
+                tc_fence_after();                                                                                        \
+                if (K < cur.nf) store_half_frame<0>(XK, g_win, lane_addr + K * 64u);                                     \
+            }                                                                                                            \
+            REQ
+            SIR_FE_BLOCK(0, x0, if (cur.nf >= 2) load_block(cur.row, cur.L, cur.jb + 2, lane, x2);)
+            SIR_FE_BLOCK(1, x1, if (cur.nf >= 3) load_block(cur.row, cur.L, cur.jb + 3, lane, x3);)
+            SIR_FE_BLOCK(2, x2, if (cur.nf >= 4) load_block(cur.row, cur.L, cur.jb + 4, lane, x4);)
+            SIR_FE_BLOCK(3, x3, if (nxt.nf > 0) load_block(nxt.row, nxt.L, nxt.jb + 0, lane, x0);)
+            SIR_FE_BLOCK(4, x4, if (nxt.nf > 0) load_block(nxt.row, nxt.L, nxt.jb + 1, lane, x1);)
+#undef SIR_FE_BLOCK
+            cur = nxt;
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&ctl->a1_full[warp]);
-                mbar_arrive(&ctl->sc_full[rs]);
-                if (warp != 0) mbar_arrive(&ctl->ring_empty[rs]);
-            }
+            if (lane == 0) mbar_arrive(&ctl->ring_empty[rs]);
         }
     } else if (warp == kWarpMma) {
         // =============================== MMA issue ===================================================================
         // Two streams of work, polled in turn: stage 1 of item i1 (sub-tile s1) and stage 2 of item i2 (row tile m2), i2
         // trailing i1.  All 32 lanes walk the loop (uniform), one elected lane issues.
-        constexpr uint32_t id1a = make_idesc_f16(128, 64), id1b = make_idesc_f16(128, 32);
-        constexpr uint32_t id2a = make_idesc_f16(128, 128), id2b = make_idesc_f16(128, 64);
-        const uint64_t b1 = make_kmajor_desc<128>(sbase + kOffB1), b2 = make_kmajor_desc<128>(sbase + kOffB2);
-        uint32_t i1 = 0, s1 = 0, i2 = 0, m2 = 0, idle = 0;
+        constexpr uint32_t id1 = make_idesc_tf32(128, 32), id2 = make_idesc_tf32(128, 64);
+        const uint64_t b1_hi = make_kmajor_desc<128>(sbase + kOffB1), b1_lo = make_kmajor_desc<128>(sbase + kOffB1 + 4096u);
+        uint32_t i1 = 0, s1 = 0, i2 = 0, m2 = 0, c2 = 0, idle = 0;
         bool have_slot = false, end1 = false;
         for (;;) {
             bool progressed = false;
-            // stage 1 first: its four MMAs are short and release an A warp; a stage 2 issued ahead of them (the tensor pipe
-            // executes in order) would keep that warp waiting for ~1,000 cycles
-#if SIR_FE_S1_FIRST
+            // stage 1 first: its MMAs are short and release the A warps; a stage 2 issued ahead of them (the tensor pipe
+            // executes in order) would keep those warps waiting for ~1,000 cycles
             if (!end1) {
                 if (!have_slot) {
                     const int rs = i1 % kRing;
@@ -424,13 +360,17 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                 }
                 if (have_slot && mbar_test_wait(&ctl->a1_full[s1], i1 & 1u) && mbar_test_wait(&ctl->d1_empty[s1], (i1 & 1u) ^ 1u)) {
                     tc_fence_after();
+                    FE_TRACE(10 + s1, i1);
                     if (elect_one_sync()) {
-                        const uint64_t a = make_kmajor_desc<128>(sbase + kOffA1 + s1 * 16384u);
-                        const uint32_t d = tmem_base + s1 * 64u;
-                        umma_f16(d, desc_advance_k(a, 0), desc_advance_k(b1, 0), id1a, 0u);      // hi . [B_hi; B_lo]
-                        umma_f16(d, desc_advance_k(a, 16), desc_advance_k(b1, 16), id1a, 1u);
-                        umma_f16(d, desc_advance_k(a, 32), desc_advance_k(b1, 0), id1b, 1u);     // lo . B_hi
-                        umma_f16(d, desc_advance_k(a, 48), desc_advance_k(b1, 16), id1b, 1u);
+                        // A from tensor memory (one column per K element, 8 per instruction); K = n1 = 32 in four steps
+                        const uint32_t d = tmem_base + kColD1 + s1 * 32u;
+                        const uint32_t a_hi = tmem_base + kColA1 + s1 * 64u, a_lo = a_hi + 32u;
+#pragma unroll
+                        for (uint32_t kk = 0; kk < 4; ++kk) umma_tf32_ts(d, a_hi + 8u * kk, b1_hi + 2u * kk, id1, kk ? 1u : 0u);
+#pragma unroll
+                        for (uint32_t kk = 0; kk < 4; ++kk) umma_tf32_ts(d, a_hi + 8u * kk, b1_lo + 2u * kk, id1, 1u);
+#pragma unroll
+                        for (uint32_t kk = 0; kk < 4; ++kk) umma_tf32_ts(d, a_lo + 8u * kk, b1_hi + 2u * kk, id1, 1u);
                         umma_commit(&ctl->a1_empty[s1]);
                         umma_commit(&ctl->d1_full[s1]);
                     }
@@ -443,81 +383,42 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                     progressed = true;
                 }
             }
-            if (i2 < i1 && mbar_test_wait(&ctl->a2_full[m2], i2 & 1u) && mbar_test_wait(&ctl->d2_empty[m2], (i2 & 1u) ^ 1u)) {
-                tc_fence_after();
-                if (elect_one_sync()) {
-                    const uint64_t ah = make_kmajor_desc<128>(sbase + kOffA2Hi + m2 * 16384u);
-                    const uint64_t al = make_kmajor_desc<128>(sbase + kOffA2Lo + m2 * 16384u);
-                    const uint32_t d = tmem_base + 256u + m2 * 128u;
-#pragma unroll
-                    for (int k = 0; k < 64; k += 16) umma_f16(d, desc_advance_k(ah, k), desc_advance_k(b2, k), id2a, k ? 1u : 0u);
-#pragma unroll
-                    for (int k = 0; k < 64; k += 16) umma_f16(d, desc_advance_k(al, k), desc_advance_k(b2, k), id2b, 1u);
-                    umma_commit(&ctl->d2_full[m2]);
-                    if (m2 == 1) umma_commit(&ctl->a2_empty);
-                }
-                __syncwarp();
-                if (++m2 == 2) {
-                    m2 = 0;
-                    ++i2;
-                }
-                progressed = true;
-            }
-#else
-            if (i2 < i1 && mbar_test_wait(&ctl->a2_full[m2], i2 & 1u) && mbar_test_wait(&ctl->d2_empty[m2], (i2 & 1u) ^ 1u)) {
-                tc_fence_after();
-                if (elect_one_sync()) {
-                    const uint64_t ah = make_kmajor_desc<128>(sbase + kOffA2Hi + m2 * 16384u);
-                    const uint64_t al = make_kmajor_desc<128>(sbase + kOffA2Lo + m2 * 16384u);
-                    const uint32_t d = tmem_base + 256u + m2 * 128u;
-#pragma unroll
-                    for (int k = 0; k < 64; k += 16) umma_f16(d, desc_advance_k(ah, k), desc_advance_k(b2, k), id2a, k ? 1u : 0u);
-#pragma unroll
-                    for (int k = 0; k < 64; k += 16) umma_f16(d, desc_advance_k(al, k), desc_advance_k(b2, k), id2b, 1u);
-                    umma_commit(&ctl->d2_full[m2]);
-                    if (m2 == 1) umma_commit(&ctl->a2_empty);
-                }
-                __syncwarp();
-                if (++m2 == 2) {
-                    m2 = 0;
-                    ++i2;
-                }
-                progressed = true;
-            }
-            if (!end1) {
-                if (!have_slot) {
-                    const int rs = i1 % kRing;
-                    if (mbar_test_wait(&ctl->ring_full[rs], (i1 / kRing) & 1u)) {
-                        const bool more = ctl->slot[rs].item >= 0;
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&ctl->ring_empty[rs]);
-                        if (more) have_slot = true;
-                        else end1 = true;
-                        progressed = true;
-                    }
-                }
-                if (have_slot && mbar_test_wait(&ctl->a1_full[s1], i1 & 1u) && mbar_test_wait(&ctl->d1_empty[s1], (i1 & 1u) ^ 1u)) {
+            // stage 2 of a tile in SIX CHUNKS of four instructions (~200 cycles of the in-order tensor pipe), with a look at
+            // stage 1 between them: issued in one go (24 instructions, > 1,100 cycles) it kept the A warps waiting for the
+            // stage-1 MMAs queued behind it - a third of their time
+            if (c2 > 0 || (mbar_test_wait(&ctl->a2_full[m2], i2 & 1u) && mbar_test_wait(&ctl->d2_empty[m2], (i2 & 1u) ^ 1u))) {
+                if (c2 == 0) {
                     tc_fence_after();
-                    if (elect_one_sync()) {
-                        const uint64_t a = make_kmajor_desc<128>(sbase + kOffA1 + s1 * 16384u);
-                        const uint32_t d = tmem_base + s1 * 64u;
-                        umma_f16(d, desc_advance_k(a, 0), desc_advance_k(b1, 0), id1a, 0u);      // hi . [B_hi; B_lo]
-                        umma_f16(d, desc_advance_k(a, 16), desc_advance_k(b1, 16), id1a, 1u);
-                        umma_f16(d, desc_advance_k(a, 32), desc_advance_k(b1, 0), id1b, 1u);     // lo . B_hi
-                        umma_f16(d, desc_advance_k(a, 48), desc_advance_k(b1, 16), id1b, 1u);
-                        umma_commit(&ctl->a1_empty[s1]);
-                        umma_commit(&ctl->d1_full[s1]);
-                    }
-                    __syncwarp();
-                    if (++s1 == 4) {
-                        s1 = 0;
-                        ++i1;
-                        have_slot = false;
-                    }
-                    progressed = true;
+                    FE_TRACE(14 + m2, i2);
                 }
+                if (elect_one_sync()) {
+                    // K = (n2, re / im) = 64 = two 128-byte column blocks of four K = 8 steps; chunk = (pass, column block):
+                    // hi.hi, hi.lo, lo.hi
+                    const uint32_t d = tmem_base + kColD2 + m2 * 64u;
+#pragma unroll 1
+                    for (uint32_t c = c2; c < c2 + SIR_FE_CHUNK; ++c) {
+                        const uint32_t pass = c >> 1, kb = c & 1u;
+                        const uint64_t a = make_kmajor_desc<128>(sbase + (pass == 2 ? kOffA2Lo : kOffA2Hi) + kb * kA2KBlock + m2 * 16384u);
+                        const uint64_t b = make_kmajor_desc<128>(sbase + kOffB2 + (pass == 1 ? 16384u : 0u) + kb * 8192u);
+#pragma unroll
+                        for (uint32_t kk = 0; kk < 4; ++kk) umma_tf32(d, a + 2u * kk, b + 2u * kk, id2, (c | kk) ? 1u : 0u);
+                    }
+                    if (c2 + SIR_FE_CHUNK == 6) {
+                        umma_commit(&ctl->d2_full[m2]);
+                        umma_commit(&ctl->a2_empty[m2]);
+                    }
+                }
+                __syncwarp();
+                c2 += SIR_FE_CHUNK;
+                if (c2 == 6) {
+                    c2 = 0;
+                    if (++m2 == 2) {
+                        m2 = 0;
+                        ++i2;
+                    }
+                }
+                progressed = true;
             }
-#endif
             if (end1 && i2 == i1) break;
             if (progressed) {
                 idle = 0;
@@ -528,13 +429,16 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
         }
     } else if (warp < kWarpD0) {
         // =============================== C: D1 -> twiddle -> stage-2 operand ========================================
-        const int q = warp & 3;                                  // TMEM lane quadrant = frame slot inside a sub-tile
+        const int q = warp & 3;                                  // TMEM lane quadrant: frames 4q .. 4q+3 of the item
         float2 tw[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) tw[k] = __ldg(reinterpret_cast<const float2*>(p.tc.twiddle) + lane * 16 + k);
-        uint32_t lane_off[8];                                    // swizzled position of this lane's (re, im) word in a row
+        // this lane's (re, im) pair = K elements 2 n2, 2 n2 + 1 of a stage-2 row: 128-byte column block n2 / 16, 16-byte chunk
+        // (n2 % 16) / 2 XOR-ed with the row index inside its 8-row atom, byte (n2 & 1) * 8
+        const uint32_t kb_off = (uint32_t)(lane >> 4) * kA2KBlock + (uint32_t)((lane & 1) << 3);
+        uint32_t lane_off[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) lane_off[c] = (uint32_t)((((lane >> 2) ^ c) << 4) | ((lane & 3) << 2));
+        for (int c = 0; c < 8; ++c) lane_off[c] = kb_off + (uint32_t)(((((lane & 15) >> 1) ^ c)) << 4);
         for (uint32_t it = 0;; ++it) {
             const int rs = it % kRing;
             pipe_wait(&ctl->ring_full[rs], (it / kRing) & 1u);
@@ -543,29 +447,29 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->ring_empty[rs]);
             if (item < 0) break;
-            bool a2_ready = false;
             for (int s = 0; s < 4; ++s) {
-                const int f = 4 * s + q;
+                // sub-tile s holds frame 4 q + s in quadrant q.  Its 17 stage-2 rows go to one of two SELF-CONTAINED 7-frame
+                // tiles, in the order the sub-tiles complete: tile 0 = sub-tile 0 and quadrants 0..2 of sub-tile 1, tile 1 =
+                // the rest (frames 14, 15 do not exist).  Position t in the tile: rows 16 t + k1 (k1 < 16) and 112 + t (k1 = 16).
+                // The two tiles are a true double buffer: stage 2 of one runs while the other is written.
+                const int f = 4 * q + s;
+                const int tile = s == 0 ? 0 : (s == 1 ? (q == 3 ? 1 : 0) : 1);
+                const int t = s == 0 ? q : (s == 1 ? (q == 3 ? 0 : 4 + q) : (s == 2 ? 1 + q : 4 + q));
                 const bool valid = f < nfr;
                 pipe_wait(&ctl->d1_full[s], it & 1u);
+                if (q == 0) FE_TRACE(16 + s, it);
                 tc_fence_after();
                 float y[32];
-                if (valid) {
-                    float u[32];
-                    const uint32_t trow = tmem_base + (uint32_t)s * 64u + ((uint32_t)(q * 32) << 16);
-                    tmem_ld_32x32_pair(trow, trow + 32, y, u);   // (hi.hi + lo.hi), (hi.lo)
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) y[i] += u[i];
-                }
+                if (valid) tmem_ld_32x32(tmem_base + kColD1 + (uint32_t)s * 32u + ((uint32_t)(q * 32) << 16), y);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctl->d1_empty[s]);
-                if (!a2_ready) {                                 // stage 2 of the previous item has read the operand
-                    pipe_wait(&ctl->a2_empty, (it & 1u) ^ 1u);
-                    a2_ready = true;
-                }
+                if (f >= kTileFrames) continue;                  // (q = 3, s >= 2: no such frame, no stage-2 arrival expected)
+                pipe_wait(&ctl->a2_empty[tile], (it & 1u) ^ 1u); // stage 2 of the previous item has read this tile
+                if (q == 0 && s == 0) FE_TRACE(20, it);
                 if (valid) {
-                    const uint32_t hi_base = sbase + kOffA2Hi + (uint32_t)f * 2048u;          // rows 16 f + k1
+                    const uint32_t tile_base = sbase + kOffA2Hi + (uint32_t)tile * 16384u;
+                    const uint32_t hi_base = tile_base + (uint32_t)t * 2048u;                 // rows 16 t + k1
 #pragma unroll
                     for (int k1 = 0; k1 < 16; ++k1) {
                         float re, im;
@@ -577,27 +481,22 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                             re = a * c - b * d;
                             im = fmaf(a, d, b * c);
                         }
-                        uint32_t hi, lo;
-                        split_pair(re, im, hi, lo);
+                        const uint32_t rb = __float_as_uint(re), ib = __float_as_uint(im);
                         const uint32_t addr = hi_base + (uint32_t)k1 * 128u + lane_off[k1 & 7];
-                        st_shared_b32(addr, hi);
-                        st_shared_b32(addr + (kOffA2Lo - kOffA2Hi), lo);
+                        st_shared_v2(addr, rb, ib);              // (the tensor core reads the 19 leading bits)
+                        st_shared_v2(addr + (kOffA2Lo - kOffA2Hi), tf32_lo_bits(rb), tf32_lo_bits(ib));
                     }
-                    {                                            // k1 = 16 (real Y): row 240 + f
-                        uint32_t hi, lo;
-                        split_pair(y[1] * tw[15].x, y[1] * tw[15].y, hi, lo);
-                        const uint32_t addr = sbase + kOffA2Hi + (uint32_t)(240 + f) * 128u +
-                                              (uint32_t)((((lane >> 2) ^ (f & 7)) << 4) | ((lane & 3) << 2));
-                        st_shared_b32(addr, hi);
-                        st_shared_b32(addr + (kOffA2Lo - kOffA2Hi), lo);
+                    {                                            // k1 = 16 (real Y): row 112 + t
+                        const uint32_t rb = __float_as_uint(y[1] * tw[15].x), ib = __float_as_uint(y[1] * tw[15].y);
+                        const uint32_t addr = tile_base + (uint32_t)(112 + t) * 128u + kb_off + (uint32_t)(((((lane & 15) >> 1) ^ (t & 7))) << 4);
+                        st_shared_v2(addr, rb, ib);
+                        st_shared_v2(addr + (kOffA2Lo - kOffA2Hi), tf32_lo_bits(rb), tf32_lo_bits(ib));
                     }
                     fence_proxy_async();
                 }
                 __syncwarp();
-                if (lane == 0) {
-                    if (f < 8) mbar_arrive(&ctl->a2_full[0]);
-                    mbar_arrive(&ctl->a2_full[1]);
-                }
+                if (lane == 0) mbar_arrive(&ctl->a2_full[tile]);
+                if (q == 0 && s == 3) FE_TRACE(21, it);
             }
         }
     } else if (warp < kWarpF0) {
@@ -617,12 +516,17 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
 #pragma unroll 1
             for (int m = 0; m < 2; ++m) {
                 pipe_wait(&ctl->d2_full[m], it & 1u);
+                if (q == 0) FE_TRACE(22 + m, it);
                 tc_fence_after();
-                const int R = 128 * m + 32 * q + lane;
-                const int f = R < 240 ? R >> 4 : R - 240, k1 = R < 240 ? R & 15 : 16;
-                const bool valid = f < nfr && R != 255;
+                // row r of tile m: position t = r / 16 with k1 = r % 16 (r < 112), or t = r - 112 with k1 = 16 (r < 119);
+                // tile 0: t < 4 is frame 4 t, else 4 (t - 4) + 1; tile 1: t = 0 is frame 13, t = 1..3 frames 4 (t - 1) + 2,
+                // t = 4..6 frames 4 (t - 4) + 3 (the C warps' order of completion)
+                const int r = 32 * q + lane;
+                const int t = r < 112 ? r >> 4 : r - 112, k1 = r < 112 ? r & 15 : 16;
+                const int f = m == 0 ? (t < 4 ? 4 * t : 4 * (t - 4) + 1) : (t == 0 ? 13 : (t < 4 ? 4 * (t - 1) + 2 : 4 * (t - 4) + 3));
+                const bool valid = r < 119 && f < nfr;
                 if (__any_sync(0xffffffffu, valid)) {
-                    const uint32_t trow = tmem_base + 256u + (uint32_t)m * 128u + ((uint32_t)(q * 32) << 16);
+                    const uint32_t trow = tmem_base + kColD2 + (uint32_t)m * 64u + ((uint32_t)(q * 32) << 16);
                     float* Pf = s_P + f * kPStride;
 #pragma unroll 1
                     for (int j = 0; j < 2; ++j) {                // (rolled: code size)
@@ -637,12 +541,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                             base = 512 - k1; step = -32; count = k1 == 0 ? 1 : (k1 == 16 ? 0 : 16);
                         }
                         if (!valid) count = 0;
-                        float v[32], u[32];
-                        tmem_ld_32x32_pair(trow + 32 * j, trow + 64 + 32 * j, v, u);
+                        float v[32];
+                        tmem_ld_32x32(trow + 32 * j, v);
                         float* dst = Pf + base;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float re = v[2 * i] + u[2 * i], im = v[2 * i + 1] + u[2 * i + 1];
+                            const float re = v[2 * i], im = v[2 * i + 1];
                             const float pw = fmaf(re, re, im * im);
                             if (i < count) dst[step * i] = pw;
                         }
@@ -652,11 +556,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctl->d2_empty[m]);
             }
-            pipe_wait(&ctl->sc_full[rs], (it / kRing) & 1u);     // the A warps' per-frame scales
             const uint32_t buf = it & 1u;
             float* tile = s_tile + buf * kTileFloats;
             pipe_wait(&ctl->tile_empty[buf], ((it >> 1) & 1u) ^ 1u);   // the F warps have drained this tile
+            if (q == 0) FE_TRACE(24, it);
             group_barrier();                                     // P complete
+            if (q == 0) FE_TRACE(25, it);
             // ---- sparse mel taps: lane = (band, frame).  The 16 lanes of a half-warp read the same four taps (broadcast)
             // and their own frame's four bins (rows 532 floats apart: conflict-free LDS.128).  A warp takes QUADS of
             // neighbouring bands (4q..4q+3; the host pads their tap runs to one length), two bands per lane, the loads of
@@ -665,7 +570,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                 const int w = warp - kWarpD0, h = lane >> 4, f = lane & 15;
                 const int n_quads = (p.n_mels + 3) >> 2;
                 const float* Pf = s_P + (f < nfr ? f : 0) * kPStride;
-                const float i2 = sl.inv2[f < nfr ? f : 0];
                 for (int pq = w; pq < n_quads; pq += 4) {
                     const int band0 = 4 * pq + h, band1 = band0 + 2;
                     const int bq = min(band0, p.n_mels - 1), br = min(band1, p.n_mels - 1);
@@ -686,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                         wva = nwa; xa = nxa; wvb = nwb; xb = nxb;
                     }
                     if (f < nfr) {
-                        float va = (a0 + a1) * i2, vb = (b0 + b1) * i2;
+                        float va = a0 + a1, vb = b0 + b1;
                         // 10 log10(x) = (10 log10 2) lg2(x): lg2.approx is good to ~1e-7 relative here, i.e. ~1e-6 dB
                         if (p.mode != SIR_OUT_MEL_POWER) {
                             va = 3.01029995663981195f * __log2f(fmaxf(va, 1e-10f));
@@ -700,11 +604,107 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->tile_full[buf]);    // release: this warp's tile entries
             group_barrier();                                     // every warp is done with P
+            if (q == 0) FE_TRACE(26, it);
             if (lane == 0) mbar_arrive(&ctl->ring_empty[rs]);
+        }
+    } else if (warp == kWarpPub) {
+        // =============================== work items: draw tickets, publish the items to the other warps (one lane) =====
+        // A warp of its own, because the draw (an atomic every CTA hits once per item), the lengths and the integer divisions
+        // wait for memory: when A warp 0 did this between its frames, register pressure made ptxas spill buffers whose loads
+        // were still pending, and every such spill waited out a memory latency - ~2,800 cycles per item on the pipeline's
+        // critical path (timeline: tools/fe_trace.py); inside the MMA warp's polling loop it delayed every MMA instead.
+        // i0 / L0 = the next item to publish and its length, r1 = the raw reply of the draw behind it
+        // (32-bit item indices: one launch has fewer than 2^31 items; a ticket outside [0, total) means "no more work")
+        const int total_i = (int)total_items;
+        int i0 = -1;
+        int L0 = 0;
+        auto length_of = [&](int item) -> int {
+            if (item < 0) return 0;
+            const int b = item / p.groups_max;
+            int L = p.lengths ? min(__ldg(p.lengths + b), p.n_samples) : p.n_samples;
+            if (p.max_samples > 0) L = min(L, p.max_samples);
+            return L;
+        };
+        // A draw is an atomic on one global word that every CTA hits once per item: its reply takes 1-2 us.  The RAW reply stays
+        // in a register (r1) and is only decoded when the item is needed, one publish later - decoding it right away (the
+        // first version) stalled the drawing lane, and with it this warp's frames and everything downstream, for ~2,800 cycles
+        // per item (timeline: tools/fe_trace.py).
+        auto draw_raw = [&]() -> unsigned long long { return atomicAdd(p.work_counter, 1ULL); };
+        auto decode = [&](unsigned long long raw) -> int {
+            const unsigned long long t = raw - p.work_base;      // wraps to huge if the base is ahead
+            return t < (unsigned long long)total_i ? (int)t : -1;
+        };
+        unsigned long long r1 = 0;                               // raw reply of the draw behind i0
+        // Request the samples of a coming item into L2 (one bulk-prefetch instruction for its 16 blocks): the A warps hold
+        // only 8 KB of loads in flight per SM, which at HBM latency is ~1 TB/s for the whole chip; at L2 latency it is enough.
+        auto prefetch_item = [&](int item, int Li) {
+            if (item < 0 || Li <= kNfft / 2) return;
+            const int b = item / p.groups_max, g = item - b * p.groups_max;
+            const int n_lo = max(0, (g * kTileFrames - 1) * kHop), n_hi = min(Li, (g * kTileFrames + kTileFrames) * kHop);
+            if (n_hi <= n_lo) return;
+            const char* base = reinterpret_cast<const char*>(static_cast<const SampleT*>(p.wave) + (int64_t)b * p.wave_stride);
+            uintptr_t lo = reinterpret_cast<uintptr_t>(base + (size_t)n_lo * sizeof(SampleT));
+            uintptr_t hi = reinterpret_cast<uintptr_t>(base + (size_t)n_hi * sizeof(SampleT));
+            lo = (lo + 15) & ~(uintptr_t)15;
+            hi &= ~(uintptr_t)15;
+#if SIR_FE_PREFETCH == 1
+            if (hi > lo) prefetch_l2_bulk(reinterpret_cast<const void*>(lo), (uint32_t)(hi - lo));
+#elif SIR_FE_PREFETCH == 2
+            for (uintptr_t a = lo; a < hi; a += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+#endif
+        };
+        if (lane == 0) {
+            i0 = decode(draw_raw());
+            r1 = draw_raw();
+            L0 = length_of(i0);
+            prefetch_item(i0, L0);
+        }
+        if (lane == 0) {
+            for (uint32_t pub = 0;;) {
+                for (uint32_t spin = 0; pub > ctl->a_progress + 3u; ++spin) {     // at most three items ahead of the A warps
+                    __nanosleep(64);
+                    if (spin > (1u << 26)) __trap();
+                }
+                const int ps = pub % kRing;
+                pipe_wait(&ctl->ring_empty[ps], ((pub / kRing) & 1u) ^ 1u);
+                ItemSlot& sl = ctl->slot[ps];
+                bool end = false;
+                for (;;) {                                       // skip tickets beyond an utterance's last group (ragged batches)
+                    if (i0 < 0) {
+                        sl.item = -1;
+                        end = true;
+                        break;
+                    }
+                    const int b = i0 / p.groups_max, g = i0 - b * p.groups_max;
+                    const bool valid = L0 > kNfft / 2;
+                    const int T = valid ? 1 + L0 / kHop : 0;
+                    const int n_groups = valid ? (T + kTileFrames - 1) / kTileFrames : 1;
+                    if (g < n_groups) {
+                        sl.item = i0;
+                        sl.b = b;
+                        sl.t0 = g * kTileFrames;
+                        sl.nfr = valid ? min(kTileFrames, T - g * kTileFrames) : 0;
+                        sl.T = T;
+                        sl.L = L0;
+                        sl.n_groups = n_groups;
+                        break;
+                    }
+                    i0 = decode(r1);
+                    L0 = length_of(i0);
+                    r1 = draw_raw();
+                }
+                mbar_arrive(&ctl->ring_full[ps]);
+                ++pub;
+                if (end) break;
+                i0 = decode(r1);                                 // advance: the next item's samples are requested into L2, the
+                L0 = length_of(i0);                              // draw after it is in flight until the next publish
+                prefetch_item(i0, L0);
+                r1 = draw_raw();
+            }
         }
     } else {
         // =============================== F: tile -> global, statistics, counting atomic, finisher ====================
-        const int ft = (warp - kWarpF0) * 32 + lane;             // 0..95
+        const int ft = (warp - kWarpF0) * 32 + lane;             // 0..63
         constexpr int kET = kFThreads;
         float* red = ctl->red;
         const bool mfcc = p.mode == SIR_OUT_MFCC;
@@ -725,6 +725,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
             const uint32_t buf = it & 1u;
             const float* tile = s_tile + buf * kTileFloats;
             pipe_wait(&ctl->tile_full[buf], (it >> 1) & 1u);
+            if (warp == kWarpF0) FE_TRACE(27, it);
 
             const bool valid_utt = T > 0;
             float* __restrict__ final_out = p.out + (int64_t)b * out_rows * p.out_frames;
@@ -771,10 +772,10 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                     f_barrier();
                     if (ft == 0) {                               // the item's partial statistics; frontend_finish_kernel merges them
                         ItemPartial part;
-                        part.s1 = ((double)red[0] + (double)red[1]) + (double)red[2];
-                        part.s2 = ((double)red[8] + (double)red[9]) + (double)red[10];
+                        part.s1 = (double)red[0] + (double)red[1];
+                        part.s2 = (double)red[8] + (double)red[9];
                         part.shift = shift;
-                        part.vmax = fmaxf(fmaxf(red[16], red[17]), red[18]);
+                        part.vmax = fmaxf(red[16], red[17]);
                         part.n = nfr * p.n_mels;
                         part.pad = 0;
                         p.partials[item] = part;
@@ -782,6 +783,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
                 }
             }
             f_barrier();                                         // red consumed; slot data no longer needed
+            if (warp == kWarpF0) FE_TRACE(28, it);
             if (lane == 0) mbar_arrive(&ctl->ring_empty[rs]);
         }
     }
@@ -936,29 +938,45 @@ int frontend_tc_upload_tables(DeviceBuffer& buf, TcDeviceTables& dev, int sample
     }
     if ((int)m_weight.size() > fetc::kMelWeightCap)
         return fail(SIR_ERR_UNSUPPORTED, "filterbank has %zu padded taps (cap %d)", m_weight.size(), fetc::kMelWeightCap);
-    const size_t o_b1 = 0, o_b2 = o_b1 + t.b1_img.size() * 2, o_tw = o_b2 + t.b2_img.size() * 2,
-                 o_mw = o_tw + t.twiddle.size() * 4, o_ms = o_mw + fetc::kMelWeightCap * 4, o_mc = o_ms + n_mels * 4,
-                 o_mo = o_mc + n_mels * 4, total = o_mo + n_mels * 4;
+    // Hann window in the order the A warps read it: [n1 / 4][lane = n2][n1 % 4] (one 16-byte load per four taps)
+    std::vector<float> win_img(1024);
+    for (int i = 0; i < 1024; ++i) {
+        const int n1 = i >> 5, l = i & 31;
+        win_img[((n1 >> 2) * 32 + l) * 4 + (n1 & 3)] = ft.window[i];
+    }
+    const size_t o_b1 = 0, o_b2 = o_b1 + t.b1_img.size() * 4, o_tw = o_b2 + t.b2_img.size() * 4,
+                 o_win = o_tw + t.twiddle.size() * 4, o_mw = o_win + win_img.size() * 4, o_ms = o_mw + fetc::kMelWeightCap * 4,
+                 o_mc = o_ms + n_mels * 4, o_mo = o_mc + n_mels * 4, total = o_mo + n_mels * 4;
     int rc = buf.reserve(total);
     if (rc != SIR_OK) return rc;
     char* base = static_cast<char*>(buf.ptr);
-    SIR_CUDA(cudaMemcpy(base + o_b1, t.b1_img.data(), t.b1_img.size() * 2, cudaMemcpyHostToDevice));
-    SIR_CUDA(cudaMemcpy(base + o_b2, t.b2_img.data(), t.b2_img.size() * 2, cudaMemcpyHostToDevice));
+    SIR_CUDA(cudaMemcpy(base + o_b1, t.b1_img.data(), t.b1_img.size() * 4, cudaMemcpyHostToDevice));
+    SIR_CUDA(cudaMemcpy(base + o_b2, t.b2_img.data(), t.b2_img.size() * 4, cudaMemcpyHostToDevice));
     SIR_CUDA(cudaMemcpy(base + o_tw, t.twiddle.data(), t.twiddle.size() * 4, cudaMemcpyHostToDevice));
+    SIR_CUDA(cudaMemcpy(base + o_win, win_img.data(), win_img.size() * 4, cudaMemcpyHostToDevice));
     SIR_CUDA(cudaMemset(base + o_mw, 0, fetc::kMelWeightCap * 4));
     SIR_CUDA(cudaMemcpy(base + o_mw, m_weight.data(), m_weight.size() * 4, cudaMemcpyHostToDevice));
     SIR_CUDA(cudaMemcpy(base + o_ms, m_start.data(), n_mels * 4, cudaMemcpyHostToDevice));
     SIR_CUDA(cudaMemcpy(base + o_mc, m_count.data(), n_mels * 4, cudaMemcpyHostToDevice));
     SIR_CUDA(cudaMemcpy(base + o_mo, m_offset.data(), n_mels * 4, cudaMemcpyHostToDevice));
-    dev.b1_img = reinterpret_cast<const uint16_t*>(base + o_b1);
-    dev.b2_img = reinterpret_cast<const uint16_t*>(base + o_b2);
+    dev.b1_img = reinterpret_cast<const float*>(base + o_b1);
+    dev.b2_img = reinterpret_cast<const float*>(base + o_b2);
     dev.twiddle = reinterpret_cast<const float*>(base + o_tw);
+    dev.win_img = reinterpret_cast<const float*>(base + o_win);
     dev.mel_weight = reinterpret_cast<const float*>(base + o_mw);
     dev.mel_start = reinterpret_cast<const int32_t*>(base + o_ms);
     dev.mel_count = reinterpret_cast<const int32_t*>(base + o_mc);
     dev.mel_offset = reinterpret_cast<const int32_t*>(base + o_mo);
     return SIR_OK;
 }
+
+#ifdef SIR_FE_TRACE
+extern "C" int sir_debug_fe_trace(long long* host, int count) {
+    const size_t n = sizeof(long long) * fetc::kTraceCtas * fetc::kTraceItems * fetc::kTraceEvents;
+    if ((size_t)count * sizeof(long long) < n) return -1;
+    return cudaMemcpyFromSymbol(host, fetc::g_fe_trace, n) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int frontend_tc_groups(int n_frames) { return (n_frames + fetc::kTileFrames - 1) / fetc::kTileFrames; }
 long long frontend_tc_tickets(long long items, long long grid) { return items + 2 * grid; }   // every CTA draws its items + 2

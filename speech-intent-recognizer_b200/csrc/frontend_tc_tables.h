@@ -7,10 +7,14 @@
 //   twiddle   Y'[k1][n2] = Y[k1][n2] W1024^(n2 k1)                      (CUDA cores, between the stages)
 //   stage 2   X[k1 + 32 k2] = sum_n2 Y'[k1][n2] W32^(n2 k2)             k2 = 0..31
 // Bins k = k1 + 32 k2 with k mod 32 <= 16 come out directly; the others are mirrors, |X[k]| = |X[1024 - k]|.
-// Both stages run on tcgen05 as fp16 (hi, lo) split products with fp32 accumulation:
+// Both stages run on tcgen05 as TF32 (hi, lo) split products with fp32 accumulation:
 //   x.B ~= x_hi.B_hi + x_hi.B_lo + x_lo.B_hi          (the dropped lo.lo term is ~2^-22 relative)
-// The B operands are stored K-major with the 128-byte swizzle of the UMMA descriptors, hi rows stacked on lo rows, as the
-// exact shared-memory image the kernel copies in.
+// hi = the fp32 value with its 13 low mantissa bits cleared - exactly what the tensor core reads of an fp32 operand
+// (measured: tools/tf32_probe.cu, the low bits are ignored) -, lo = x - hi (exact in fp32; the tensor core keeps its 11
+// leading bits).  TF32 has the exponent range of fp32: no per-frame scaling, no subnormal corner (the fp16 split needed
+// a power-of-two scale per frame, i.e. a maximum over the windowed samples).  The constant matrices are split with round
+// to nearest on the host.  The B operands are stored K-major with the 128-byte swizzle of the UMMA descriptors (rows of
+// 32 four-byte elements), as the exact shared-memory image the kernel copies in.
 //
 // Stage-1 outputs are the 32 REAL numbers that describe Y[0..16] (Im Y[0] = Im Y[16] = 0):
 //   o = 0: Re Y[0];  o = 1: Re Y[16];  o = 2j: Re Y[j];  o = 2j + 1: Im Y[j]   (j = 1..15)
@@ -25,48 +29,39 @@
 namespace sir {
 namespace fetc {
 
-constexpr int kTileFrames = 15;          // frames per work item: 15 x 17 = 255 stage-2 rows = two 128-row UMMA tiles
+constexpr int kTileFrames = 14;          // frames per work item: two self-contained 128-row UMMA tiles of 7 frames x 17 stage-2 rows
 constexpr int kPStride = 532;            // floats per frame of the power buffer: 16-byte aligned rows whose 16-byte chunk index
                                          // advances by 5 (mod 8) per frame - lanes = frames read LDS.128 without bank conflicts
 
-// fp32 -> fp16 bits, round to nearest even (host-side twin of cvt.rn.f16.f32)
-inline uint16_t half_bits(float f) {
-    uint32_t x;
-    std::memcpy(&x, &f, 4);
-    const uint32_t sign = (x >> 16) & 0x8000u;
-    x &= 0x7FFFFFFFu;
-    if (x >= 0x7F800000u) return (uint16_t)(sign | 0x7C00u | (x > 0x7F800000u ? 0x200u : 0u));
-    if (x >= 0x477FF000u) return (uint16_t)(sign | 0x7C00u);                 // rounds to >= 65520 -> inf
-    if (x < 0x33000001u) return (uint16_t)sign;                              // < 2^-25 -> 0
-    int e = (int)(x >> 23) - 127;
-    uint32_t m = (x & 0x7FFFFFu) | 0x800000u;
-    int shift = e < -14 ? (13 + (-14 - e)) : 13;                             // subnormal results shift further
-    uint32_t half_m = m >> shift;
-    const uint32_t rem = m & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
-    if (rem > halfway || (rem == halfway && (half_m & 1u))) ++half_m;
-    if (e < -14) return (uint16_t)(sign | half_m);                           // (a carry into bit 10 is the smallest normal)
-    return (uint16_t)(sign | (((uint32_t)(e + 15) << 10) + (half_m - 0x400u)));   // carry bumps the exponent
-}
-inline float half_value(uint16_t h) {
-    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
-    const int e = (h >> 10) & 31;
-    const uint32_t m = h & 0x3FFu;
-    float v;
-    if (e == 0) v = std::ldexp((float)m, -24);
-    else if (e == 31) v = m ? NAN : INFINITY;
-    else v = std::ldexp((float)(m | 0x400u), e - 25);
-    return sign ? -v : v;
-}
-
-// Byte offset of fp16 element (row, k) inside a K-major SWIZZLE_128B operand tile whose rows are 128 bytes (64 fp16):
+// Byte offset of 4-byte element (row, k), k = 0..31, inside a K-major SWIZZLE_128B operand tile whose rows are 128 bytes:
 // 8-row atoms of 1024 bytes, the 16-byte chunk index XOR-ed with the row index inside the atom.
 inline uint32_t sw128_offset(int row, int k) {
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 2) ^ (row & 7)) & 7) << 4) + (k & 3) * 4);
+}
+
+// TF32 pieces of a double: hi = nearest value with a 10-bit mantissa, lo = the same of the remainder
+inline float tf32_round(double v) {
+    float f = (float)v;
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    u += 0xFFFu + ((u >> 13) & 1u);                                          // round to nearest even on bit 13
+    u &= 0xFFFFE000u;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+inline float tf32_trunc(float f) {                                           // what the tensor core reads of an fp32 operand
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    u &= 0xFFFFE000u;
+    std::memcpy(&f, &u, 4);
+    return f;
 }
 
 struct HostTcTables {
-    std::vector<uint16_t> b1_img;        // stage-1 operand image: 64 rows x 128 bytes = 4096 halves (rows 0..31 hi, 32..63 lo)
-    std::vector<uint16_t> b2_img;        // stage-2 operand image: 128 rows x 128 bytes = 8192 halves (rows 0..63 hi, 64..127 lo)
+    std::vector<float> b1_img;           // stage-1 operand image: [hi | lo] x 32 rows (o) x 128 bytes (K = n1): 2048 floats
+    std::vector<float> b2_img;           // stage-2 operand image: [hi K 0..31 | hi K 32..63 | lo K 0..31 | lo K 32..63] x 64 rows (nu)
+                                         // x 128 bytes: 8192 floats
+    std::vector<float> win_img;          // Hann window as [8][32 lanes][4]: lane's w[32 n1 + lane], n1 = 4c .. 4c + 3
     std::vector<float> twiddle;          // [32 n2][16 (k1 = 1..16)][2]: (cos, -sin)(2 pi n2 k1 / 1024)
     std::vector<float> b1, b2;           // the unsplit fp32 matrices [K][N] (for the host emulation)
 };
@@ -92,27 +87,27 @@ inline double stage2_entry(int kappa, int nu) {
 inline HostTcTables build_tc_tables() {
     const double pi = 3.14159265358979323846;
     HostTcTables t;
-    t.b1_img.assign(64 * 64, 0);
-    t.b2_img.assign(128 * 64, 0);
+    t.b1_img.assign(2 * 32 * 32, 0.f);
+    t.b2_img.assign(4 * 64 * 32, 0.f);
     t.b1.assign(32 * 32, 0.f);
     t.b2.assign(64 * 64, 0.f);
     for (int n1 = 0; n1 < 32; ++n1)
         for (int o = 0; o < 32; ++o) {
             const float v = (float)stage1_entry(n1, o);
             t.b1[n1 * 32 + o] = v;
-            const uint16_t hi = half_bits(v);
-            const uint16_t lo = half_bits((float)(stage1_entry(n1, o) - (double)half_value(hi)));
-            t.b1_img[sw128_offset(o, n1) / 2] = hi;
-            t.b1_img[sw128_offset(32 + o, n1) / 2] = lo;
+            const float hi = tf32_round(stage1_entry(n1, o));
+            const float lo = tf32_round(stage1_entry(n1, o) - (double)hi);
+            t.b1_img[sw128_offset(o, n1) / 4] = hi;
+            t.b1_img[1024 + sw128_offset(o, n1) / 4] = lo;
         }
     for (int kappa = 0; kappa < 64; ++kappa)
         for (int nu = 0; nu < 64; ++nu) {
             const float v = (float)stage2_entry(kappa, nu);
             t.b2[kappa * 64 + nu] = v;
-            const uint16_t hi = half_bits(v);
-            const uint16_t lo = half_bits((float)(stage2_entry(kappa, nu) - (double)half_value(hi)));
-            t.b2_img[sw128_offset(nu, kappa) / 2] = hi;
-            t.b2_img[sw128_offset(64 + nu, kappa) / 2] = lo;
+            const float hi = tf32_round(stage2_entry(kappa, nu));
+            const float lo = tf32_round(stage2_entry(kappa, nu) - (double)hi);
+            t.b2_img[(kappa >> 5) * 2048 + sw128_offset(nu, kappa & 31) / 4] = hi;
+            t.b2_img[4096 + (kappa >> 5) * 2048 + sw128_offset(nu, kappa & 31) / 4] = lo;
         }
     t.twiddle.resize(32 * 16 * 2);
     for (int n2 = 0; n2 < 32; ++n2)

@@ -235,6 +235,25 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::tf32: A and B hold fp32 bit patterns of which the tensor core reads sign, exponent and the 10 leading mantissa bits
+// (the 13 low bits are ignored - measured, tools/tf32_probe.cu); K = 8 per instruction (32 bytes of a K-major row).
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// A in tensor memory: lane = row, one 32-bit column per element; one instruction reads 8 columns starting at `tmem_a`.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // registers -> TMEM: every thread of the warp writes 32 consecutive 32-bit columns of ITS lane (warp quadrant)
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -318,6 +337,11 @@ __device__ __forceinline__ uint64_t desc_advance_k(uint64_t desc, uint32_t k_ele
 // kind::f16 instruction descriptor: D = F32 [4,6)=1, A/B = F16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::tf32 instruction descriptor: D = F32, A/B = TF32 (2) at [7,10) / [10,13), both K-major.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ---- fp16 hi/lo split ---------------------------------------------------------------------------------------

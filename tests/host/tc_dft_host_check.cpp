@@ -1,6 +1,7 @@
-// CPU emulation of the tensor-core DFT frontend's arithmetic (frontend_tc.cu): per-frame power-of-two scaling, fp16
-// (hi, lo) operand splits, the two matrix stages with the operand IMAGES the kernel copies into shared memory (decoded
-// through the same swizzle function), the twiddle step and the mirrored bin map - against a direct double-precision DFT.
+// CPU emulation of the tensor-core DFT frontend's arithmetic (frontend_tc.cu): TF32 (hi, lo) operand splits as the tensor
+// core reads them (the 13 low mantissa bits of an fp32 operand are ignored), the two matrix stages with the operand IMAGES
+// the kernel copies into shared memory (decoded through the same swizzle function), the twiddle step and the mirrored bin
+// map - against a direct double-precision DFT.
 // Built and run by tests/test_host_logic.py with g++.  Bar: per trial, the worst mel-band error (dB) stays within 8x of what an
 // fp32 radix-2 FFT of the same frame makes (pure tones 100+ dB above the noise floor are hard for fp32 itself), or 1e-4 dB.
 #include <cmath>
@@ -15,9 +16,9 @@
 using namespace sir;
 using namespace sir::fetc;
 
-static void split(float v, float& hi, float& lo) {       // the kernel's split: hi = fp16(v), lo = fp16(v - hi)
-    hi = half_value(half_bits(v));
-    lo = half_value(half_bits(v - hi));
+static void split(float v, float& hi, float& lo) {       // what the tensor core reads of v, and of what that left behind
+    hi = tf32_trunc(v);
+    lo = tf32_trunc(v - hi);
 }
 
 int main() {
@@ -27,13 +28,13 @@ int main() {
     std::vector<float> b1h(32 * 32), b1l(32 * 32), b2h(64 * 64), b2l(64 * 64);
     for (int k = 0; k < 32; ++k)
         for (int o = 0; o < 32; ++o) {
-            b1h[k * 32 + o] = half_value(tc.b1_img[sw128_offset(o, k) / 2]);
-            b1l[k * 32 + o] = half_value(tc.b1_img[sw128_offset(32 + o, k) / 2]);
+            b1h[k * 32 + o] = tc.b1_img[sw128_offset(o, k) / 4];
+            b1l[k * 32 + o] = tc.b1_img[1024 + sw128_offset(o, k) / 4];
         }
     for (int k = 0; k < 64; ++k)
         for (int n = 0; n < 64; ++n) {
-            b2h[k * 64 + n] = half_value(tc.b2_img[sw128_offset(n, k) / 2]);
-            b2l[k * 64 + n] = half_value(tc.b2_img[sw128_offset(64 + n, k) / 2]);
+            b2h[k * 64 + n] = tc.b2_img[(k >> 5) * 2048 + sw128_offset(n, k & 31) / 4];
+            b2l[k * 64 + n] = tc.b2_img[4096 + (k >> 5) * 2048 + sw128_offset(n, k & 31) / 4];
         }
     // every bin of the one-sided spectrum is produced exactly once
     std::vector<int> hits(513, 0);
@@ -81,35 +82,18 @@ int main() {
             pref[k] = re * re + im * im;
         }
         // kernel arithmetic
-        float m = 0.f;                                               // the scale comes from the largest WINDOWED value
-        for (int n = 0; n < 1024; ++n) m = std::fmax(m, std::fabs(x[n] * ft.window[n]));
-        uint32_t mb;
-        std::memcpy(&mb, &m, 4);
-        uint32_t eb = mb >> 23;
-        eb = eb < 65 ? 65 : (eb > 187 ? 187 : eb);
-        const uint32_t sb = (254u - eb) << 23, ib = eb << 23;
-        float sc, inv;
-        std::memcpy(&sc, &sb, 4);
-        std::memcpy(&inv, &ib, 4);
         std::vector<float> ah(1024), al(1024);
-        for (int n = 0; n < 1024; ++n) {
-            const float t = (x[n] * ft.window[n]) * sc;               // the power-of-two scaling is exact
-            ah[n] = half_value(half_bits(t));
-            al[n] = half_value(half_bits(t - ah[n]));
-        }
+        for (int n = 0; n < 1024; ++n) split(x[n] * ft.window[n], ah[n], al[n]);
         std::vector<float> P(513, -1.f);
         std::vector<float> a2h(17 * 64), a2l(17 * 64);
         for (int n2 = 0; n2 < 32; ++n2) {
             float y[32];
             for (int o = 0; o < 32; ++o) {
-                float d0 = 0.f, d1 = 0.f;                                 // columns [0,32) and [32,64) of the accumulator
-                for (int n1 = 0; n1 < 32; ++n1) {
-                    const float h = ah[32 * n1 + n2], l = al[32 * n1 + n2];
-                    d0 += h * b1h[n1 * 32 + o];
-                    d1 += h * b1l[n1 * 32 + o];
-                    d0 += l * b1h[n1 * 32 + o];
-                }
-                y[o] = d0 + d1;
+                float d0 = 0.f;                                           // one accumulator, three passes
+                for (int n1 = 0; n1 < 32; ++n1) d0 += ah[32 * n1 + n2] * b1h[n1 * 32 + o];
+                for (int n1 = 0; n1 < 32; ++n1) d0 += ah[32 * n1 + n2] * b1l[n1 * 32 + o];
+                for (int n1 = 0; n1 < 32; ++n1) d0 += al[32 * n1 + n2] * b1h[n1 * 32 + o];
+                y[o] = d0;
             }
             for (int k1 = 0; k1 <= 16; ++k1) {
                 float re, im;
@@ -132,16 +116,14 @@ int main() {
                 float xr[2];
                 for (int cp = 0; cp < 2; ++cp) {
                     const int nu = 2 * k2 + cp;
-                    float d0 = 0.f, d1 = 0.f;
-                    for (int kap = 0; kap < 64; ++kap) {
-                        d0 += a2h[k1 * 64 + kap] * b2h[kap * 64 + nu];
-                        d1 += a2h[k1 * 64 + kap] * b2l[kap * 64 + nu];
-                        d0 += a2l[k1 * 64 + kap] * b2h[kap * 64 + nu];
-                    }
-                    xr[cp] = d0 + d1;
+                    float d0 = 0.f;
+                    for (int kap = 0; kap < 64; ++kap) d0 += a2h[k1 * 64 + kap] * b2h[kap * 64 + nu];
+                    for (int kap = 0; kap < 64; ++kap) d0 += a2h[k1 * 64 + kap] * b2l[kap * 64 + nu];
+                    for (int kap = 0; kap < 64; ++kap) d0 += a2l[k1 * 64 + kap] * b2h[kap * 64 + nu];
+                    xr[cp] = d0;
                 }
                 const int k = power_bin(k1, k2);
-                if (k >= 0) P[k] = (xr[0] * xr[0] + xr[1] * xr[1]) * (inv * inv);
+                if (k >= 0) P[k] = xr[0] * xr[0] + xr[1] * xr[1];
             }
         // fp32 iterative radix-2 FFT of the same windowed frame (what an fp32 library FFT does)
         std::vector<float> fr(1024), fi(1024, 0.f);

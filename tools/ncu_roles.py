@@ -39,7 +39,7 @@ def role(off):
         if off >= a: r = k
     return r
 def is_wait(loc):
-    return loc and ((loc[0] == 'tc_common.cuh' and loc[1] < 130) or (loc[0] == 'frontend_tc.cu' and 88 <= loc[1] <= 108))
+    return loc and ((loc[0] == 'tc_common.cuh' and loc[1] < 130) or (loc[0] == 'frontend_tc.cu' and 99 <= loc[1] <= 117))
 S = collections.Counter(); W = collections.Counter(); I = collections.Counter(); WI = collections.Counter()
 for r in data:
     off = int(r[0], 16) - base

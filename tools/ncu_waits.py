@@ -19,7 +19,7 @@ src = open('/root/repo/speech-intent-recognizer_b200/csrc/frontend_tc.cu').read(
 # a wait = samples on instructions inside pipe_wait / mbar_* helper lines; attribute to the NEXT frontend_tc.cu line >= 230 that follows in address order
 def is_wait(loc, sass):
     if not loc: return False
-    return (loc[0] == 'tc_common.cuh' and loc[1] < 130) or (loc[0] == 'frontend_tc.cu' and 88 <= loc[1] <= 106)
+    return (loc[0] == 'tc_common.cuh' and loc[1] < 130) or (loc[0] == 'frontend_tc.cu' and 99 <= loc[1] <= 117)
 tot = sum(float(r[idx['# Samples']]) for r in data)
 agg = collections.Counter(); insn = collections.Counter()
 for r in data:
