@@ -565,12 +565,16 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
             // ---- sparse mel taps: lane = (band, frame).  The 16 lanes of a half-warp read the same four taps (broadcast)
             // and their own frame's four bins (rows 532 floats apart: conflict-free LDS.128).  A warp takes QUADS of
             // neighbouring bands (4q..4q+3; the host pads their tap runs to one length), two bands per lane, the loads of
-            // tap group i + 1 in flight while group i is accumulated; quads go round-robin over the four warps.
+            // tap group i + 1 in flight while group i is accumulated.
             if (nfr > 0) {
                 const int w = warp - kWarpD0, h = lane >> 4, f = lane & 15;
                 const int n_quads = (p.n_mels + 3) >> 2;
                 const float* Pf = s_P + (f < nfr ? f : 0) * kPStride;
-                for (int pq = w; pq < n_quads; pq += 4) {
+                // quads in SNAKE order over the four warps (w, 7 - w, 8 + w, 15 - w, ...): the tap runs grow with the band index, and
+                // with a plain round-robin the warp with the widest bands kept the other three waiting at the barrier below
+                for (int j = 0; 4 * j < n_quads; ++j) {
+                    const int pq = 4 * j + ((j & 1) ? 3 - w : w);
+                    if (pq >= n_quads) continue;
                     const int band0 = 4 * pq + h, band1 = band0 + 2;
                     const int bq = min(band0, p.n_mels - 1), br = min(band1, p.n_mels - 1);
                     const int n4 = s_mel_count[4 * pq] >> 2;     // the same for the whole quad

@@ -16,6 +16,8 @@ for ln in open(disasm, errors='ignore'):
     if m: seq.append((int(m.group(1), 16), last, m.group(2)))
 offs = [a for a, _, _ in seq]
 src = open('/root/repo/speech-intent-recognizer_b200/csrc/frontend_tc.cu').read().splitlines()
+_pw = next(i for i, l in enumerate(src, 1) if 'void pipe_wait(uint64_t* bar' in l)
+PW = (_pw, next(i for i in range(_pw, _pw + 40) if src[i - 1].startswith('}')))
 marks = {}
 for i, l in enumerate(src, 1):
     if 'if (warp < 4) {' in l and 'A' not in marks: marks['A'] = i
@@ -23,6 +25,7 @@ for i, l in enumerate(src, 1):
     if 'else if (warp < kWarpD0)' in l: marks['C'] = i
     if 'else if (warp < kWarpF0)' in l: marks['DE'] = i
     if 'F: tile -> global' in l: marks['F'] = i
+    if 'else if (warp == kWarpPub)' in l: marks['PUB'] = i
 order = sorted(marks.items(), key=lambda kv: kv[1])
 def first_addr(lo, hi):
     c = [a for a, l, _ in seq if l and l[0] == 'frontend_tc.cu' and lo <= l[1] < hi]
@@ -39,7 +42,7 @@ def role(off):
         if off >= a: r = k
     return r
 def is_wait(loc):
-    return loc and ((loc[0] == 'tc_common.cuh' and loc[1] < 130) or (loc[0] == 'frontend_tc.cu' and 99 <= loc[1] <= 117))
+    return loc and ((loc[0] == 'tc_common.cuh' and loc[1] < 130) or (loc[0] == 'frontend_tc.cu' and PW[0] <= loc[1] <= PW[1]))
 S = collections.Counter(); W = collections.Counter(); I = collections.Counter(); WI = collections.Counter()
 for r in data:
     off = int(r[0], 16) - base

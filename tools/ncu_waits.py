@@ -16,10 +16,12 @@ for ln in open(disasm, errors='ignore'):
     if m: seq.append((int(m.group(1), 16), last, m.group(2)))
 offs = [a for a, _, _ in seq]
 src = open('/root/repo/speech-intent-recognizer_b200/csrc/frontend_tc.cu').read().splitlines()
+_pw = next(i for i, l in enumerate(src, 1) if 'void pipe_wait(uint64_t* bar' in l)
+PW = (_pw, next(i for i in range(_pw, _pw + 40) if src[i - 1].startswith('}')))
 # a wait = samples on instructions inside pipe_wait / mbar_* helper lines; attribute to the NEXT frontend_tc.cu line >= 230 that follows in address order
 def is_wait(loc, sass):
     if not loc: return False
-    return (loc[0] == 'tc_common.cuh' and loc[1] < 130) or (loc[0] == 'frontend_tc.cu' and 99 <= loc[1] <= 117)
+    return (loc[0] == 'tc_common.cuh' and loc[1] < 130) or (loc[0] == 'frontend_tc.cu' and PW[0] <= loc[1] <= PW[1])
 tot = sum(float(r[idx['# Samples']]) for r in data)
 agg = collections.Counter(); insn = collections.Counter()
 for r in data:
