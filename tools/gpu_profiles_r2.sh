@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 evidence: launch list of the bench command + ncu --set full of one warm step of every hot kernel.
 set -u
-OUT=gpurun_out; mkdir -p $OUT; TAG=r2p
+OUT=gpurun_out; mkdir -p $OUT; TAG=${1:-r2q}
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-train --e2e-repeats 1"
 $CMD > $OUT/${TAG}_plain.json 2> $OUT/${TAG}_plain.err && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
