@@ -888,6 +888,38 @@ def run_inference(ctx, out):
             line["cpu_baseline"] = {"value": arm.n * n_steps / (fs + ws), "unit": "utt/s", "cores": arm.threads,
                                     "kind": arm.kind, "sample": arm.describe(n_steps, fs, ws),
                                     "host_cpus": os.cpu_count() or 1}
+            # the same path with ONE thread (the reference pipeline exports OMP_NUM_THREADS=1,
+            # run_pipeline.py:42) and the CPU's best case (the whole batch in one mel_transform call instead of the
+            # per-utterance loop), so that the ratio is not read as Python overhead; a few seconds each
+            if args.workload == "config2" and arm.ref_extractor is not None:
+                try:
+                    with torch.no_grad():
+                        w = arm.pcm.to(torch.float32) / 32768.0
+                        ex = arm.ref_extractor
+
+                        def batched():
+                            m = ex.amplitude_to_db(ex.mel_transform(w))
+                            m = (m - m.mean(dim=(1, 2), keepdim=True)) / (m.std(dim=(1, 2), keepdim=True) + 1e-5)
+                            arm.model(torch.nn.functional.pad(m, (0, OUT_FRAMES - m.shape[2])))
+                        batched()
+                        t0 = time.perf_counter()
+                        k = 0
+                        while k < 2 or (time.perf_counter() - t0 < 2.0 and k < 20):
+                            batched()
+                            k += 1
+                        line["cpu_baseline"]["batched_features_value"] = arm.n * k / (time.perf_counter() - t0)
+                        torch.set_num_threads(1)
+                        sub = CpuArm(ctx.synth, 32, L, n_mels, max_duration=max_duration, threads=1)
+                        sub.step()
+                        k1, f1, w1 = sub.run_for(3.0, min_steps=1, max_steps=8)
+                        line["cpu_baseline"]["one_thread_value"] = sub.n * k1 / (f1 + w1)
+                        line["cpu_baseline"]["variants"] = ("batched_features_value: one mel_transform call for the whole batch + "
+                                                            "batched forward, all cores; one_thread_value: the per-utterance "
+                                                            "loop + forward on 32 utterances with torch.set_num_threads(1)")
+                except Exception as e:  # noqa: BLE001 - the variants are optional context
+                    line["cpu_baseline"]["variants"] = f"not measured: {type(e).__name__}: {e}"
+                finally:
+                    torch.set_num_threads(os.cpu_count() or 1)
         elif world > 1:
             line["cpu_baseline"] = None
             line["cpu_baseline_note"] = "timed on rank 0 at N = 1 only (see the N = 1 line): no CPU work while other ranks hold GPUs"
