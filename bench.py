@@ -423,12 +423,17 @@ class Ctx:
             self.dist.destroy_process_group()
 
 
-def stable_repeats(run, repeats, warm_min=1, warm_max=8, tol=0.03):
+def stable_repeats(run, repeats, warm_min=1, warm_max=8, tol=0.03, agree=None):
     """Warm `run()` (a wall-clock timed K-step loop returning seconds) until two consecutive runs agree within `tol`, then
-    take `repeats` measured runs.  Returns (median seconds, [measured seconds], warm runs used)."""
+    take `repeats` measured runs.  Returns (median seconds, [measured seconds], warm runs used).
+    `agree` (ctx.reduce_max) makes the stop decision COLLECTIVE: `run` holds barriers, so every rank must warm the same
+    number of times - with a per-rank decision one rank can leave the loop a run earlier than the others and the job hangs
+    in the next barrier (seen at 8 GPUs on the config-3 workload)."""
     prev, used = None, 0
     for used in range(1, warm_max + 1):
         t = run()
+        if agree is not None:
+            t = agree(t)
         if prev is not None and used > warm_min and abs(t - prev) <= tol * max(t, prev):
             break
         prev = t
@@ -678,7 +683,7 @@ def run_precompute(ctx, out):
         ctx.sampler.mark()
         return t
 
-    e2e_s, e2e_times, warm_used = stable_repeats(e2e_run, min(args.e2e_repeats, 3))
+    e2e_s, e2e_times, warm_used = stable_repeats(e2e_run, min(args.e2e_repeats, 3), agree=ctx.reduce_max)
     e2e_steps = max(1, args.steps // 2)
     clocks = ctx.sampler.stop()
     check = float((host_feats[:64].cuda() - extractor.extract_batch(host_pcm[:64].cuda(), max_duration=5.0)).abs().max())
@@ -813,10 +818,10 @@ def run_inference(ctx, out):
             ctx.sampler.mark()
         return t
 
-    e2e_s, e2e_times, e2e_warm = stable_repeats(lambda: e2e_run(host_pcm, True), args.e2e_repeats)
+    e2e_s, e2e_times, e2e_warm = stable_repeats(lambda: e2e_run(host_pcm, True), args.e2e_repeats, agree=ctx.reduce_max)
     pcm_logits = last["logits"].clone()
     clocks = ctx.sampler.stop()
-    e2e_f32_s, e2e_f32_times, e2e_f32_warm = stable_repeats(lambda: e2e_run(host, False), args.e2e_repeats)
+    e2e_f32_s, e2e_f32_times, e2e_f32_warm = stable_repeats(lambda: e2e_run(host, False), args.e2e_repeats, agree=ctx.reduce_max)
     # the same kernels on the same bytes give the same result as the device-resident path
     pcm_dev = (host_pcm.cuda().to(torch.float32) / 32768.0).contiguous()
     e2e_check = float((pcm_logits.cuda() - step_device(pcm_dev, feats)).abs().max())
