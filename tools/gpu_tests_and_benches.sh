@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-OUT=gpurun_out; mkdir -p $OUT; TAG=${1:-r2l}
+OUT=gpurun_out; mkdir -p $OUT; TAG=${1:-r2}
 timeout 900 python -m pytest -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/${TAG}_pytest_gpu.log
 timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; tail -2 $OUT/${TAG}_bench.err
 for w in config3 config5; do
