@@ -449,3 +449,39 @@ def test_config1_mic_recording_durations_batch1_and_ragged(fe, model):
                 assert int(got.argmax()) == int(want.argmax()), i
             checked += 1
     assert checked == 8
+
+
+def test_frontend_work_item_boundaries(fe):
+    """Utterance lengths around the frontend's 14-frame work items and their two 7-frame stage-2 tiles: T = 1 + L // 512 of
+    2, 7, 8, 13, 14, 15, 21, 27, 28, 29, 43 frames, with L on, just below and just above a hop boundary (the last block of an
+    utterance goes through the reflect-padding load path), one batch of ragged lengths, fp32 and PCM16, against the oracle;
+    plus two pathological utterances whose loud burst ends a few samples into an otherwise near-silent frame (the case that
+    broke an fp16 split scaled by the raw maximum): a broadband burst (bar 1e-4) and a PURE TONE 110 dB above the noise floor
+    of its own frames - there the bands far from the tone sit at the rounding floor of any fp32 transform (the fp32 oracle is
+    5e-5 of the scale away from a float64 evaluation, the three-pass split 3e-4: tools/tc_dft_emulate.py), bar 1e-3."""
+    rng = np.random.default_rng(314)
+    frames = (2, 7, 8, 13, 14, 15, 21, 27, 28, 29, 43)
+    lengths = []
+    for T in frames:
+        lengths += [max(512 * (T - 1), 513), 512 * (T - 1) + 511, 512 * (T - 1) + int(rng.integers(1, 511))]
+    lengths = np.asarray(lengths, np.int32)
+    Lmax = int(lengths.max())
+    waves = synth.speech_like(77, len(lengths), Lmax)
+    # loud bursts that end a few samples into a frame whose remainder is near-silent
+    tone = 8
+    for i in (5, tone):
+        waves[i, :] = 1e-5 * rng.standard_normal(Lmax).astype(np.float32)
+    waves[5, 1000:2055] += 0.3 * rng.standard_normal(1055).astype(np.float32)
+    waves[tone, 1000:2055] += 0.4 * np.sin(0.3 * np.arange(1055, dtype=np.float32))
+    out = fe.forward(dev(waves), lengths=dev(lengths), out_frames=48).cpu().numpy()
+    pcm = np.clip(np.round(waves * 32767.0), -32768, 32767).astype(np.int16)
+    out16 = fe.forward(dev(pcm), lengths=dev(lengths), out_frames=48).cpu().numpy()
+    for i, n in enumerate(lengths):
+        T = 1 + int(n) // 512
+        want = logmel_np.extract_features(waves[i, :n])
+        assert want.shape == (64, T)
+        bar = 1e-3 if i == tone else FEATURE_REL_TOL
+        assert rel_to_scale(out[i, :, :T], want) < bar, (i, int(n), T)
+        assert not out[i, :, T:].any()
+        want16 = logmel_np.extract_features(pcm[i, :n].astype(np.float32) / 32768.0)
+        assert rel_to_scale(out16[i, :, :T], want16) < bar, (i, int(n), T, "pcm16")
