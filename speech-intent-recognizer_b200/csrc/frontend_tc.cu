@@ -5,13 +5,14 @@
 // Replaces (per utterance) scripts/precompute_features.py:59-73, scripts/dataset.py:105-113,160-176 of the reference and
 // the torchaudio calls behind them, like frontend.cu, whose CUDA-core FFT it supersedes: that kernel
 // needs ~1,360 warp instructions per frame and is issue / latency bound at 8-11 % of the HBM roofline; here the butterflies
-// are MMAs.  Numerics: frontend_tc_tables.h, tests/host/tc_dft_host_check.cpp (within ~2x of an fp32 FFT's own rounding
+// are MMAs.  Numerics: frontend_tc_tables.h, tests/host/tc_dft_host_check.cpp (within ~5x of an fp32 FFT's own rounding
 // error).  TF32 pieces need no scaling (fp32 exponent range) and the split is a mask and a subtraction; the first version
 // of this kernel used fp16 pieces, which cost a maximum over every windowed frame, a power-of-two rescale and three
 // conversions per value on the CUDA cores - the resource this kernel is bound by.
 //
-// One persistent CTA per SM, 16 warps, work item = 15 consecutive frames of one utterance (15 x 17 stage-2 rows = 255 = two
-// 128-row UMMA tiles), drawn from a ticket counter:
+// One persistent CTA per SM, 16 warps, work item = 14 consecutive frames of one utterance = two self-contained 128-row UMMA
+// tiles of 7 frames x 17 stage-2 rows (a true double buffer between the twiddle warps and the stage-2 MMAs), drawn from a
+// ticket counter.  The kernel is bound by the shared-memory data pipe (profiles/r2_summary.md):
 //   warps 0-3   "A": load samples (lane = n2, one coalesced 128-byte request per 32 samples; a 512-sample block is loaded
 //                once and serves the two frames that overlap it), Hann window, TF32 (hi, lo) split, and write the stage-1
 //                operand rows (frame, n2) x K = n1 STRAIGHT INTO TENSOR MEMORY (tcgen05.st: lane = row, 32 columns hi,
@@ -26,7 +27,8 @@
 //   warps 9-12  "D/E": read D2 (lane = (frame, k1), 32 complex bins k1 + 32 k2), |X|^2 into the one-sided power spectrum
 //                (the bins with k mod 32 > 16 are mirrors), sparse mel taps, dB -> one of two [n_mels][16] tiles in shared
 //                memory.  These warps never touch global memory.
-//   warps 13-15 "F": tile -> global and the item's partial statistics (frontend_finish_kernel merges them).
+//   warps 13-14 "F": tile -> global and the item's partial statistics (frontend_finish_kernel merges them).
+//   warp 15     draws the tickets and publishes the items to the other warps (three ahead of the A warps).
 // Every hand-off is an mbarrier; every wait is bounded and traps.
 #include <vector>
 
@@ -81,10 +83,7 @@ struct Control {
     uint64_t tile_full[2], tile_empty[2];
     ItemSlot slot[kRing];
     uint32_t tmem_base;
-    int unit_counter;
     volatile uint32_t a_progress;              // the item A warp 0 works on (the publisher stays at most three ahead of it)
-    int flag;
-    int pad;
     float red[48];
 };
 
@@ -231,7 +230,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_frontend_tc_kernel(const F
             mbar_init(&ctl->tile_full[i], 4);
             mbar_init(&ctl->tile_empty[i], 2);
         }
-        ctl->unit_counter = 0;
         ctl->a_progress = 0;
         fence_barrier_init();
     }
