@@ -24,7 +24,21 @@ namespace tc {
 
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint32_t* box);
 
-constexpr int kCpThreads = 192;
+constexpr int kCpThreads = 192;           // conv3 (stream kernel): TMA producer, MMA issuer, 4 epilogue warps
+constexpr int kCp2Threads = 224;          // conv2 (persistent kernel): + a warp that collects the barriers of a tile
+
+// Optional timeline of the MMA-issuing warp of CTA 0 (build with -DSIR_CONV_TRACE; tools/conv_trace.py reads it): clock64 per
+// tile after the ring / accumulator waits and, per horizontal tap, after the stage wait and after its MMAs + commit are issued.
+// Measured (conv2, 256 utterances): 2,880 cycles per tile = 3 x ~740 issuing (the thread is held at tcgen05.mma while the
+// pipe's short queue is full) + ~100 per barrier wait although the phases are complete + 240 for the next tile: 660 cycles
+// per tile with a draining tensor pipe.  Probing the next barriers between the first and the remaining MMAs of a batch
+// made it slower (0.102 ms instead of 0.089: the queue is too short to cover a second elect / sync region).
+#ifdef SIR_CONV_TRACE
+__device__ long long g_conv_trace[64][8];
+#define CONV_TRACE(T, E) do { if (blockIdx.x == 0 && (T) < 64u && lane == 0) g_conv_trace[T][E] = clock64(); } while (0)
+#else
+#define CONV_TRACE(T, E) do { } while (0)
+#endif
 
 template <int CIN, int COUT, int STAGES>
 struct CpLayout {
@@ -35,7 +49,7 @@ struct CpLayout {
     static constexpr int kStageBytes = 2 * kABytes;
     static constexpr int kOffA = kWBytes;
     static constexpr int kOffBar = kOffA + STAGES * kStageBytes;
-    static constexpr int kSmemBytes = kOffBar + (2 * STAGES + 5) * 8 + (int)sizeof(TileRing) + 16 + 1024;
+    static constexpr int kSmemBytes = kOffBar + (2 * STAGES + 5 + 2) * 8 + (int)sizeof(TileRing) + 32 + 1024;
     static_assert(kTapBytes % 1024 == 0 && kABytes % 1024 == 0, "operand tiles keep 1024-byte alignment");
     static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -49,7 +63,7 @@ struct CpParams {
 };
 
 template <int CIN, int COUT, int STAGES>
-__global__ void __launch_bounds__(kCpThreads, 1)
+__global__ void __launch_bounds__(kCp2Threads, 1)
     conv3x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                               const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                               const CpParams p) {
@@ -62,8 +76,10 @@ __global__ void __launch_bounds__(kCpThreads, 1)
     uint64_t* w_full = empty + STAGES;
     uint64_t* acc_full = w_full + 1;       // [2]
     uint64_t* acc_empty = acc_full + 2;    // [2]
-    TileRing* ring = reinterpret_cast<TileRing*>(acc_empty + 2);
+    uint64_t* go = acc_empty + 2;          // [2] "everything tile lt needs is there" (helper warp -> MMA warp)
+    TileRing* ring = reinterpret_cast<TileRing*>(go + 2);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring + 1);
+    volatile int* go_tile = reinterpret_cast<volatile int*>(tmem_slot + 2);      // [2] the tile behind go[lt & 1] (-1: none left)
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -79,8 +95,9 @@ __global__ void __launch_bounds__(kCpThreads, 1)
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
             mbar_init(&acc_empty[a], 4);           // one arrival per epilogue warp
+            mbar_init(&go[a], 1);
         }
-        ring_init(ring, 5);                            // MMA warp + 4 epilogue warps
+        ring_init(ring, 5);                            // helper warp + 4 epilogue warps
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<4 * COUT>(tmem_slot);     // 2 accumulators x [hi.hi + lo.hi | hi.lo]
@@ -123,18 +140,24 @@ __global__ void __launch_bounds__(kCpThreads, 1)
         mbar_wait(w_full, 0);
         tc_fence_after();
         const uint32_t sbase = smem_u32(smem);
-        uint32_t it = 0, lt = 0, rt = 0;
-        for (int tile = ring_next(ring, rt, lane); tile >= 0; tile = ring_next(ring, rt, lane), ++lt) {
+        // The issuing thread is held at a tcgen05.mma while the pipe's short queue is full, so whatever it does between two
+        // batches runs while the queue drains: with a wait per activation stage, the accumulator wait and the tile ring that
+        // was 660 of 2,880 cycles per tile (CONV_TRACE above).  Warp 6 now collects everything a tile needs and raises ONE
+        // barrier (go) per tile; this warp waits for it and issues the tile's 36 MMAs in one go.
+        uint32_t s = 0;
+        for (uint32_t lt = 0;; ++lt) {
             const uint32_t acc = lt & 1u;
-            mbar_wait(&acc_empty[acc], ((lt >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
-            tc_fence_after();
+            CONV_TRACE(lt, 0);
+            mbar_wait(&go[acc], (lt >> 1) & 1u);
+            if (go_tile[acc] < 0) break;
+            tc_fence_after();                                        // (the epilogue's reads of this accumulator are done)
+            CONV_TRACE(lt, 1);
             const uint32_t d_tmem = tmem_base + acc * 2 * COUT;
-            for (int kw = 0; kw < 3; ++kw, ++it) {
-                const int s = it % STAGES;
-                mbar_wait(&full[s], (it / STAGES) & 1u);
-                tc_fence_after();
-                const uint32_t a_base = sbase + L::kOffA + s * L::kStageBytes;
-                if (elect_one_sync()) {
+            if (elect_one_sync()) {
+                uint32_t sk = s;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const uint32_t a_base = sbase + L::kOffA + sk * L::kStageBytes;
 #pragma unroll
                     for (int kh = 0; kh < 3; ++kh) {
                         const uint32_t a_off = kh * 16 * L::kRowBytes;      // vertical tap = 16 rows further down the halo box
@@ -148,11 +171,40 @@ __global__ void __launch_bounds__(kCpThreads, 1)
                             umma_f16(d_tmem, desc_advance_k(a_lo, k), desc_advance_k(b_hi, k), idesc, 1u);
                         }
                     }
-                    umma_commit(&empty[s]);
-                    if (kw == 2) umma_commit(&acc_full[acc]);
+                    umma_commit(&empty[sk]);
+                    sk = sk + 1 == STAGES ? 0 : sk + 1;
                 }
-                __syncwarp();
+                umma_commit(&acc_full[acc]);
             }
+            __syncwarp();
+            CONV_TRACE(lt, 7);
+            s = (s + 3) % STAGES;
+        }
+    } else if (warp == 6) {
+        // ---- helper: per tile, wait for its three activation stages and for the accumulator, then raise go ------------------
+        uint32_t rt = 0, s = 0, sph = 0;
+        for (uint32_t lt = 0;; ++lt) {
+            const uint32_t acc = lt & 1u;
+            const int tile = ring_next(ring, rt, lane);
+            if (tile >= 0) {
+                for (int kw = 0; kw < 3; ++kw) {
+                    mbar_wait(&full[s], sph);
+                    if (++s == STAGES) {
+                        s = 0;
+                        sph ^= 1u;
+                    }
+                }
+            }
+            // the epilogue has drained this accumulator - which also says that the MMA warp has consumed go[acc] of tile lt - 2
+            // (waited for even behind the last tile: a second arrival on a barrier whose previous phase nobody has looked at
+            // yet would make that phase indistinguishable from the one before it)
+            mbar_wait(&acc_empty[acc], ((lt >> 1) & 1u) ^ 1u);
+            if (lane == 0) {
+                go_tile[acc] = tile;
+                mbar_arrive(&go[acc]);
+            }
+            __syncwarp();
+            if (tile < 0) break;
         }
     } else {
         // ---- epilogue warps: TMEM lane quadrant q; rows of the quadrant = pixel rows 2q, 2q+1 of the tile ----------
@@ -192,6 +244,13 @@ __global__ void __launch_bounds__(kCpThreads, 1)
     }
 }
 
+#ifdef SIR_CONV_TRACE
+extern "C" int sir_debug_conv_trace(long long* host, int count) {
+    if (count < 64 * 8) return -1;
+    return cudaMemcpyFromSymbol(host, g_conv_trace, sizeof(long long) * 64 * 8) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 // conv (3x3, s1, p1) + shift + ReLU + 2x2 max-pool, channels-last fp16 hi/lo in and out; weights [9][COUT][CIN].
 template <int CIN, int COUT>
 int tc_conv3x3_persistent(const __half* in_hi, const __half* in_lo, const __half* w_hi, const __half* w_lo, const float* shift,
@@ -224,7 +283,7 @@ int tc_conv3x3_persistent(const __half* in_hi, const __half* in_lo, const __half
     p.tickets = tickets ? tickets->first() : TileTickets{nullptr, 0};
     {
         ProfScope ps(name, st);
-        kern<<<grid, kCpThreads, L::kSmemBytes, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
+        kern<<<grid, kCp2Threads, L::kSmemBytes, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
     }
     SIR_CHECK_LAUNCH(name);
     if (tickets) tickets->consumed(p.num_tiles, grid);
