@@ -242,6 +242,12 @@ int sir_model_forward_head(sir_model* m, int batch_total, int n_frames, float* d
 int sir_gemm_nt_split_f16(const float* d_a, const float* d_w, const float* d_bias, float* d_c, int M, int N, int K,
                           void* stream);
 
+/* sir_gemm_tile_width: the activation-row tile width (UMMA N; one of 160, 176, 208, 256) the persistent kernel behind
+ * sir_gemm_nt_split_f16 uses for M rows and N output columns on a device of `sms` SMs: the width whose 128 x width
+ * tiles need the fewest rounds x width over the SMs.  Pure host arithmetic (no device call); exported so that the
+ * choice can be tested without a GPU.  Returns 0 when the shape takes the non-persistent kernel (< 32 tiles). */
+int sir_gemm_tile_width(int M, int N, int sms);
+
 /* sir_conv3x3_nhwc_split_f16: 3x3 convolution (stride 1, zero padding 1, no bias) of channels-last fp32 tensors,
  * d_in [B,H,W,C_in] * d_w [9 taps][C_out][C_in] -> d_out [B,H,W,C_out], as the implicit GEMM on tcgen05 behind
  * conv2 / conv3 (models/models.py:12-15) and behind their data gradients; (C_in, C_out) in

@@ -70,6 +70,7 @@ SIGNATURES = {
     "sir_adam_step_state": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int, c_float, c_float, c_float,
                                     c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "sir_gemm_nt_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "sir_gemm_tile_width": (c_int, [c_int, c_int, c_int]),
     "sir_conv3x3_nhwc_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sir_pipeline_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p]),
@@ -256,6 +257,11 @@ def gemm_nt_split_f16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> t
     check(load_library().sir_gemm_nt_split_f16(ptr(a), ptr(w), ptr(bias), ptr(c), M, N, K, stream_ptr()),
           "sir_gemm_nt_split_f16")
     return c
+
+
+def gemm_tile_width(M: int, N: int, sms: int = 148) -> int:
+    """Activation-row tile width the persistent GEMM picks for this shape (0: the shape takes the non-persistent kernel)."""
+    return int(load_library().sir_gemm_tile_width(M, N, sms))
 
 
 class Model:

@@ -293,19 +293,26 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
 // ---------------------------------------------------------------------------------------------------------------
 // Persistent GEMM for the GRU input projections C[M, N] = X[M, K] W[N, K]^T + bias (M = B*T rows, N = 1536,
 // K = 1024 / 512), computed TRANSPOSED: the weight rows are the UMMA M dimension (128 per tile), the activation rows
-// the UMMA N dimension in tiles of 176.  Why 176: with 6400 activation rows the usual 128 x 128 / 128 x 256 tilings
-// give 600 / 300 tiles = 4.05 / 2.03 waves on 148 SMs (measured: a third of the launch runs 4 % of the SMs), while
-// 12 x ceil(6400 / 176) = 444 tiles = exactly 3 waves.  One CTA per SM walks its tiles; two TMEM accumulators let the
-// epilogue of tile i (bias add, transposed fp32 store: 32 lanes = 32 consecutive output columns) overlap the MMAs of
-// tile i+1; barrier setup, TMEM allocation and pipeline fill are paid once per CTA.
+// the UMMA N dimension in tiles of BN, and BN is picked per shape so that the tiles fill whole waves of the 148 SMs:
+// with 6400 activation rows (256 utterances x 200 frames / 8: the bench's shape) the usual 128 x 128 / 128 x 256
+// tilings give 600 / 300 tiles = 4.05 / 2.03 waves (measured: a third of the launch runs 4 % of the SMs) while
+// 12 x ceil(6400 / 176) = 444 tiles are exactly 3; with 9472 rows (256 x 296 frames) BN = 176 would give 648 tiles =
+// 4.4 waves (5 rounds of 176 columns) and BN = 256 exactly 3 rounds of 256 (- 13 % tensor time).  gp_pick_bn()
+// minimises rounds x BN over the instantiated widths (the bench's shapes, 6400 and 12800 rows, both keep 176).
+// One CTA per SM walks its tiles; two TMEM accumulators let the epilogue of tile i (bias add, transposed fp32 store:
+// 32 lanes = 32 consecutive output columns) overlap the MMAs of tile i+1; barrier setup, TMEM allocation and pipeline
+// fill are paid once per CTA.
 // ---------------------------------------------------------------------------------------------------------------
+template <int BN>
 struct GpLayout {
-    static constexpr int kBK = 32, kStages = 5, kBN = 176;         // K-blocks of 32 = 64-byte swizzle rows
+    static constexpr int kBK = 32, kBN = BN;                       // K-blocks of 32 = 64-byte swizzle rows
     static constexpr int kABytes = 128 * kBK * 2;                  // weight tile, one of (hi, lo): 8 KB
-    static constexpr int kBBytes = kBN * kBK * 2;                  // activation tile: 11 KB
-    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // 38 KB
+    static constexpr int kBBytes = kBN * kBK * 2;                  // activation tile: 10 - 16 KB
+    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // 36 - 48 KB
+    static constexpr int kStages = 5 * kStageBytes <= 200 * 1024 ? 5 : 4;
     static constexpr int kOffBar = kStages * kStageBytes;
     static constexpr int kSmemBytes = kOffBar + (2 * kStages + 4) * 8 + (int)sizeof(TileRing) + 16 + 1024;
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M = 128; two accumulators of <= 256 columns");
     static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "operand tiles keep 1024-byte alignment");
     static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -320,11 +327,12 @@ struct GpParams {
     const float* out_scale;
 };
 
+template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
     gemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                            const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
                            const GpParams p) {
-    using L = GpLayout;
+    using L = GpLayout<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
@@ -464,10 +472,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
 }
 
-static int tc_gemm_nt_persistent(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo, const float* bias,
-                                 float* C, int M, int N, int K, cudaStream_t st, const char* name, TicketSource* tickets,
-                                 const GemmOutput* out) {
-    using L = GpLayout;
+template <int BN>
+static int gp_launch(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo, const float* bias, float* C,
+                     int M, int N, int K, cudaStream_t st, const char* name, TicketSource* tickets, const GemmOutput* out) {
+    using L = GpLayout<BN>;
     CUtensorMap tw_hi, tw_lo, tx_hi, tx_lo;
     const uint64_t xdims[2] = {(uint64_t)K, (uint64_t)M}, wdims[2] = {(uint64_t)K, (uint64_t)N};
     const uint32_t wbox[2] = {L::kBK, 128}, xbox[2] = {L::kBK, L::kBN};
@@ -487,24 +495,57 @@ static int tc_gemm_nt_persistent(const __half* a_hi, const __half* a_lo, const _
     p.C2 = out && out->C2 ? out->C2 : C;
     p.m_split = out && out->C2 ? out->m_split : M;
     p.out_scale = out ? out->out_scale : nullptr;
-    SIR_SMEM_OPTIN(gemm_persistent_kernel, L::kSmemBytes);
+    SIR_SMEM_OPTIN(gemm_persistent_kernel<BN>, L::kSmemBytes);
     const int num_sms = device_sm_count();
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     p.tickets = tickets ? tickets->first() : TileTickets{nullptr, 0};
     {
         ProfScope ps(name, st);
-        gemm_persistent_kernel<<<grid, kTcThreads, L::kSmemBytes, st>>>(tw_hi, tw_lo, tx_hi, tx_lo, p);
+        gemm_persistent_kernel<BN><<<grid, kTcThreads, L::kSmemBytes, st>>>(tw_hi, tw_lo, tx_hi, tx_lo, p);
     }
     SIR_CHECK_LAUNCH(name);
     if (tickets) tickets->consumed(p.num_tiles, grid);
     return SIR_OK;
 }
 
+// Activation-tile width for M activation rows and N / 128 weight tiles on `sms` SMs: the width whose tiles need the
+// least tensor time, rounds x BN (every round costs one tile of BN columns on the busiest SM); ties go to the wider tile
+// (fewer tiles, fewer re-reads of the weight rows).
+constexpr int kGpWidths[] = {160, 176, 208, 256};
+static int gp_pick_bn(int M, int tiles_w, int sms) {
+    int best = kGpWidths[0];
+    int64_t best_cost = INT64_MAX;
+    for (int bn : kGpWidths) {
+        const int64_t tiles = (int64_t)tiles_w * ((M + bn - 1) / bn);
+        const int64_t cost = ((tiles + sms - 1) / sms) * bn;
+        if (cost <= best_cost) {
+            best_cost = cost;
+            best = bn;
+        }
+    }
+    return best;
+}
+
+static bool gp_worthwhile(int M, int N) {   // enough tiles to be worth a persistent launch
+    return (int64_t)((M + 175) / 176) * (N / 128) >= 32;
+}
+
+static int tc_gemm_nt_persistent(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo, const float* bias,
+                                 float* C, int M, int N, int K, cudaStream_t st, const char* name, TicketSource* tickets,
+                                 const GemmOutput* out) {
+    switch (gp_pick_bn(M, N / 128, device_sm_count())) {
+        case 160: return gp_launch<160>(a_hi, a_lo, w_hi, w_lo, bias, C, M, N, K, st, name, tickets, out);
+        case 176: return gp_launch<176>(a_hi, a_lo, w_hi, w_lo, bias, C, M, N, K, st, name, tickets, out);
+        case 208: return gp_launch<208>(a_hi, a_lo, w_hi, w_lo, bias, C, M, N, K, st, name, tickets, out);
+        default: return gp_launch<256>(a_hi, a_lo, w_hi, w_lo, bias, C, M, N, K, st, name, tickets, out);
+    }
+}
+
 // C[M,N] = out_scale * A[M,K] W[N,K]^T + bias ; operands as fp16 hi/lo pairs.  N % 128 == 0, K % 64 == 0.
 int tc_gemm_nt(const __half* a_hi, const __half* a_lo, const __half* w_hi, const __half* w_lo, const float* bias,
                float* C, int M, int N, int K, cudaStream_t st, const char* name, TicketSource* tickets, const GemmOutput* out) {
     if (N % 128 || K % 64) return fail(SIR_ERR_INVALID, "tc_gemm_nt: N %% 128 and K %% 64 required (N %d, K %d)", N, K);
-    if ((int64_t)((M + 175) / 176) * (N / 128) >= 32)   // enough tiles to be worth a persistent launch
+    if (gp_worthwhile(M, N))
         return tc_gemm_nt_persistent(a_hi, a_lo, w_hi, w_lo, bias, C, M, N, K, st, name, tickets, out);
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     const uint64_t adims[2] = {(uint64_t)K, (uint64_t)M}, bdims[2] = {(uint64_t)K, (uint64_t)N};
@@ -588,6 +629,11 @@ int split_f16_async(const float* in, __half* hi, __half* lo, int64_t n, cudaStre
 
 // ---- C ABI: the split-precision tensor-core GEMM as a stand-alone operator --------------------------------------
 using namespace sir;
+
+extern "C" int sir_gemm_tile_width(int M, int N, int sms) {
+    if (M < 1 || N < 128 || N % 128 || sms < 1 || !sir::tc::gp_worthwhile(M, N)) return 0;
+    return sir::tc::gp_pick_bn(M, N / 128, sms);
+}
 
 extern "C" int sir_gemm_nt_split_f16(const float* d_a, const float* d_w, const float* d_bias, float* d_c, int M, int N,
                                      int K, void* stream) {

@@ -60,6 +60,19 @@ def test_no_cpu_fallback(lib):
     assert lib.sir_model_create(ctypes.byref(h), 31, 60) == -3
 
 
+def test_gemm_tile_width_fills_whole_waves(lib):
+    """The persistent GEMM's tile width per shape: least rounds x width over 148 SMs (the GRU projections: 12 weight tiles)."""
+    assert native.gemm_tile_width(6400, 1536) == 176        # 256 utt x 200 frames: 37 x 12 = 444 tiles = exactly 3 rounds
+    assert native.gemm_tile_width(9472, 1536) == 256        # 256 utt x 296 frames: 37 x 12 = 444 tiles again, 176 would need 5 rounds
+    assert native.gemm_tile_width(7690, 1536) == 208
+    assert native.gemm_tile_width(592, 1536) == 160         # training batch 16: one round either way, narrowest tile
+    assert native.gemm_tile_width(100, 1536) == 0           # too few tiles for the persistent kernel
+    for M in (353, 1000, 4100, 12345, 86016):
+        w = native.gemm_tile_width(M, 1536)
+        rounds = lambda bn: -(-12 * -(-M // bn) // 148) * bn
+        assert w in (160, 176, 208, 256) and rounds(w) == min(rounds(b) for b in (160, 176, 208, 256))
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "speech-intent-recognizer_b200")
     for dirpath, _, files in os.walk(pkg):

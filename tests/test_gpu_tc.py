@@ -9,7 +9,9 @@ native = importlib.import_module("speech-intent-recognizer_b200._native")
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 192), (6400, 1536, 1024), (275, 256, 512), (1, 128, 64),
-                                   (4100, 512, 128), (6400, 768, 256)])     # the last three take the persistent 128x256 kernel
+                                   (4100, 512, 128), (6400, 768, 256), (9472, 1536, 512), (7690, 1536, 128), (9465, 1536, 64)])
+# shapes with >= 32 tiles take the persistent kernel; its tile widths: 6400 x 1536 -> 176, 4100 x 512 and 6400 x 768 -> 160,
+# 9472 / 9465 (ragged last tile) x 1536 -> 256, 7690 x 1536 -> 208 (tests/test_abi_cpu.py checks the choice itself)
 def test_gemm_nt_split_f16_matches_fp64(M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + K)
     a = torch.randn(M, K, device="cuda", generator=g) * 3.0
