@@ -23,8 +23,10 @@ Utterances are independent, so N GPUs run N shards with no data-path collective 
  e2e    : the same metric through the public Python API from HOST buffers holding 16-bit PCM - what a WAV file holds and
           what the reference's loader starts from (scripts/precompute_features.py:47) - H2D copy + pipeline + D2H of the
           result inside the timed region, every step.  `e2e_fp32` is the same loop from fp32 host buffers.
- roofline / frontend_roofline / rooflines / stages : per-kernel device times from a separate K-step pass with CUDA events
-          around each stage on the launching stream (sir_profile_*), algorithmic flops / bytes per DESIGN.md section 4.
+ roofline / frontend_roofline / slowest_stage_roofline / rooflines / stages : per-kernel device times from a separate K-step
+          pass with CUDA events around each stage on the launching stream (sir_profile_*), algorithmic flops / bytes per
+          DESIGN.md section 4.  `roofline` is the frontend's (the kernel BASELINE.json's metric names, HBM-bound);
+          `slowest_stage_roofline` the slowest single stage's (the GRU recurrence: a latency chain), `rooflines` all of them.
  cpu_baseline : the reference's CPU path on this box's host cores (rank 0, N = 1 only): the reference's own classes from
           baseline/_ref when build() could copy them ("reference"), else oracle/torch_port.py ("port").
 """
@@ -845,8 +847,13 @@ def run_inference(ctx, out):
         fe_bytes = 4 * min(L, int(max_duration * 16000) if max_duration else L) + 4 * n_mels * OUT_FRAMES
         stage_out, rooflines = stage_rooflines(ctx, stages, args.steps, B, n_mels, fe_bytes,
                                                args.workload == "config2" and B == 256)
-        roofline = max(rooflines, key=lambda r: r["ms"]) if rooflines else None
+        slowest = max(rooflines, key=lambda r: r["ms"]) if rooflines else None
         fr = next((r for r in rooflines if r["kernel"] == "logmel_frontend_kernel"), None)
+        # `roofline` is the frontend's: BASELINE.json's metric names it ("frontend HBM GB/s vs peak") and it is the one
+        # HBM-bound kernel of the step.  The slowest single stage is reported beside it, every stage in `rooflines`.
+        roofline = dict(fr, choice="the kernel BASELINE.json's metric names (frontend HBM GB/s vs peak); the slowest "
+                                   f"single stage is {slowest['kernel']} ({slowest['ms']} ms), see slowest_stage_roofline "
+                                   "and rooflines") if fr else slowest
 
         def copy_bound(ms, nbytes):
             return {"h2d_gbs_per_gpu": round(nbytes / (ms * 1e-3) / 1e9, 2), "utt_s": round(B * world / (ms * 1e-3)),
@@ -880,7 +887,8 @@ def run_inference(ctx, out):
                          "warm_runs": e2e_f32_warm,
                          "ms_per_step_of_each_repeat": [round(t * 1e3 / args.steps, 4) for t in e2e_f32_times],
                          "h2d_copy_bound": copy_bound(h2d_f32_ms, B * L * 4)},
-            "roofline": roofline, "frontend_roofline": fr, "rooflines": rooflines, "stages": stage_out,
+            "roofline": roofline, "frontend_roofline": fr, "slowest_stage_roofline": slowest, "rooflines": rooflines,
+            "stages": stage_out,
         }
         if train_obj is not None:
             line["train"] = train_obj
