@@ -321,26 +321,37 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_pool_tc_kernel(const floa
     const int d_img = stride / tiles_img, d_r = stride - d_img * tiles_img, d_ty = d_r / tiles_x, d_tx = d_r - d_ty * tiles_x;
     int tile = blockIdx.x * kC1Wgs + g;
     int img = tile / tiles_img, ty = (tile - img * tiles_img) / tiles_x, tx = (tile - img * tiles_img) - ty * tiles_x;
+    // the 4 x 4 input patch behind pooled pixel (Y2, X2) of image `img` (rows 2 Y2 - 1 .., columns 2 X2 - 1 ..), zero outside
+    auto load_patch = [&](int img_, int ty_, int tx_, float (&v)[16]) {
+        const int Y2 = ty_ * PH + py, X2 = tx_ * PW + px;
+        const bool in_img = Y2 < H2 && X2 < W2;
+        const float* __restrict__ src = feat + (int64_t)img_ * H * W;
+        const int r0 = 2 * Y2 - 1, c0 = 2 * X2 - 1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = r0 + i;
+            const bool rv = in_img && r >= 0 && r < H;
+            const float* __restrict__ rowp = src + (int64_t)(rv ? r : 0) * W + (rv ? c0 : 0);
+            v[4 * i + 0] = rv && c0 >= 0 ? __ldg(rowp) : 0.f;
+            v[4 * i + 1] = rv ? __ldg(rowp + 1) : 0.f;
+            v[4 * i + 2] = rv ? __ldg(rowp + 2) : 0.f;
+            v[4 * i + 3] = rv && c0 + 3 < W ? __ldg(rowp + 3) : 0.f;
+        }
+    };
+    float patch[16];
+    if (tile < num_tiles) load_patch(img, ty, tx, patch);
     uint32_t it = 0;
     for (; tile < num_tiles; tile += stride, ++it) {
         const int Y2 = ty * PH + py, X2 = tx * PW + px;
         const bool inside = Y2 < H2 && X2 < W2;
-        // ---- build: the 4 x 4 input patch (rows 2 Y2 - 1 .., columns 2 X2 - 1 ..), zero outside the image ---------------
+        const int64_t pix = ((int64_t)img * H2 + Y2) * W2 + X2;
+        // ---- build: split the patch once, four operand rows -----------------------------------------------------------
         {
-            const float* __restrict__ src = feat + (int64_t)img * H * W;
-            const int r0 = 2 * Y2 - 1, c0 = 2 * X2 - 1;
             uint32_t h[4][2], l[4][2];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int r = r0 + i;
-                const bool rv = inside && r >= 0 && r < H;
-                const float* __restrict__ rowp = src + (int64_t)(rv ? r : 0) * W + (rv ? c0 : 0);
-                const float v0 = rv && c0 >= 0 ? __ldg(rowp) : 0.f;
-                const float v1 = rv ? __ldg(rowp + 1) : 0.f;
-                const float v2 = rv ? __ldg(rowp + 2) : 0.f;
-                const float v3 = rv && c0 + 3 < W ? __ldg(rowp + 3) : 0.f;
-                c1_split_pair_sat(v0, v1, h[i][0], l[i][0]);
-                c1_split_pair_sat(v2, v3, h[i][1], l[i][1]);
+                c1_split_pair_sat(patch[4 * i], patch[4 * i + 1], h[i][0], l[i][0]);
+                c1_split_pair_sat(patch[4 * i + 2], patch[4 * i + 3], h[i][1], l[i][1]);
             }
             c1_store_member<0, 0>(row_addr, sw, h, l);
             c1_store_member<0, 1>(row_addr, sw, h, l);
@@ -364,11 +375,23 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_pool_tc_kernel(const floa
             }
             __syncwarp();
         }
+        // the next tile's patch is loaded while this tile's MMAs run and its epilogue waits for tensor memory
+        tx += d_tx;
+        if (tx >= tiles_x) {
+            tx -= tiles_x;
+            ++ty;
+        }
+        ty += d_ty;
+        if (ty >= tiles_y) {
+            ty -= tiles_y;
+            ++img;
+        }
+        img += d_img;
+        if (tile + stride < num_tiles) load_patch(img, ty, tx, patch);
         c1_mma_wait(bar, it & 1u);
         tc_fence_after();
         // ---- epilogue: max over the four members (column groups), + shift, ReLU, (hi, lo), 16 channels at a time --------
         {
-            const int64_t pix = ((int64_t)img * H2 + Y2) * W2 + X2;
 #pragma unroll
             for (int cc = 0; cc < 32; cc += 16) {
                 float v0[16], v1[16], v2[16], v3[16];
@@ -391,17 +414,6 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_pool_tc_kernel(const floa
                 }
             }
         }
-        tx += d_tx;
-        if (tx >= tiles_x) {
-            tx -= tiles_x;
-            ++ty;
-        }
-        ty += d_ty;
-        if (ty >= tiles_y) {
-            ty -= tiles_y;
-            ++img;
-        }
-        img += d_img;
     }
     tc_fence_before();
     __syncthreads();

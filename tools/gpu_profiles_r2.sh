@@ -8,7 +8,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 echo "launch list rc=$?"
 timeout 120 python tools/c1prof.py > /dev/null 2>&1
 $CMD > /dev/null 2>&1 && \
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"logmel_frontend_tc|frontend_finish|conv1_tc|conv3x3_persistent|conv3x3_stream|gemm_persistent|gru_layer_pp" --launch-skip 30 -c 10 \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"logmel_frontend_tc|frontend_finish|conv1_|conv3x3_persistent|conv3x3_stream|gemm_persistent|gru_layer_pp" --launch-skip 30 -c 10 \
     -o $OUT/${TAG}_full -f $CMD > $OUT/${TAG}_ncu_full.log 2>&1
 echo "full rc=$?"
 ncu -i $OUT/${TAG}_full.ncu-rep --page raw --csv > $OUT/${TAG}_full_raw.csv 2>/dev/null
