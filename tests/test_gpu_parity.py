@@ -151,6 +151,21 @@ def test_classifier_matches_golden(model):
     assert np.max(np.abs(yv - g["logits_var"])) < LOGIT_ABS_TOL
 
 
+@pytest.mark.parametrize("B,T", [(1, 16), (3, 24), (5, 72), (2, 48), (33, 136), (7, 88), (150, 56)])
+def test_classifier_shapes_against_oracle(model, B, T):
+    """Frame counts and batch sizes around the kernels' tile shapes: conv1's pooled patches (16 x 8 pooled pixels: T / 2 on and
+    off multiples of 8), conv2 / conv3 tiles with ragged edges, GRU slices of 16 and of 64 utterances, 2 to 17 time steps."""
+    rng = np.random.default_rng(100 * B + T)
+    x = rng.standard_normal((B, 64, T)).astype(np.float32)
+    x[:, :, T - T // 4:] = 0.0                                          # a padded tail, as the dataset pads
+    got = model.forward(dev(x)).cpu().numpy()
+    n = min(B, 6)                                                       # the numpy oracle on a few rows, first and last
+    rows = np.r_[0:n // 2 + n % 2, B - n // 2:B]
+    want = classifier_np.forward(x[rows], synth.make_weights(1234))
+    assert np.max(np.abs(got[rows] - want)) < LOGIT_ABS_TOL
+    assert np.isfinite(got).all()
+
+
 def test_pipeline_matches_oracle_and_argmax(fe, model):
     """waveform -> logits: config-2 shape at a size the oracle finishes in seconds."""
     B = 24
