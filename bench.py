@@ -798,12 +798,18 @@ def run_inference(ctx, out):
     def e2e_loop(n, src):
         """n steps, each with its own H2D copy and D2H read; up to `depth` batches in flight, all drained before return."""
         pending, res = [], None
+        t_submit = t_wait = 0.0
         for _ in range(n):
+            t0 = time.perf_counter()
             pending.append(pipe.submit(src))
+            t1 = time.perf_counter()
             if len(pending) == args.depth:
                 res = pipe.collect(pending.pop(0))
+            t_submit += t1 - t0
+            t_wait += time.perf_counter() - t1
         while pending:
             res = pipe.collect(pending.pop(0))
+        last["host_ms"] = (round(t_submit * 1e3 / n, 4), round(t_wait * 1e3 / n, 4))
         return res
 
     last = {}
@@ -822,6 +828,7 @@ def run_inference(ctx, out):
 
     e2e_s, e2e_times, e2e_warm = stable_repeats(lambda: e2e_run(host_pcm, True), args.e2e_repeats, agree=ctx.reduce_max)
     pcm_logits = last["logits"].clone()
+    e2e_host_ms = last["host_ms"]
     clocks = ctx.sampler.stop()
     e2e_f32_s, e2e_f32_times, e2e_f32_warm = stable_repeats(lambda: e2e_run(host, False), args.e2e_repeats, agree=ctx.reduce_max)
     # the same kernels on the same bytes give the same result as the device-resident path
@@ -881,6 +888,10 @@ def run_inference(ctx, out):
                                                               "consecutive runs agree within 3 %",
                     "warm_runs": e2e_warm, "ms_per_step_of_each_repeat": [round(t * 1e3 / args.steps, 4) for t in e2e_times],
                     "fraction_of_value": round((total_utts / e2e_s) / (total_utts / (dev_ms * 1e-3)), 4),
+                    "host_ms_per_step": {"enqueue": e2e_host_ms[0], "waiting_in_collect": e2e_host_ms[1],
+                                         "note": "rank 0, last repeat: CPU time inside submit() (enqueueing copies and "
+                                                 "launches) and time blocked in collect(); enqueue close to the step time "
+                                                 "means the host thread, not the GPU or the copy, bounds this number"},
                     "h2d_copy_bound": copy_bound(h2d_pcm_ms, B * L * 2)},
             "e2e_fp32": {"value": total_utts / e2e_f32_s, "unit": "utt/s", "h2d_bytes_per_step": B * L * 4,
                          "d2h_bytes_per_step": B * NUM_CLASSES * 4, "api": "the same submit/collect loop with fp32 host buffers",

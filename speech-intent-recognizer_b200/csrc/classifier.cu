@@ -135,11 +135,19 @@ __global__ void __launch_bounds__(256) attention_fc_kernel(const float* __restri
     {                                                       // context = sum_t w_t y_t: 2 features per thread
         const float2* __restrict__ yb2 = reinterpret_cast<const float2*>(yb4);
         float2 c = make_float2(0.f, 0.f);
-        for (int t = 0; t < T; ++t) {
-            const float2 v = yb2[t * 256 + tid];
-            const float w = score[t];
-            c.x = fmaf(v.x, w, c.x);
-            c.y = fmaf(v.y, w, c.y);
+        constexpr int kU = 5;                               // loads of five time steps in flight; the sum keeps the order of t
+        for (int t0 = 0; t0 < T; t0 += kU) {
+            float2 v[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) v[u] = t0 + u < T ? yb2[(t0 + u) * 256 + tid] : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (t0 + u < T) {
+                    const float w = score[t0 + u];
+                    c.x = fmaf(v[u].x, w, c.x);
+                    c.y = fmaf(v[u].y, w, c.y);
+                }
+            }
         }
         reinterpret_cast<float2*>(ctx)[tid] = c;
     }

@@ -14,6 +14,8 @@ the data-parallel trainer (scripts/train.py) all-reduces that buffer with a sing
 """
 from __future__ import annotations
 
+import itertools
+
 import torch
 import torch.nn as nn
 
@@ -158,7 +160,10 @@ class CNNAudioGRU(nn.Module):
         return torch.cat(parts).contiguous()
 
     def _versions(self):
-        return tuple((t.data_ptr(), t._version) for t in self.state_dict().values())
+        # (address, in-place version) of every parameter and buffer: changes when a tensor is written in place or replaced.
+        # Walks the module tree itself - state_dict() builds a detached copy of every entry and cost a third of the host
+        # time of IntentPipeline.submit.
+        return tuple((t.data_ptr(), t._version) for t in itertools.chain(self.parameters(), self.buffers()))
 
     def _ensure_native(self):
         if self._native_model is None:

@@ -61,6 +61,7 @@ class _Slot:
         self.waves = {}                          # (B, L, dtype) -> device staging buffer, kept across dtype changes
         self.d_wave = self.feats = self.logits = self.host_logits = None
         self.done = torch.cuda.Event()
+        self.copied = []                         # one event per sub-batch copy, reused from step to step
         self.busy = False
         self.stream = torch.cuda.Stream()        # every slot computes on its own stream (own workspace in the handle)
 
@@ -128,14 +129,17 @@ class IntentPipeline:
         staged = B <= _native.Model.MAX_STAGED_BATCH
         n_sub = max(1, min(self.sub_batches, B)) if staged else 1
         bounds = [(i * B) // n_sub for i in range(n_sub + 1)]
-        events = []
+        while len(slot.copied) < n_sub:
+            slot.copied.append(torch.cuda.Event())
+        events = slot.copied
         with torch.cuda.stream(copy):
             for i in range(n_sub):
                 a, b = bounds[i], bounds[i + 1]
-                slot.d_wave[a:b].copy_(waves[a:b], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy)
-                events.append(ev)
+                if n_sub == 1:
+                    slot.d_wave.copy_(waves, non_blocking=True)
+                else:
+                    slot.d_wave[a:b].copy_(waves[a:b], non_blocking=True)
+                events[i].record(copy)
         with torch.cuda.stream(compute):
             for i in range(n_sub):
                 a, b = bounds[i], bounds[i + 1]

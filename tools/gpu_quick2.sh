@@ -7,5 +7,5 @@ timeout 600 python bench.py --no-cpu-baseline > $OUT/${TAG}_bench.json 2> $OUT/$
 python - <<PY
 import json
 d=json.loads(open('gpurun_out/${TAG}_bench.json').read().strip().splitlines()[-1])
-print(round(d['value']), round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value']), {k:round(v['ms_per_step'],4) for k,v in d.get('stages',{}).items()})
+print(round(d["value"]), round(d["ms_per_step"],4), "e2e", round(d["e2e"]["value"]), d["e2e"].get("host_ms_per_step",{}).get("enqueue"), {k:round(v['ms_per_step'],4) for k,v in d.get('stages',{}).items()})
 PY
