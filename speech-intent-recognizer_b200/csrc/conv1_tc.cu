@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kC1Threads, 2) conv1_tc_kernel(const float* __
 // into four operand matrices (member (dy, dx) = matrix 2 dy + dx, 128 rows x 64 B, SWIZZLE_64B).  Four groups of
 // three N = 32 MMAs put the members' results into four column groups of the SAME tensor-memory lane, so the pool is
 // three max instructions per channel in registers, and the thread finishes its pixel alone: + shift, ReLU, (hi, lo)
-// split, two 32-byte stores per 16 channels.  ~115 instructions per input pixel instead of ~240.
+// split, two 32-byte stores per 16 channels.  16.2 M warp instructions per 256-utterance launch instead of 42 M.
 // A warpgroup works on a patch of (128 / PW) x PW pooled pixels; 4 warpgroups x 128 accumulator columns fill tensor
 // memory, so one CTA per SM.
 // ---------------------------------------------------------------------------------------------------------------
