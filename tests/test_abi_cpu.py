@@ -143,3 +143,27 @@ def test_host_binding_helper_is_optional():
         assert os.sched_getaffinity(0) == before
     else:
         os.sched_setaffinity(0, before)
+
+
+def test_weight_version_token_sees_every_kind_of_change():
+    """CNNAudioGRU re-uploads its weights to the native handle when `_versions()` changes: in-place writes (optimizer steps,
+    load_state_dict), buffer updates (BatchNorm statistics) and replaced parameter objects must all change it; reading must not."""
+    models = importlib.import_module("speech-intent-recognizer_b200.models.models")
+    m = models.CNNAudioGRU(31)
+    v0 = m._versions()
+    assert m._versions() == v0 and len(v0) == len(list(m.parameters())) + len(list(m.buffers()))
+    _ = m.state_dict()                                                   # reading does not change the token
+    assert m._versions() == v0
+    with torch.no_grad():
+        m.fc.bias.add_(1.0)                                              # in-place write to a parameter
+    v1 = m._versions()
+    assert v1 != v0
+    m.bn2.running_mean.mul_(0.5)                                         # in-place write to a buffer
+    v2 = m._versions()
+    assert v2 != v1
+    m.load_state_dict(m.state_dict())                                    # copy_ into every entry
+    v3 = m._versions()
+    assert v3 != v2
+    m.conv1.weight = torch.nn.Parameter(m.conv1.weight.detach().clone())  # a replaced parameter object
+    assert m._versions() != v3
+
